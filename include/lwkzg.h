@@ -1,0 +1,208 @@
+/*
+ * lwkzg.h -- C ABI of liblwkzg_b200.so, the B200-native (sm_100a CUDA) drop-in
+ * for the EIP-4844 hot path of lambdaclass/lambdaworks_kzg.
+ *
+ * Part 1 is the c-kzg-4844 compatible boundary.  Every prototype and struct
+ * layout is exactly what the reference exports from src/lib.rs (#[no_mangle]
+ * extern "C") / declares in src/c_kzg_4844.h; the reference line each item
+ * replaces is cited.  Part 2 is additive: batch / device-pointer entry points
+ * (the c-kzg ABI is one blob per call) and a few utility calls used by the
+ * benchmark and the tests.
+ *
+ * No torch / CUDA types appear in any signature: device buffers are passed as
+ * plain `void *` device addresses and streams as `void *` (a cudaStream_t).
+ *
+ * There is NO CPU compute path behind these symbols: without a usable CUDA
+ * device every compute call returns C_KZG_ERROR.
+ */
+#ifndef LWKZG_H
+#define LWKZG_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ Part 1 */
+
+/* reference: src/lib.rs:64-92, src/c_kzg_4844.h:38-60 */
+#define BYTES_PER_COMMITMENT 48
+#define BYTES_PER_PROOF 48
+#define BYTES_PER_FIELD_ELEMENT 32
+#define FIELD_ELEMENTS_PER_BLOB 4096
+#define BYTES_PER_BLOB (FIELD_ELEMENTS_PER_BLOB * BYTES_PER_FIELD_ELEMENT)
+#define TRUSTED_SETUP_NUM_G1_POINTS 4096
+#define TRUSTED_SETUP_NUM_G2_POINTS 65
+
+/* reference: src/lib.rs:94-98, src/c_kzg_4844.h:85-112 */
+typedef struct { uint8_t bytes[32]; } Bytes32;
+typedef struct { uint8_t bytes[48]; } Bytes48;
+typedef struct { uint8_t bytes[BYTES_PER_BLOB]; } Blob;
+typedef Bytes48 KZGCommitment;
+typedef Bytes48 KZGProof;
+
+/* reference: src/lib.rs:45-57, src/c_kzg_4844.h:125-130 */
+typedef enum {
+    C_KZG_OK = 0,  /* Success */
+    C_KZG_BADARGS, /* The supplied data is invalid in some way */
+    C_KZG_ERROR,   /* Internal error / any failure in MODE_REFERENCE */
+    C_KZG_MALLOC,  /* Could not allocate memory */
+} C_KZG_RET;
+
+/* blst-shaped value types.  reference: src/lib.rs:100-166 (#[repr(C)]).
+ * NB: the *values* stored by the reference (and by this library) are canonical
+ * (non-Montgomery) integers with limbs most-significant first, affine with
+ * z = 1 -- src/srs.rs:131-213 -- i.e. shape- but not value-compatible with blst. */
+typedef uint64_t limb_t;
+typedef struct { limb_t l[4]; } blst_fr;
+typedef struct { limb_t l[6]; } blst_fp;
+typedef struct { blst_fp fp[2]; } blst_fp2;
+typedef struct { blst_fp x, y, z; } blst_p1;
+typedef struct { blst_fp x, y; } blst_p1_affine;
+typedef struct { blst_fp2 x, y, z; } blst_p2;
+typedef struct { blst_fp2 x, y; } blst_p2_affine;
+typedef blst_p1 g1_t;
+typedef blst_p2 g2_t;
+typedef blst_fr fr_t;
+
+/* reference: src/lib.rs:173-197, src/c_kzg_4844.h:141-156 (never populated by
+ * the reference: KZGSettings.fs is always NULL, src/lib.rs:754-758). */
+typedef struct {
+    uint64_t max_width;
+    fr_t *expanded_roots_of_unity;
+    fr_t *reverse_roots_of_unity;
+    fr_t *roots_of_unity;
+} FFTSettings;
+
+/* reference: src/lib.rs:210-222, src/c_kzg_4844.h:161-170.
+ * g1_values: 4096 x blst_p1, g2_values: 65 x blst_p2, both malloc()ed by the
+ * loaders and released by free_trusted_setup.  When THIS library's loaders
+ * build the struct, `fs` points at a library-owned object whose first bytes are
+ * a zeroed FFTSettings followed by the device context (SRS and fixed-base
+ * tables resident in HBM).  Settings assembled by hand with fs == NULL (as the
+ * reference's own loaders produce) are accepted too: a device context is then
+ * created on first use and cached, keyed by the pointers and a content hash. */
+typedef struct {
+    FFTSettings *fs;
+    g1_t *g1_values;
+    g2_t *g2_values;
+} KZGSettings;
+
+/* reference: src/lib.rs:709-715 (BADARGS unless n1 == 4096 && n2 == 65) */
+C_KZG_RET load_trusted_setup(KZGSettings *out, const uint8_t *g1_bytes, size_t n1,
+                             const uint8_t *g2_bytes, size_t n2);
+/* reference: src/lib.rs:779-802 + src/srs.rs:25-128 (line-based text format) */
+C_KZG_RET load_trusted_setup_file(KZGSettings *out, FILE *in);
+/* reference: src/lib.rs:821-829 (returns a code; c-kzg declares void) */
+C_KZG_RET free_trusted_setup(KZGSettings *s);
+
+/* reference: src/lib.rs:253-283 */
+C_KZG_RET blob_to_kzg_commitment(KZGCommitment *out, const Blob *blob, const KZGSettings *s);
+/* reference: src/lib.rs:300-344 */
+C_KZG_RET compute_kzg_proof(KZGProof *proof_out, Bytes32 *y_out, const Blob *blob,
+                            const Bytes32 *z_bytes, const KZGSettings *s);
+/* reference: src/lib.rs:361-404 */
+C_KZG_RET compute_blob_kzg_proof(KZGProof *out, const Blob *blob, const Bytes48 *commitment_bytes,
+                                 const KZGSettings *s);
+/* reference: src/lib.rs:407-453 */
+C_KZG_RET verify_kzg_proof(bool *ok, const Bytes48 *commitment_bytes, const Bytes32 *z_bytes,
+                           const Bytes32 *y_bytes, const Bytes48 *proof_bytes, const KZGSettings *s);
+/* reference: src/lib.rs:456-505 */
+C_KZG_RET verify_blob_kzg_proof(bool *ok, const Blob *blob, const Bytes48 *commitment_bytes,
+                                const Bytes48 *proof_bytes, const KZGSettings *s);
+/* reference: src/lib.rs:525-614 (n == 0 -> *ok = false, C_KZG_OK; n == 1 -> single path) */
+C_KZG_RET verify_blob_kzg_proof_batch(bool *ok, const Blob *blobs, const Bytes48 *commitments_bytes,
+                                      const Bytes48 *proofs_bytes, size_t n, const KZGSettings *s);
+
+/* ------------------------------------------------------------------ Part 2 */
+/* Additive batch API.  `status` (may be NULL) receives one C_KZG_RET per item
+ * so a bad item does not poison the batch; the function's return value is
+ * C_KZG_OK iff the call itself ran (per-item failures are only in `status`,
+ * or -- when status == NULL -- the first failing item's code is returned).
+ * Results are bit-identical to n calls of the matching Part-1 function. */
+
+/* host buffers */
+C_KZG_RET lwkzg_blob_to_kzg_commitment_batch(KZGCommitment *out, const Blob *blobs, size_t n,
+                                             const KZGSettings *s, int *status);
+C_KZG_RET lwkzg_compute_blob_kzg_proof_batch(KZGProof *out, const Blob *blobs,
+                                             const Bytes48 *commitments, size_t n,
+                                             const KZGSettings *s, int *status);
+C_KZG_RET lwkzg_compute_kzg_proof_batch(KZGProof *proofs, Bytes32 *ys, const Blob *blobs,
+                                        const Bytes32 *zs, size_t n, const KZGSettings *s,
+                                        int *status);
+/* commitment = blob_to_kzg_commitment(blob); proof = compute_blob_kzg_proof(blob, commitment) */
+C_KZG_RET lwkzg_commit_and_prove_batch(KZGCommitment *commitments, KZGProof *proofs,
+                                       const Blob *blobs, size_t n, const KZGSettings *s,
+                                       int *status);
+
+/* device buffers (plain device addresses on the context's GPU), asynchronous on
+ * `stream` (a cudaStream_t, NULL = default stream).  d_status: n ints on the
+ * device or NULL. */
+C_KZG_RET lwkzg_commit_and_prove_batch_device(void *d_commitments, void *d_proofs,
+                                              const void *d_blobs, size_t n,
+                                              const KZGSettings *s, void *stream, void *d_status);
+C_KZG_RET lwkzg_blob_to_kzg_commitment_batch_device(void *d_commitments, const void *d_blobs,
+                                                    size_t n, const KZGSettings *s, void *stream);
+C_KZG_RET lwkzg_compute_blob_kzg_proof_batch_device(void *d_proofs, const void *d_blobs,
+                                                    const void *d_commitments, size_t n,
+                                                    const KZGSettings *s, void *stream,
+                                                    void *d_status);
+
+/* Generic G1 multi-scalar multiplication (the reference's g1_lincomb,
+ * src/lib.rs:241-243): out = sum scalars[i] * points[i].  points: n x 96 bytes
+ * canonical big-endian affine x||y (all-zero = infinity); scalars: n x 32 bytes
+ * big-endian, reduced mod r; out: 48-byte compressed. Host buffers. */
+C_KZG_RET lwkzg_g1_lincomb(Bytes48 *out, const uint8_t *points_xy_be, const uint8_t *scalars_be,
+                           size_t n);
+
+/* Multi-GPU batched verification building blocks (one process per GPU; the
+ * caller all-gathers the tiny outputs, e.g. with NCCL):
+ *   phase 1: per local blob i -> tuple_i = compress(C_i) || z_i || y_i || compress(pi_i)
+ *            (160 bytes, the exact bytes hashed by src/utils.rs:166-206); any
+ *            invalid item sets status and the call returns C_KZG_ERROR.
+ *   phase 2: given ALL n_total tuples (gathered in rank order) and this rank's
+ *            range [first, first+n_local), writes the rank's partial sums
+ *            (3 points x 96 bytes canonical affine: sum r^i pi_i,
+ *            sum r^i z_i pi_i, sum r^i (C_i - y_i G)).
+ *   phase 3: given all ranks' partial sums, runs the 2-pairing check. */
+C_KZG_RET lwkzg_verify_batch_phase1(uint8_t *tuples160, const Blob *blobs,
+                                    const Bytes48 *commitments, const Bytes48 *proofs,
+                                    size_t n_local, const KZGSettings *s);
+C_KZG_RET lwkzg_verify_batch_phase2(uint8_t *partial288, const uint8_t *all_tuples160,
+                                    size_t n_total, size_t first, size_t n_local,
+                                    const KZGSettings *s);
+C_KZG_RET lwkzg_verify_batch_phase3(bool *ok, const uint8_t *partials288, size_t n_ranks,
+                                    const KZGSettings *s);
+
+/* Synthetic blobs: word i of blob k = four big-endian u64 from
+ * SplitMix64 seeded with 0xB2004844 ^ (k*4096+i), byte[0] &= 0x3f.  Written
+ * straight into device memory so large batches never cross PCIe. */
+C_KZG_RET lwkzg_synth_blobs_device(void *d_blobs, uint64_t first_blob, size_t n, void *stream);
+/* same generator on the host (tests / CPU baseline feed) */
+void lwkzg_synth_blob_host(uint8_t *blob, uint64_t k);
+
+/* Integer-pipe peak probe: runs a dependency-free IMAD micro-kernel on the
+ * current device and returns MAC32/s (32x32+64 multiply-accumulates per
+ * second) for variant 0 = mad.lo.cc/madc.hi.cc pairs, 1 = mad.wide.u32. */
+double lwkzg_imad_peak(int variant);
+
+/* Options: "window_bits" (fixed-base table window c, 4..15; default 13; must
+ * be set before the settings are first used), "msm_blocks_per_blob" (0 = auto),
+ * "chunk_blobs" (host-batch pipeline chunk, default 256).  Returns 0 on success. */
+int lwkzg_set_option(const char *name, long value);
+long lwkzg_get_option(const char *name);
+
+/* kernels launched by this library since load (the bench's gpu_launches) */
+uint64_t lwkzg_kernel_launches(void);
+/* human-readable description of the last error on this thread ("" if none) */
+const char *lwkzg_last_error(void);
+const char *lwkzg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWKZG_H */

@@ -1,0 +1,161 @@
+// Fp2 = Fp[u]/(u^2 + 1) and the G2 (twist, y^2 = x^3 + 4(1+u)) point decoder.
+// Replaces lambdaworks-math's Degree2ExtensionField / BLS12381TwistCurve as
+// used by /root/reference/src/compression.rs:105-139 and src/srs.rs:175-247.
+// Cold code (setup + the two fixed G2 points of the pairing check): all Fp
+// products go through the out-of-line fp_mul_ni to keep code size down.
+#pragma once
+#include "field.cuh"
+
+namespace lw {
+
+struct Fp2 {
+  Fp c0, c1;
+};
+
+LW_INL Fp2 fp2_zero() { Fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
+LW_INL Fp2 fp2_one() { Fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
+LW_INL bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+LW_INL bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+LW_INL Fp2 fp2_add(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = fp_add(a.c0, b.c0); r.c1 = fp_add(a.c1, b.c1); return r; }
+LW_INL Fp2 fp2_sub(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = fp_sub(a.c0, b.c0); r.c1 = fp_sub(a.c1, b.c1); return r; }
+LW_INL Fp2 fp2_neg(const Fp2& a) { Fp2 r; r.c0 = fp_neg(a.c0); r.c1 = fp_neg(a.c1); return r; }
+LW_INL Fp2 fp2_dbl(const Fp2& a) { Fp2 r; r.c0 = fp_dbl(a.c0); r.c1 = fp_dbl(a.c1); return r; }
+LW_INL Fp2 fp2_conj(const Fp2& a) { Fp2 r; r.c0 = a.c0; r.c1 = fp_neg(a.c1); return r; }
+
+// (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u
+LW_DEV inline Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+  Fp t0, t1, t2;
+  fp_mul_ni(t0, a.c0, b.c0);
+  fp_mul_ni(t1, a.c1, b.c1);
+  Fp sa = fp_add(a.c0, a.c1), sb = fp_add(b.c0, b.c1);
+  fp_mul_ni(t2, sa, sb);
+  Fp2 r;
+  r.c0 = fp_sub(t0, t1);
+  r.c1 = fp_sub(fp_sub(t2, t0), t1);
+  return r;
+}
+// (a0 + a1 u)^2 = (a0 + a1)(a0 - a1) + 2 a0 a1 u
+LW_DEV inline Fp2 fp2_sqr(const Fp2& a) {
+  Fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t0, t1;
+  fp_mul_ni(t0, s, d);
+  fp_mul_ni(t1, a.c0, a.c1);
+  Fp2 r;
+  r.c0 = t0;
+  r.c1 = fp_dbl(t1);
+  return r;
+}
+LW_DEV inline Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) {
+  Fp2 r;
+  fp_mul_ni(r.c0, a.c0, k);
+  fp_mul_ni(r.c1, a.c1, k);
+  return r;
+}
+// multiply by the non-residue xi = 1 + u:  (a0 - a1) + (a0 + a1) u
+LW_INL Fp2 fp2_mul_xi(const Fp2& a) { Fp2 r; r.c0 = fp_sub(a.c0, a.c1); r.c1 = fp_add(a.c0, a.c1); return r; }
+LW_DEV inline Fp2 fp2_inv(const Fp2& a) {
+  Fp t0, t1;
+  fp_sqr_ni(t0, a.c0);
+  fp_sqr_ni(t1, a.c1);
+  Fp n = fp_inv(fp_add(t0, t1));
+  Fp2 r;
+  fp_mul_ni(r.c0, a.c0, n);
+  Fp t;
+  fp_mul_ni(t, a.c1, n);
+  r.c1 = fp_neg(t);
+  return r;
+}
+
+// Square root in Fp; returns false if `a` is a non-residue.
+LW_DEV inline bool fp_sqrt(Fp& out, const Fp& a) {
+  Fp s = fp_sqrt_candidate(a), chk;
+  fp_sqr_ni(chk, s);
+  if (!fp_eq(chk, a)) return false;
+  out = s;
+  return true;
+}
+
+// A square root in Fp2 (complex method), false if none exists.
+LW_DEV inline bool fp2_sqrt(Fp2& out, const Fp2& a) {
+  if (fp_is_zero(a.c1)) {
+    Fp s;
+    if (fp_sqrt(s, a.c0)) { out.c0 = s; out.c1 = fp_zero(); return true; }
+    if (fp_sqrt(s, fp_neg(a.c0))) { out.c0 = fp_zero(); out.c1 = s; return true; }
+    return false;
+  }
+  Fp t0, t1, n;
+  fp_sqr_ni(t0, a.c0);
+  fp_sqr_ni(t1, a.c1);
+  if (!fp_sqrt(n, fp_add(t0, t1))) return false;
+  // 1/2 in Montgomery form: (p+1)/2 * R -> compute as inv(2)
+  Fp two = fp_dbl(fp_one());
+  Fp half = fp_inv(two);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    Fp nn = attempt == 0 ? n : fp_neg(n);
+    Fp t;
+    fp_mul_ni(t, fp_add(a.c0, nn), half);
+    Fp x0;
+    if (!fp_sqrt(x0, t) || fp_is_zero(x0)) continue;
+    Fp x1;
+    fp_mul_ni(x1, a.c1, fp_inv(fp_dbl(x0)));
+    Fp2 cand; cand.c0 = x0; cand.c1 = x1;
+    if (fp2_eq(fp2_sqr(cand), a)) { out = cand; return true; }
+  }
+  return false;
+}
+
+struct G2Affine {
+  Fp2 x, y;
+};
+
+LW_DEV inline Fp2 g2_curve_b() {
+  Fp2 b;
+  for (int i = 0; i < 12; i++) { b.c0.l[i] = k::FP_B[i]; b.c1.l[i] = k::FP_B[i]; }
+  return b;
+}
+LW_DEV inline bool g2a_on_curve(const G2Affine& p) {
+  Fp2 lhs = fp2_sqr(p.y);
+  Fp2 rhs = fp2_add(fp2_mul(fp2_sqr(p.x), p.x), g2_curve_b());
+  return fp2_eq(lhs, rhs);
+}
+
+// ZCash lexicographic "largest" for Fp2: compare c1 first, then c0 (canonical values).
+LW_DEV inline bool fp2_is_lex_large(const Fp2& y) {
+  Fp c1 = fp_from_mont(y.c1);
+  if (!fp_is_zero(c1)) return fp_canon_is_lex_large(c1);
+  return fp_canon_is_lex_large(fp_from_mont(y.c0));
+}
+
+// 96-byte compressed G2 (bytes[0..48] = x.c1, bytes[48..96] = x.c0), following
+// src/compression.rs:105-139: bit7 required, bit6 -> infinity, x reduced mod p,
+// no subgroup check.  The sign bit (bit5) is honoured (ZCash rule); the
+// reference ignores it, which coincides for the shipped setups.
+LW_DEV inline bool g2_decompress(G2Affine& out, bool& is_inf, const uint8_t* in96) {
+  is_inf = false;
+  uint8_t b0 = in96[0];
+  if (!(b0 & 0x80)) return false;
+  if (b0 & 0x40) { is_inf = true; out.x = fp2_zero(); out.y = fp2_zero(); return true; }
+  uint8_t tmp[48];
+  for (int i = 0; i < 48; i++) tmp[i] = in96[i];
+  tmp[0] = b0 & 0x1F;
+  Fp2 x;
+  x.c1 = fp_from_be48(tmp);
+  // x.c0 carries no flag bits but may be >= 2^381: reduce fully
+  {
+    Fp a;
+    for (int i = 0; i < 12; i++) {
+      const uint8_t* q = in96 + 48 + 44 - 4 * i;
+      a.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+    }
+    mod_reduce_small<FpCfg, 9>(a.l);
+    x.c0 = fp_to_mont(a);
+  }
+  Fp2 y2 = fp2_add(fp2_mul(fp2_sqr(x), x), g2_curve_b());
+  Fp2 y;
+  if (!fp2_sqrt(y, y2)) return false;
+  bool want_large = (b0 & 0x20) != 0;
+  if (fp2_is_lex_large(y) != want_large) y = fp2_neg(y);
+  out.x = x; out.y = y;
+  return true;
+}
+
+}  // namespace lw

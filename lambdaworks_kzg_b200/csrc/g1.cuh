@@ -1,0 +1,235 @@
+// BLS12-381 G1 (y^2 = x^3 + 4) point arithmetic.
+//
+// Replaces lambdaworks-math's ShortWeierstrassProjectivePoint<BLS12381Curve>
+// (operate_with / operate_with_self / neg / to_affine; call sites
+// /root/reference/src/lib.rs:36-37, 241-243, 664-688, src/compression.rs:22-27).
+// The group element computed is the same whatever the coordinate system, so we
+// use the cheapest ones for a GPU:
+//   * affine (x, y) for stored bases / table entries (96 B); infinity = (0, 0),
+//     which is not on the curve and therefore unambiguous;
+//   * XYZZ (X, Y, ZZ, ZZZ), x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2, for accumulators
+//     (mixed add 8M+2S, add 12M+2S, double 6M+3S; EFD "xyzz", a = 0).
+//     Infinity <=> ZZ == 0.
+// Every formula handles the exceptional cases (P = Q, P = -Q, infinity) so the
+// result is exact for arbitrary inputs -- needed for bit-parity on edge blobs.
+#pragma once
+#include "field.cuh"
+
+namespace lw {
+
+struct G1Affine {
+  Fp x, y;
+};
+struct G1Xyzz {
+  Fp x, y, zz, zzz;
+};
+
+LW_INL bool g1a_is_inf(const G1Affine& p) { return fp_is_zero(p.x) && fp_is_zero(p.y); }
+LW_INL G1Affine g1a_inf() { G1Affine r; r.x = fp_zero(); r.y = fp_zero(); return r; }
+LW_INL G1Affine g1a_neg(const G1Affine& p) { G1Affine r; r.x = p.x; r.y = fp_neg(p.y); return r; }
+LW_INL G1Affine g1a_cneg(const G1Affine& p, bool neg) { G1Affine r; r.x = p.x; r.y = fp_cneg(p.y, neg); return r; }
+LW_INL G1Affine g1a_generator() {
+  G1Affine g;
+  for (int i = 0; i < 12; i++) { g.x.l[i] = k::G1_GEN_X[i]; g.y.l[i] = k::G1_GEN_Y[i]; }
+  return g;
+}
+// y^2 == x^3 + 4 (infinity (0,0) is NOT on the curve: mirrors from_affine in
+// /root/reference/src/srs.rs:155-172)
+LW_INL bool g1a_on_curve(const G1Affine& p) {
+  Fp b; for (int i = 0; i < 12; i++) b.l[i] = k::FP_B[i];
+  Fp lhs = fp_sqr(p.y);
+  Fp rhs = fp_add(fp_mul(fp_sqr(p.x), p.x), b);
+  return fp_eq(lhs, rhs);
+}
+
+LW_INL bool xyzz_is_inf(const G1Xyzz& p) { return fp_is_zero(p.zz); }
+LW_INL G1Xyzz xyzz_inf() { G1Xyzz r; r.x = fp_zero(); r.y = fp_zero(); r.zz = fp_zero(); r.zzz = fp_zero(); return r; }
+LW_INL G1Xyzz xyzz_from_affine(const G1Affine& p) {
+  G1Xyzz r;
+  if (g1a_is_inf(p)) return xyzz_inf();
+  r.x = p.x; r.y = p.y; r.zz = fp_one(); r.zzz = fp_one();
+  return r;
+}
+LW_INL G1Xyzz xyzz_neg(const G1Xyzz& p) { G1Xyzz r = p; r.y = fp_neg(p.y); return r; }
+
+// 2 * (affine p), p != infinity
+LW_INL G1Xyzz xyzz_dbl_affine(const G1Affine& p) {
+  G1Xyzz r;
+  Fp U = fp_dbl(p.y);
+  Fp V = fp_sqr(U);
+  Fp W = fp_mul(U, V);
+  Fp S = fp_mul(p.x, V);
+  Fp X2 = fp_sqr(p.x);
+  Fp M = fp_add(fp_dbl(X2), X2);
+  r.x = fp_sub(fp_sqr(M), fp_dbl(S));
+  r.y = fp_sub(fp_mul(M, fp_sub(S, r.x)), fp_mul(W, p.y));
+  r.zz = V;
+  r.zzz = W;
+  return r;
+}
+
+LW_INL G1Xyzz xyzz_dbl(const G1Xyzz& p) {
+  if (xyzz_is_inf(p)) return p;
+  G1Xyzz r;
+  Fp U = fp_dbl(p.y);
+  Fp V = fp_sqr(U);
+  Fp W = fp_mul(U, V);
+  Fp S = fp_mul(p.x, V);
+  Fp X2 = fp_sqr(p.x);
+  Fp M = fp_add(fp_dbl(X2), X2);
+  r.x = fp_sub(fp_sqr(M), fp_dbl(S));
+  r.y = fp_sub(fp_mul(M, fp_sub(S, r.x)), fp_mul(W, p.y));
+  r.zz = fp_mul(V, p.zz);
+  r.zzz = fp_mul(W, p.zzz);
+  return r;  // y == 0 (2-torsion) gives zz = 0 = infinity, as it should
+}
+
+// acc += p   (p affine)
+LW_INL void xyzz_madd(G1Xyzz& acc, const G1Affine& p) {
+  if (g1a_is_inf(p)) return;
+  if (xyzz_is_inf(acc)) {
+    acc.x = p.x; acc.y = p.y; acc.zz = fp_one(); acc.zzz = fp_one();
+    return;
+  }
+  Fp U2 = fp_mul(p.x, acc.zz);
+  Fp S2 = fp_mul(p.y, acc.zzz);
+  Fp Pd = fp_sub(U2, acc.x);
+  Fp Rd = fp_sub(S2, acc.y);
+  if (fp_is_zero(Pd)) {
+    if (fp_is_zero(Rd)) acc = xyzz_dbl_affine(p);
+    else acc = xyzz_inf();
+    return;
+  }
+  Fp PP = fp_sqr(Pd);
+  Fp PPP = fp_mul(Pd, PP);
+  Fp Q = fp_mul(acc.x, PP);
+  Fp X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
+  Fp Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(acc.y, PPP));
+  acc.zz = fp_mul(acc.zz, PP);
+  acc.zzz = fp_mul(acc.zzz, PPP);
+  acc.x = X3;
+  acc.y = Y3;
+}
+
+// a += b   (both XYZZ)
+LW_INL void xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
+  if (xyzz_is_inf(b)) return;
+  if (xyzz_is_inf(a)) { a = b; return; }
+  Fp U1 = fp_mul(a.x, b.zz);
+  Fp U2 = fp_mul(b.x, a.zz);
+  Fp S1 = fp_mul(a.y, b.zzz);
+  Fp S2 = fp_mul(b.y, a.zzz);
+  Fp Pd = fp_sub(U2, U1);
+  Fp Rd = fp_sub(S2, S1);
+  if (fp_is_zero(Pd)) {
+    if (fp_is_zero(Rd)) a = xyzz_dbl(a);
+    else a = xyzz_inf();
+    return;
+  }
+  Fp PP = fp_sqr(Pd);
+  Fp PPP = fp_mul(Pd, PP);
+  Fp Q = fp_mul(U1, PP);
+  Fp X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
+  Fp Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(S1, PPP));
+  a.zz = fp_mul(fp_mul(a.zz, b.zz), PP);
+  a.zzz = fp_mul(fp_mul(a.zzz, b.zzz), PPP);
+  a.x = X3;
+  a.y = Y3;
+}
+
+// XYZZ -> affine (one inversion); infinity -> (0,0)
+LW_DEV inline G1Affine xyzz_to_affine(const G1Xyzz& p) {
+  if (xyzz_is_inf(p)) return g1a_inf();
+  Fp zzz_inv = fp_inv(p.zzz);
+  Fp t = fp_mul(p.zz, zzz_inv);  // ZZ/ZZZ = 1/sqrt(ZZ)
+  Fp zz_inv = fp_sqr(t);         // ZZ^2/ZZZ^2 = 1/ZZ
+  G1Affine r;
+  r.x = fp_mul(p.x, zz_inv);
+  r.y = fp_mul(p.y, zzz_inv);
+  return r;
+}
+
+// a == b as group elements
+LW_INL bool xyzz_eq(const G1Xyzz& a, const G1Xyzz& b) {
+  bool ia = xyzz_is_inf(a), ib = xyzz_is_inf(b);
+  if (ia || ib) return ia && ib;
+  return fp_eq(fp_mul(a.x, b.zz), fp_mul(b.x, a.zz)) && fp_eq(fp_mul(a.y, b.zzz), fp_mul(b.y, a.zzz));
+}
+
+// [k]p for a canonical 256-bit little-endian scalar (8 x u32), MSB-first
+// double-and-add.  Cold path (verification, table seeding).
+LW_DEV inline G1Xyzz g1_mul_scalar(const G1Affine& p, const uint32_t* kk, int nlimbs) {
+  G1Xyzz acc = xyzz_inf();
+  bool started = false;
+  for (int w = nlimbs - 1; w >= 0; w--) {
+    uint32_t word = kk[w];
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) acc = xyzz_dbl(acc);
+      if ((word >> bit) & 1u) { xyzz_madd(acc, p); started = true; }
+    }
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------- codecs
+// /root/reference/src/compression.rs:33-60
+LW_DEV inline void g1_compress(uint8_t* out48, const G1Affine& p) {
+  if (g1a_is_inf(p)) {
+    out48[0] = 0xC0;
+    for (int i = 1; i < 48; i++) out48[i] = 0;
+    return;
+  }
+  Fp xc = fp_from_mont(p.x);
+  Fp yc = fp_from_mont(p.y);
+  fp_canon_to_be48(out48, xc);
+  out48[0] |= 0x80;
+  if (fp_canon_is_lex_large(yc)) out48[0] |= 0x20;
+}
+
+// Subgroup test with the same accept set as the reference's [r]P == O
+// (src/compression.rs:22-27): for BLS12-381, P in G1 <=> phi(P) == [-x^2]P
+// where phi(x,y) = (beta x, y)  (Scott, "A note on group membership tests for
+// G1, G2 and GT on BLS pairing-friendly curves", 2021).  [x^2]P costs two
+// 64-bit double-and-add ladders instead of a 255-bit one.
+LW_DEV inline G1Xyzz g1_mul_u64(const G1Xyzz& p, unsigned long long e) {
+  G1Xyzz acc = xyzz_inf();
+  bool started = false;
+  for (int bit = 63; bit >= 0; bit--) {
+    if (started) acc = xyzz_dbl(acc);
+    if ((e >> bit) & 1ull) { xyzz_add(acc, p); started = true; }
+  }
+  return acc;
+}
+LW_DEV inline bool g1_in_subgroup(const G1Affine& p) {
+  if (g1a_is_inf(p)) return true;
+  G1Xyzz P = xyzz_from_affine(p);
+  G1Xyzz t = g1_mul_u64(g1_mul_u64(P, k::BLS_X_ABS), k::BLS_X_ABS);  // [x^2]P
+  Fp beta; for (int i = 0; i < 12; i++) beta.l[i] = k::FP_BETA[i];
+  G1Xyzz phi = P;
+  phi.x = fp_mul(P.x, beta);
+  return xyzz_eq(phi, xyzz_neg(t));
+}
+
+// /root/reference/src/compression.rs:62-103.  Returns false
+// on any rejection.  *out is affine; infinity -> (0,0).
+LW_DEV inline bool g1_decompress(G1Affine& out, const uint8_t* in48) {
+  uint8_t b0 = in48[0];
+  if (!(b0 & 0x80)) return false;
+  if (b0 & 0x40) { out = g1a_inf(); return true; }  // remaining bits unchecked, like the reference
+  uint8_t tmp[48];
+  for (int i = 0; i < 48; i++) tmp[i] = in48[i];
+  tmp[0] = b0 & 0x1F;
+  Fp x = fp_from_be48(tmp);
+  Fp b; for (int i = 0; i < 12; i++) b.l[i] = k::FP_B[i];
+  Fp y2 = fp_add(fp_mul(fp_sqr(x), x), b);
+  Fp y = fp_sqrt_candidate(y2);
+  if (!fp_eq(fp_sqr(y), y2)) return false;
+  bool large = fp_canon_is_lex_large(fp_from_mont(y));
+  bool want_large = (b0 & 0x20) != 0;
+  // y == 0 cannot happen (no 2-torsion); if it did both roots coincide.
+  if (large != want_large) y = fp_neg(y);
+  out.x = x; out.y = y;
+  return g1_in_subgroup(out);
+}
+
+}  // namespace lw

@@ -1,0 +1,84 @@
+// Host-side launch interface of the CUDA kernels (internal; the public
+// boundary is include/lwkzg.h).  Every launcher enqueues on `st` and returns;
+// errors are collected with cudaGetLastError by the caller.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace lw {
+
+constexpr int N_POINTS = 4096;          // FIELD_ELEMENTS_PER_BLOB
+constexpr int BLOB_BYTES = 4096 * 32;
+constexpr int AFFINE_BYTES = 96;        // Montgomery x||y, 2 x 12 u32
+constexpr int XYZZ_BYTES = 192;
+
+uint64_t launches();                    // kernels launched so far
+void count_launch(int n = 1);
+
+// ---- setup (table.cu)
+// canonical LE limbs (x||y, 24 u32 per point; all-zero = infinity) -> Montgomery
+// affine; flags[i] = 1 if the point is not on the curve (infinity counts as
+// "not on curve": srs.rs:155-172), flags2[i] = 1 if not in the r-torsion.
+void launch_srs_import(void* d_aff_out, const void* d_canon_in, int* d_not_on_curve, int* d_not_in_subgroup, int n, cudaStream_t st);
+// bases[j][i] = 2^(c j) P_i  (affine, Montgomery), j < nwin
+void launch_table_bases(void* d_bases, const void* d_aff, int c, int nwin, int npoints, cudaStream_t st);
+// table[(j*npoints+i) << (c-1) | (d-1)] = d * bases[j][i], d = 1..2^(c-1)
+void launch_table_fill(void* d_table, const void* d_bases, int c, int nwin, int npoints, cudaStream_t st);
+
+// ---- fixed-base MSM (msm.cu)
+// scalars: n blobs of 4096 x 32 bytes; be_input: raw big-endian blob words
+// (reduced mod r on the fly) or canonical little-endian u32 limbs.
+// partials: n * blocks_per_blob XYZZ accumulators.
+void launch_msm_gather(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input,
+                       int n_blobs, int blocks_per_blob, cudaStream_t st);
+// sum partials, normalise, compress.  d_aff_out (may be NULL): Montgomery affine.
+void launch_msm_finalize(void* d_out48, void* d_aff_out, const void* d_partials, int parts_per_blob, int n_blobs, cudaStream_t st);
+int msm_threads_per_block();
+
+// ---- Fiat-Shamir + polynomial (poly.cu)
+// SHA-256 midstate over domain || le64(4096) || le64(0) || blob[0 .. 131040)
+void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st);
+// finish with blob tail + 48 commitment bytes -> z canonical (8 u32 LE per blob)
+void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st);
+// z from caller bytes (big-endian, reduced)
+void launch_fr_from_be(void* d_z, const void* d_z_be32, int n, cudaStream_t st);
+// y = p(z), q = (p - y)/(X - z): warp per blob.  d_q (n x 4096 x 8 u32 canonical,
+// may be NULL), d_y_be32 (n x 32 bytes big-endian, may be NULL), d_y (canonical u32, may be NULL)
+void launch_poly_eval_quot(void* d_q, void* d_y, void* d_y_be32, const void* d_blobs, const void* d_z, int n, cudaStream_t st);
+
+// ---- point codecs (codec.cu)
+// status[i] = 0 ok / 2 (C_KZG_ERROR) rejected.  d_aff (Montgomery, may be NULL),
+// d_recompressed48 (canonical re-encoding, may be NULL)
+void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st);
+void launch_status_or(int* d_status, const int* d_other, int n, cudaStream_t st);
+
+// ---- synthetic data + probes (misc.cu)
+void launch_synth_blobs(void* d_blobs, uint64_t first_blob, size_t n, cudaStream_t st);
+double run_imad_peak(int variant);
+
+// ---- verification (verify.cu)
+struct G2PreparedDev;  // opaque: line coefficients of one G2 point
+size_t g2_prepared_bytes();
+// canonical LE limbs x.c0,x.c1,y.c0,y.c1 (48 u32) -> prepared lines; flag = 1 if not on the twist
+void launch_g2_prepare(void* d_prepared, int* d_bad, const void* d_canon_in, cudaStream_t st);
+// single verification: C - y*g1_0 + z*pi  vs  pi  (bilinear rearrangement)
+// inputs: affine Montgomery C, pi; canonical z, y.  ok written as int.
+void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
+                          const void* d_g1_0_aff, const void* d_prep0, const void* d_prep1, cudaStream_t st);
+// tuples: compress(C)||z||y||compress(pi) (160 B each)
+void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st);
+// r = H(domain || le64(4096) || le64(n_total) || tuples) -> canonical r (8 u32)
+void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st);
+// partial sums over [first, first+n_local): 3 XYZZ blocks-partials then reduced to 3 affine (canonical BE 96 B each)
+void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
+                           size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st);
+size_t batch_partials_scratch_bytes(int n_local);
+// sum n_ranks partial triples, then e(rhs, g2_0) * e(-proof_lincomb, g2_1) == 1
+void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const void* d_prep0, const void* d_prep1, cudaStream_t st);
+
+// ---- generic (variable-base) MSM for lwkzg_g1_lincomb (varmsm.cu)
+void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st);
+size_t var_msm_scratch_bytes(size_t n);
+
+}  // namespace lw

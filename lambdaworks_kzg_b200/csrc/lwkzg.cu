@@ -1,0 +1,737 @@
+// Host runtime and C ABI of liblwkzg_b200.so (declared in include/lwkzg.h).
+//
+// Mirrors the orchestration of /root/reference/src/lib.rs:245-858 -- same
+// entry points, argument meaning, order of checks and error mapping (SURVEY
+// App. A.11) -- with the arithmetic moved to the CUDA kernels in this
+// directory.  The per-call SRS re-hydration of the reference
+// (kzgsettings_to_structured_reference_string, src/srs.rs:258-280) becomes a
+// device context that is built once per KZGSettings and stays resident in HBM.
+//
+// There is no CPU compute path in here: the host only parses text, moves bytes
+// and launches kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lwkzg.h"
+#include "kernels.h"
+#include "kernels_setup.h"
+
+namespace {
+
+using namespace lw;
+
+thread_local std::string tl_err;
+
+void set_err(const std::string& s) { tl_err = s; }
+
+#define CU_TRY(expr)                                                                      \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      set_err(std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+      return false;                                                                       \
+    }                                                                                     \
+  } while (0)
+
+struct Options {
+  long window_bits = 13;
+  long msm_blocks_per_blob = 0;
+  long chunk_blobs = 512;
+  Options() {
+    if (const char* e = getenv("LWKZG_WINDOW_BITS")) window_bits = atol(e);
+    if (const char* e = getenv("LWKZG_CHUNK_BLOBS")) chunk_blobs = atol(e);
+    if (const char* e = getenv("LWKZG_MSM_BLOCKS_PER_BLOB")) msm_blocks_per_blob = atol(e);
+  }
+};
+Options& opts() {
+  static Options o;
+  return o;
+}
+std::mutex g_mu;  // guards options + the lazy-context cache
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CU_TRY(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return true;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+constexpr uint64_t CTX_MAGIC = 0x4c574b5a47423230ull;  // "LWKZGB20"
+constexpr int NSLOT = 2;
+
+struct Slot {
+  cudaStream_t st = nullptr, aux = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_aux = nullptr, ev_done = nullptr, ev_fork = nullptr;
+  DevBuf blobs, q, partials, states, z, y, ybe, c48, cin48, p48, caff, status, status2, zbe;
+};
+
+struct Ctx {
+  FFTSettings fs_prefix;  // MUST be first: KZGSettings.fs points here
+  uint64_t magic;
+  int device;
+  int c, nwin;
+  bool srs_valid;     // every g1 value on the curve (else every call errors, like the reference's re-hydration)
+  bool srs_in_g1;     // every g1 value in the r-torsion
+  bool g2_valid;      // g2[0], g2[1] on the twist
+  void* d_srs;        // 4096 affine Montgomery
+  void* d_table;      // fixed-base digit table
+  void* d_prep0;      // prepared g2[0] / g2[1] line coefficients
+  void* d_prep1;
+  Slot slot[NSLOT];
+  std::mutex mu;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// ------------------------------------------------------------------ g1/g2 value layout
+// src/srs.rs:131-213: canonical integers, u64 limbs most-significant first.
+void canon_to_blst_fp(blst_fp* out, const uint32_t* le12) {
+  for (int k = 0; k < 6; k++) out->l[k] = ((uint64_t)le12[11 - 2 * k] << 32) | (uint64_t)le12[10 - 2 * k];
+}
+void blst_fp_to_canon(uint32_t* le12, const blst_fp* in) {
+  for (int k = 0; k < 6; k++) {
+    le12[11 - 2 * k] = (uint32_t)(in->l[k] >> 32);
+    le12[10 - 2 * k] = (uint32_t)in->l[k];
+  }
+}
+
+// ------------------------------------------------------------------ context
+void destroy_ctx(Ctx* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  for (auto& s : c->slot) {
+    if (s.st) cudaStreamSynchronize(s.st);
+    if (s.aux) cudaStreamSynchronize(s.aux);
+    for (DevBuf* b : {&s.blobs, &s.q, &s.partials, &s.states, &s.z, &s.y, &s.ybe, &s.c48, &s.cin48, &s.p48, &s.caff, &s.status, &s.status2, &s.zbe}) b->release();
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
+    if (s.ev_aux) cudaEventDestroy(s.ev_aux);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.st) cudaStreamDestroy(s.st);
+    if (s.aux) cudaStreamDestroy(s.aux);
+  }
+  if (c->d_srs) cudaFree(c->d_srs);
+  if (c->d_table) cudaFree(c->d_table);
+  if (c->d_prep0) cudaFree(c->d_prep0);
+  if (c->d_prep1) cudaFree(c->d_prep1);
+  c->magic = 0;
+  delete c;
+}
+
+bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2) {
+  CU_TRY(cudaGetDevice(&c->device));
+  int lo = 0, hi = 0;
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  for (auto& s : c->slot) {
+    CU_TRY(cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, lo));
+    CU_TRY(cudaStreamCreateWithPriority(&s.aux, cudaStreamNonBlocking, hi));  // SHA midstate: latency critical
+    CU_TRY(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s.ev_aux, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+  }
+  cudaStream_t st = c->slot[0].st;
+
+  // ---- SRS import
+  std::vector<uint32_t> canon((size_t)N_POINTS * 24);
+  for (int i = 0; i < N_POINTS; i++) {
+    blst_fp_to_canon(&canon[(size_t)i * 24], &g1[i].x);
+    blst_fp_to_canon(&canon[(size_t)i * 24 + 12], &g1[i].y);
+  }
+  void* d_canon = nullptr;
+  int* d_flags = nullptr;
+  CU_TRY(cudaMalloc(&d_canon, canon.size() * 4));
+  CU_TRY(cudaMalloc(&d_flags, 2 * N_POINTS * sizeof(int)));
+  CU_TRY(cudaMalloc(&c->d_srs, (size_t)N_POINTS * AFFINE_BYTES));
+  CU_TRY(cudaMemcpyAsync(d_canon, canon.data(), canon.size() * 4, cudaMemcpyHostToDevice, st));
+  launch_srs_import(c->d_srs, d_canon, d_flags, d_flags + N_POINTS, N_POINTS, st);
+  std::vector<int> flags(2 * N_POINTS);
+  CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, flags.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  cudaFree(d_canon);
+  cudaFree(d_flags);
+  c->srs_valid = true;
+  c->srs_in_g1 = true;
+  for (int i = 0; i < N_POINTS; i++) {
+    if (flags[i]) c->srs_valid = false;
+    if (flags[N_POINTS + i]) c->srs_in_g1 = false;
+  }
+
+  // ---- G2: g2[0], g2[1] -> prepared Miller-loop lines
+  c->g2_valid = false;
+  {
+    uint32_t g2canon[2][48];
+    for (int k = 0; k < 2; k++) {
+      blst_fp_to_canon(&g2canon[k][0], &g2[k].x.fp[0]);
+      blst_fp_to_canon(&g2canon[k][12], &g2[k].x.fp[1]);
+      blst_fp_to_canon(&g2canon[k][24], &g2[k].y.fp[0]);
+      blst_fp_to_canon(&g2canon[k][36], &g2[k].y.fp[1]);
+    }
+    void* d_g2 = nullptr;
+    int* d_bad = nullptr;
+    CU_TRY(cudaMalloc(&d_g2, sizeof(g2canon)));
+    CU_TRY(cudaMalloc(&d_bad, 2 * sizeof(int)));
+    CU_TRY(cudaMalloc(&c->d_prep0, g2_prepared_bytes()));
+    CU_TRY(cudaMalloc(&c->d_prep1, g2_prepared_bytes()));
+    CU_TRY(cudaMemcpyAsync(d_g2, g2canon, sizeof(g2canon), cudaMemcpyHostToDevice, st));
+    launch_g2_prepare(c->d_prep0, d_bad, d_g2, st);
+    launch_g2_prepare(c->d_prep1, d_bad + 1, (const uint8_t*)d_g2 + 48 * 4, st);
+    int bad[2] = {1, 1};
+    CU_TRY(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_g2);
+    cudaFree(d_bad);
+    c->g2_valid = !bad[0] && !bad[1];
+  }
+
+  if (!c->srs_valid) return true;  // usable only to report C_KZG_ERROR, like the reference
+
+  // ---- fixed-base digit table; shrink the window if HBM is short
+  long want_c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    want_c = opts().window_bits;
+  }
+  if (want_c < 4) want_c = 4;
+  if (want_c > 15) want_c = 15;
+  size_t free_b = 0, total_b = 0;
+  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  int cbits = (int)want_c;
+  for (;; cbits--) {
+    int nw = 255 / cbits + 1;
+    size_t need = ((size_t)nw * N_POINTS << (cbits - 1)) * AFFINE_BYTES;
+    if (need + (size_t(6) << 30) <= free_b || cbits <= 4) break;
+  }
+  c->c = cbits;
+  c->nwin = 255 / cbits + 1;
+  size_t entries = (size_t)c->nwin * N_POINTS << (cbits - 1);
+  CU_TRY(cudaMalloc(&c->d_table, entries * AFFINE_BYTES));
+  void* d_bases = nullptr;
+  CU_TRY(cudaMalloc(&d_bases, (size_t)c->nwin * N_POINTS * AFFINE_BYTES));
+  launch_table_bases(d_bases, c->d_srs, c->c, c->nwin, N_POINTS, st);
+  launch_table_fill(c->d_table, d_bases, c->c, c->nwin, N_POINTS, st);
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaGetLastError());
+  cudaFree(d_bases);
+  return true;
+}
+
+Ctx* build_ctx(const g1_t* g1, const g2_t* g2) {
+  Ctx* c = new Ctx();
+  memset(&c->fs_prefix, 0, sizeof(c->fs_prefix));
+  c->magic = CTX_MAGIC;
+  c->d_srs = c->d_table = c->d_prep0 = c->d_prep1 = nullptr;
+  c->c = c->nwin = 0;
+  c->srs_valid = c->srs_in_g1 = c->g2_valid = false;
+  if (!build_ctx_inner(c, g1, g2)) {
+    std::string e = tl_err;
+    destroy_ctx(c);
+    set_err(e);
+    return nullptr;
+  }
+  return c;
+}
+
+// lazily created contexts for hand-assembled KZGSettings (fs == NULL)
+struct LazyKey {
+  const void* g1;
+  const void* g2;
+  uint64_t hash;
+  bool operator<(const LazyKey& o) const {
+    if (g1 != o.g1) return g1 < o.g1;
+    if (g2 != o.g2) return g2 < o.g2;
+    return hash < o.hash;
+  }
+};
+std::map<LazyKey, Ctx*>& lazy_map() {
+  static std::map<LazyKey, Ctx*> m;
+  return m;
+}
+uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+  const uint64_t* w = (const uint64_t*)p;  // all inputs are multiples of 8 bytes
+  for (size_t i = 0; i < n / 8; i++) {
+    h ^= w[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+Ctx* ctx_of(const KZGSettings* s) {
+  if (!s || !s->g1_values || !s->g2_values) {
+    set_err("null KZGSettings");
+    return nullptr;
+  }
+  if (s->fs) {
+    Ctx* c = reinterpret_cast<Ctx*>(s->fs);
+    if (c->magic == CTX_MAGIC) return c;
+  }
+  LazyKey key{s->g1_values, s->g2_values, 0};
+  key.hash = fnv1a(s->g1_values, sizeof(g1_t) * N_POINTS);
+  key.hash = fnv1a(s->g2_values, sizeof(g2_t) * 2, key.hash);
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = lazy_map().find(key);
+  if (it != lazy_map().end()) return it->second;
+  // drop stale contexts registered for the same pointers
+  for (auto j = lazy_map().begin(); j != lazy_map().end();) {
+    if (j->first.g1 == key.g1 && j->first.g2 == key.g2) {
+      destroy_ctx(j->second);
+      j = lazy_map().erase(j);
+    } else {
+      ++j;
+    }
+  }
+  g_mu.unlock();
+  Ctx* c = build_ctx(s->g1_values, s->g2_values);
+  g_mu.lock();
+  if (c) lazy_map()[key] = c;
+  return c;
+}
+
+// ------------------------------------------------------------------ pipeline
+enum class Mode { Commit, CommitProve, BlobProof, PointProof };
+
+int auto_bpb(int n) {
+  long o;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    o = opts().msm_blocks_per_blob;
+  }
+  if (o > 0) return (int)o;
+  int target = (2048 + n - 1) / n;
+  int b = 1;
+  while (b < target) b <<= 1;
+  return std::min(b, 128);
+}
+
+bool slot_reserve(Slot& s, int n, int bpb, bool need_blobs) {
+  if (need_blobs && !s.blobs.ensure((size_t)n * BLOB_BYTES)) return false;
+  return s.q.ensure((size_t)n * BLOB_BYTES) && s.partials.ensure((size_t)n * bpb * XYZZ_BYTES) && s.states.ensure((size_t)n * 32) &&
+         s.z.ensure((size_t)n * 32) && s.y.ensure((size_t)n * 32) && s.ybe.ensure((size_t)n * 32) && s.c48.ensure((size_t)n * 48) &&
+         s.cin48.ensure((size_t)n * 48) && s.p48.ensure((size_t)n * 48) && s.caff.ensure((size_t)n * AFFINE_BYTES) &&
+         s.status.ensure((size_t)n * sizeof(int)) && s.status2.ensure((size_t)n * sizeof(int)) && s.zbe.ensure((size_t)n * 32);
+}
+
+// Enqueue one chunk on slot.st (+ slot.aux for the SHA midstate).  All pointers
+// are device pointers.  Outputs: d_c48 (Commit/CommitProve), d_p48 (all but
+// Commit), d_ybe (PointProof), d_status (BlobProof: decode status of the given
+// commitments; else zero-filled).
+bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void* d_c48, void* d_p48, void* d_ybe, int* d_status,
+                   const void* d_commit_in48, const void* d_z_in_be) {
+  const int bpb = auto_bpb(n);
+  cudaStream_t st = s.st;
+  if (mode == Mode::Commit) {
+    launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, true, n, bpb, st);
+    launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
+    if (d_status) CU_TRY(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int), st));
+    return true;
+  }
+  const void* commit_for_hash = nullptr;
+  if (mode == Mode::CommitProve || mode == Mode::BlobProof) {
+    // fork: SHA-256 midstate over the blob on the high-priority aux stream
+    CU_TRY(cudaEventRecord(s.ev_fork, st));
+    CU_TRY(cudaStreamWaitEvent(s.aux, s.ev_fork, 0));
+    launch_challenge_midstate(s.states.p, d_blobs, n, s.aux);
+    CU_TRY(cudaEventRecord(s.ev_aux, s.aux));
+  }
+  if (mode == Mode::CommitProve) {
+    launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, true, n, bpb, st);
+    launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
+    commit_for_hash = d_c48;
+    if (d_status) CU_TRY(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int), st));
+    if (!c->srs_in_g1) {
+      // compute_blob_kzg_proof re-validates its commitment argument
+      // (lib.rs:373): only matters for hand-made setups with points outside G1
+      launch_g1_decompress(nullptr, nullptr, d_status ? d_status : (int*)s.status.p, d_c48, n, st);
+    }
+  } else if (mode == Mode::BlobProof) {
+    // lib.rs:373-378: decode the commitment first; the hash sees its canonical re-encoding (utils.rs:138)
+    launch_g1_decompress(nullptr, s.c48.p, d_status ? d_status : (int*)s.status.p, d_commit_in48, n, st);
+    commit_for_hash = s.c48.p;
+  }
+  if (mode == Mode::PointProof) {
+    launch_fr_from_be(s.z.p, d_z_in_be, n, st);
+    if (d_status) CU_TRY(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int), st));
+  } else {
+    CU_TRY(cudaStreamWaitEvent(st, s.ev_aux, 0));
+    launch_challenge_finish(s.z.p, s.states.p, d_blobs, commit_for_hash, n, st);
+  }
+  launch_poly_eval_quot(s.q.p, nullptr, d_ybe, d_blobs, s.z.p, n, st);
+  launch_msm_gather(s.partials.p, c->d_table, c->c, s.q.p, false, n, bpb, st);
+  launch_msm_finalize(d_p48, nullptr, s.partials.p, bpb, n, st);
+  return true;
+}
+
+C_KZG_RET first_bad(const std::vector<int>& st) {
+  for (int v : st)
+    if (v) return (C_KZG_RET)v;
+  return C_KZG_OK;
+}
+
+// Host-buffer batch driver: chunked, double-buffered over two stream slots so
+// the H2D copy of chunk k+1 overlaps the kernels of chunk k.
+C_KZG_RET host_batch(Mode mode, const KZGSettings* s, size_t n, const Blob* blobs, const Bytes48* commit_in, const Bytes32* z_in,
+                     Bytes48* c_out, Bytes48* p_out, Bytes32* y_out, int* status) {
+  if (n == 0) return C_KZG_OK;
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  if (!c->srs_valid) {
+    set_err("SRS re-hydration failed: g1_values holds a point that is not on the curve");
+    if (status) for (size_t i = 0; i < n; i++) status[i] = C_KZG_ERROR;
+    return C_KZG_ERROR;
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard dg(c->device);
+  long chunk;
+  {
+    std::lock_guard<std::mutex> lk2(g_mu);
+    chunk = std::max(1L, opts().chunk_blobs);
+  }
+  std::vector<int> st_host(n, 0);
+  // outputs land in temporaries so that failed items leave caller memory untouched (lib.rs:275-281, 334-341)
+  std::vector<Bytes48> c_tmp(c_out ? n : 0), p_tmp(p_out ? n : 0);
+  std::vector<Bytes32> y_tmp(y_out ? n : 0);
+  auto fail = [&]() {
+    for (auto& sl : c->slot) { cudaStreamSynchronize(sl.st); cudaStreamSynchronize(sl.aux); }
+    return C_KZG_ERROR;
+  };
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    int m = (int)std::min<size_t>(chunk, n - off);
+    Slot& sl = c->slot[k % NSLOT];
+    if (cudaStreamSynchronize(sl.st) != cudaSuccess) { set_err("stream sync failed"); return fail(); }
+    if (!slot_reserve(sl, m, auto_bpb(m), true)) return fail();
+    if (cudaMemcpyAsync(sl.blobs.p, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, sl.st) != cudaSuccess) { set_err("H2D failed"); return fail(); }
+    if (mode == Mode::BlobProof) cudaMemcpyAsync(sl.cin48.p, commit_in + off, (size_t)m * 48, cudaMemcpyHostToDevice, sl.st);
+    if (mode == Mode::PointProof) cudaMemcpyAsync(sl.zbe.p, z_in + off, (size_t)m * 32, cudaMemcpyHostToDevice, sl.st);
+    void* d_c48 = (mode == Mode::BlobProof) ? nullptr : sl.c48.p;
+    if (!enqueue_chunk(c, sl, mode, sl.blobs.p, m, d_c48, sl.p48.p, y_out ? sl.ybe.p : nullptr, (int*)sl.status.p, sl.cin48.p, sl.zbe.p)) return fail();
+    if (c_out) cudaMemcpyAsync(&c_tmp[off], sl.c48.p, (size_t)m * 48, cudaMemcpyDeviceToHost, sl.st);
+    if (p_out) cudaMemcpyAsync(&p_tmp[off], sl.p48.p, (size_t)m * 48, cudaMemcpyDeviceToHost, sl.st);
+    if (y_out) cudaMemcpyAsync(&y_tmp[off], sl.ybe.p, (size_t)m * 32, cudaMemcpyDeviceToHost, sl.st);
+    cudaMemcpyAsync(&st_host[off], sl.status.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, sl.st);
+  }
+  for (auto& sl : c->slot) {
+    cudaError_t e = cudaStreamSynchronize(sl.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sl.aux);
+    if (e != cudaSuccess) { set_err(std::string("kernel failure: ") + cudaGetErrorString(e)); return C_KZG_ERROR; }
+  }
+  if (cudaGetLastError() != cudaSuccess) { set_err("CUDA launch failure"); return C_KZG_ERROR; }
+  for (size_t i = 0; i < n; i++) {
+    if (st_host[i] == 0) {
+      if (c_out) c_out[i] = c_tmp[i];
+      if (p_out) p_out[i] = p_tmp[i];
+      if (y_out) y_out[i] = y_tmp[i];
+    }
+    if (status) status[i] = st_host[i];
+  }
+  if (!status) {
+    C_KZG_RET r = first_bad(st_host);
+    if (r != C_KZG_OK) set_err("invalid input item");
+    return r;
+  }
+  return C_KZG_OK;
+}
+
+// Device-buffer batch driver, asynchronous with respect to the host: forks from
+// `user` onto the two internal slots and joins back.
+C_KZG_RET device_batch(Mode mode, const KZGSettings* s, size_t n, const void* d_blobs, const void* d_commit_in, void* d_c_out,
+                       void* d_p_out, void* d_status, cudaStream_t user) {
+  if (n == 0) return C_KZG_OK;
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  if (!c->srs_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard dg(c->device);
+  long chunk;
+  {
+    std::lock_guard<std::mutex> lk2(g_mu);
+    chunk = std::max(1L, opts().chunk_blobs);
+  }
+  // buffers must be big enough BEFORE anything is enqueued (a realloc would
+  // pull memory from under kernels still in flight on the other slot)
+  size_t nchunks = (n + chunk - 1) / chunk;
+  for (size_t k = 0; k < std::min<size_t>(nchunks, NSLOT); k++) {
+    int m = (int)std::min<size_t>(chunk, n);
+    cudaStreamSynchronize(c->slot[k].st);
+    if (!slot_reserve(c->slot[k], m, auto_bpb(m), false)) return C_KZG_ERROR;
+  }
+  cudaEvent_t ev_user;
+  if (cudaEventCreateWithFlags(&ev_user, cudaEventDisableTiming) != cudaSuccess) { set_err("event"); return C_KZG_ERROR; }
+  cudaEventRecord(ev_user, user);
+  for (auto& sl : c->slot) cudaStreamWaitEvent(sl.st, ev_user, 0);
+  size_t k = 0;
+  bool ok = true;
+  for (size_t off = 0; off < n && ok; off += chunk, k++) {
+    int m = (int)std::min<size_t>(chunk, n - off);
+    Slot& sl = c->slot[k % NSLOT];
+    const uint8_t* b = (const uint8_t*)d_blobs + off * BLOB_BYTES;
+    void* co = d_c_out ? (uint8_t*)d_c_out + off * 48 : (mode == Mode::CommitProve ? sl.c48.p : nullptr);
+    void* po = d_p_out ? (uint8_t*)d_p_out + off * 48 : nullptr;
+    const void* ci = d_commit_in ? (const uint8_t*)d_commit_in + off * 48 : nullptr;
+    int* so = d_status ? (int*)d_status + off : nullptr;
+    ok = enqueue_chunk(c, sl, mode, b, m, co, po, nullptr, so, ci, nullptr);
+  }
+  for (auto& sl : c->slot) {
+    cudaEventRecord(sl.ev_done, sl.st);
+    cudaStreamWaitEvent(user, sl.ev_done, 0);
+  }
+  cudaEventDestroy(ev_user);
+  if (!ok || cudaGetLastError() != cudaSuccess) { if (ok) set_err("CUDA launch failure"); return C_KZG_ERROR; }
+  return C_KZG_OK;
+}
+
+// ------------------------------------------------------------------ setup loading
+bool hex_nibble(char ch, uint8_t& v) {
+  if (ch >= '0' && ch <= '9') { v = (uint8_t)(ch - '0'); return true; }
+  if (ch >= 'a' && ch <= 'f') { v = (uint8_t)(ch - 'a' + 10); return true; }
+  if (ch >= 'A' && ch <= 'F') { v = (uint8_t)(ch - 'A' + 10); return true; }
+  return false;
+}
+// hex::decode_to_slice semantics: exact length, hex digits only
+bool hex_line(const std::string& ln, uint8_t* out, size_t nbytes) {
+  if (ln.size() != 2 * nbytes) return false;
+  for (size_t i = 0; i < nbytes; i++) {
+    uint8_t a, b;
+    if (!hex_nibble(ln[2 * i], a) || !hex_nibble(ln[2 * i + 1], b)) return false;
+    out[i] = (uint8_t)(a << 4 | b);
+  }
+  return true;
+}
+// str::parse::<usize>: optional '+', digits only, no whitespace
+bool parse_usize(const std::string& ln, size_t& v) {
+  size_t i = 0;
+  if (i < ln.size() && ln[i] == '+') i++;
+  if (i >= ln.size()) return false;
+  v = 0;
+  for (; i < ln.size(); i++) {
+    if (ln[i] < '0' || ln[i] > '9') return false;
+    if (v > (SIZE_MAX - 9) / 10) return false;
+    v = v * 10 + (size_t)(ln[i] - '0');
+  }
+  return true;
+}
+
+// Decode + validate compressed points on the device, then lay out KZGSettings
+// exactly as src/srs.rs:99-153 / src/lib.rs:724-758 do.  n1 / n2 may be
+// smaller than 4096 / 65 for the file loader (tests/trusted_setup_4.txt): the
+// arrays are always allocated full size and zero-padded so later calls stay
+// memory safe (they then fail SRS re-hydration -> C_KZG_ERROR).
+C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, size_t n1, const uint8_t* g2_bytes, size_t n2) {
+  size_t a1 = std::max<size_t>(n1, N_POINTS), a2 = std::max<size_t>(n2, TRUSTED_SETUP_NUM_G2_POINTS);
+  void *d_in1 = nullptr, *d_in2 = nullptr, *d_c1 = nullptr, *d_c2 = nullptr;
+  int* d_st = nullptr;
+  std::vector<uint32_t> c1(n1 * 24), c2(n2 * 48);
+  std::vector<int> st(n1 + n2);
+  auto cleanup = [&]() {
+    cudaFree(d_in1); cudaFree(d_in2); cudaFree(d_c1); cudaFree(d_c2); cudaFree(d_st);
+  };
+  auto run = [&]() -> bool {
+    CU_TRY(cudaMalloc(&d_in1, std::max<size_t>(n1, 1) * 48));
+    CU_TRY(cudaMalloc(&d_in2, std::max<size_t>(n2, 1) * 96));
+    CU_TRY(cudaMalloc(&d_c1, std::max<size_t>(n1, 1) * 96));
+    CU_TRY(cudaMalloc(&d_c2, std::max<size_t>(n2, 1) * 192));
+    CU_TRY(cudaMalloc(&d_st, (n1 + n2 + 1) * sizeof(int)));
+    if (n1) CU_TRY(cudaMemcpy(d_in1, g1_bytes, n1 * 48, cudaMemcpyHostToDevice));
+    if (n2) CU_TRY(cudaMemcpy(d_in2, g2_bytes, n2 * 96, cudaMemcpyHostToDevice));
+    launch_setup_decode_g1(d_c1, d_st, d_in1, (int)n1, 0);
+    launch_setup_decode_g2(d_c2, d_st + n1, d_in2, (int)n2, 0);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaGetLastError());
+    if (n1) CU_TRY(cudaMemcpy(c1.data(), d_c1, n1 * 96, cudaMemcpyDeviceToHost));
+    if (n2) CU_TRY(cudaMemcpy(c2.data(), d_c2, n2 * 192, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(st.data(), d_st, (n1 + n2) * sizeof(int), cudaMemcpyDeviceToHost));
+    return true;
+  };
+  bool ok = run();
+  cleanup();
+  if (!ok) return C_KZG_ERROR;
+  for (size_t i = 0; i < n1; i++)
+    if (st[i] != 0) { set_err("invalid G1 point in trusted setup"); return C_KZG_ERROR; }
+  for (size_t i = 0; i < n2; i++)
+    if (st[n1 + i] == 2) { set_err("invalid G2 point in trusted setup"); return C_KZG_ERROR; }
+
+  g1_t* g1 = (g1_t*)calloc(a1, sizeof(g1_t));
+  g2_t* g2 = (g2_t*)calloc(a2, sizeof(g2_t));
+  if (!g1 || !g2) { free(g1); free(g2); return C_KZG_MALLOC; }
+  for (size_t i = 0; i < n1; i++) {
+    canon_to_blst_fp(&g1[i].x, &c1[i * 24]);
+    canon_to_blst_fp(&g1[i].y, &c1[i * 24 + 12]);
+    g1[i].z.l[5] = 1;  // z = 1, most-significant-first limbs (srs.rs:131-153; also for infinity)
+  }
+  for (size_t i = n1; i < a1; i++) g1[i].z.l[5] = 1;
+  for (size_t i = 0; i < n2; i++) {
+    canon_to_blst_fp(&g2[i].x.fp[0], &c2[i * 48]);
+    canon_to_blst_fp(&g2[i].x.fp[1], &c2[i * 48 + 12]);
+    canon_to_blst_fp(&g2[i].y.fp[0], &c2[i * 48 + 24]);
+    canon_to_blst_fp(&g2[i].y.fp[1], &c2[i * 48 + 36]);
+    if (st[n1 + i] == 0) g2[i].z.fp[0].l[5] = 1;  // affine z = 1 + 0u ; infinity keeps z = 0
+  }
+  Ctx* c = build_ctx(g1, g2);
+  if (!c) { free(g1); free(g2); return C_KZG_ERROR; }
+  out->fs = reinterpret_cast<FFTSettings*>(c);
+  out->g1_values = g1;
+  out->g2_values = g2;
+  return C_KZG_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* lwkzg_last_error(void) { return tl_err.c_str(); }
+const char* lwkzg_version(void) { return "lwkzg-b200 0.1 (sm_100a)"; }
+uint64_t lwkzg_kernel_launches(void) { return lw::launches(); }
+
+int lwkzg_set_option(const char* name, long value) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::string n(name ? name : "");
+  if (n == "window_bits") { if (value < 4 || value > 15) return 1; opts().window_bits = value; return 0; }
+  if (n == "msm_blocks_per_blob") { if (value < 0 || value > 128 || (value & (value - 1))) return 1; opts().msm_blocks_per_blob = value; return 0; }
+  if (n == "chunk_blobs") { if (value < 1) return 1; opts().chunk_blobs = value; return 0; }
+  return 1;
+}
+long lwkzg_get_option(const char* name) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::string n(name ? name : "");
+  if (n == "window_bits") return opts().window_bits;
+  if (n == "msm_blocks_per_blob") return opts().msm_blocks_per_blob;
+  if (n == "chunk_blobs") return opts().chunk_blobs;
+  return -1;
+}
+
+double lwkzg_imad_peak(int variant) { return lw::run_imad_peak(variant); }
+
+C_KZG_RET load_trusted_setup(KZGSettings* out, const uint8_t* g1_bytes, size_t n1, const uint8_t* g2_bytes, size_t n2) {
+  if (n1 != TRUSTED_SETUP_NUM_G1_POINTS || n2 != TRUSTED_SETUP_NUM_G2_POINTS) return C_KZG_BADARGS;  // lib.rs:716-718
+  if (!out || !g1_bytes || !g2_bytes) return C_KZG_ERROR;
+  return settings_from_compressed(out, g1_bytes, n1, g2_bytes, n2);
+}
+
+C_KZG_RET load_trusted_setup_file(KZGSettings* out, FILE* in) {
+  if (!out || !in) return C_KZG_ERROR;
+  std::string contents;
+  char buf[65536];
+  size_t got;
+  while ((got = fread(buf, 1, sizeof(buf), in)) > 0) contents.append(buf, got);
+  // str::lines(): split on '\n', strip one trailing '\r'
+  std::vector<std::string> lines;
+  size_t pos = 0;
+  while (pos < contents.size()) {
+    size_t nl = contents.find('\n', pos);
+    std::string ln = contents.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+    if (!ln.empty() && ln.back() == '\r') ln.pop_back();
+    lines.push_back(ln);
+    if (nl == std::string::npos) break;
+    pos = nl + 1;
+  }
+  size_t n1 = 0, n2 = 0;
+  if (lines.size() < 2 || !parse_usize(lines[0], n1) || !parse_usize(lines[1], n2)) { set_err("invalid trusted setup header"); return C_KZG_ERROR; }
+  if (n1 > (1u << 20) || n2 > (1u << 20)) { set_err("implausible point counts"); return C_KZG_ERROR; }
+  // srs.rs:54-79: lines beyond n1+n2 are ignored, a short file just yields fewer points
+  size_t avail = lines.size() - 2;
+  size_t m1 = std::min(n1, avail), m2 = std::min(n2, avail - m1);
+  std::vector<uint8_t> g1b(m1 * 48 + 1), g2b(m2 * 96 + 1);
+  for (size_t i = 0; i < m1; i++)
+    if (!hex_line(lines[2 + i], &g1b[i * 48], 48)) { set_err("bad G1 hex line"); return C_KZG_ERROR; }
+  for (size_t i = 0; i < m2; i++)
+    if (!hex_line(lines[2 + m1 + i], &g2b[i * 96], 96)) { set_err("bad G2 hex line"); return C_KZG_ERROR; }
+  return settings_from_compressed(out, g1b.data(), m1, g2b.data(), m2);
+}
+
+C_KZG_RET free_trusted_setup(KZGSettings* s) {
+  if (!s) return C_KZG_OK;
+  if (s->fs) {
+    Ctx* c = reinterpret_cast<Ctx*>(s->fs);
+    if (c->magic == CTX_MAGIC) destroy_ctx(c);
+    s->fs = nullptr;
+  } else {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto j = lazy_map().begin(); j != lazy_map().end();) {
+      if (j->first.g1 == s->g1_values && j->first.g2 == s->g2_values) {
+        destroy_ctx(j->second);
+        j = lazy_map().erase(j);
+      } else {
+        ++j;
+      }
+    }
+  }
+  free(s->g1_values);  // lib.rs:824-825
+  free(s->g2_values);
+  s->g1_values = nullptr;
+  s->g2_values = nullptr;
+  return C_KZG_OK;
+}
+
+// ---- batch API (host buffers)
+C_KZG_RET lwkzg_blob_to_kzg_commitment_batch(KZGCommitment* out, const Blob* blobs, size_t n, const KZGSettings* s, int* status) {
+  return host_batch(Mode::Commit, s, n, blobs, nullptr, nullptr, out, nullptr, nullptr, status);
+}
+C_KZG_RET lwkzg_compute_blob_kzg_proof_batch(KZGProof* out, const Blob* blobs, const Bytes48* commitments, size_t n, const KZGSettings* s, int* status) {
+  return host_batch(Mode::BlobProof, s, n, blobs, commitments, nullptr, nullptr, out, nullptr, status);
+}
+C_KZG_RET lwkzg_compute_kzg_proof_batch(KZGProof* proofs, Bytes32* ys, const Blob* blobs, const Bytes32* zs, size_t n, const KZGSettings* s, int* status) {
+  return host_batch(Mode::PointProof, s, n, blobs, nullptr, zs, nullptr, proofs, ys, status);
+}
+C_KZG_RET lwkzg_commit_and_prove_batch(KZGCommitment* commitments, KZGProof* proofs, const Blob* blobs, size_t n, const KZGSettings* s, int* status) {
+  return host_batch(Mode::CommitProve, s, n, blobs, nullptr, nullptr, commitments, proofs, nullptr, status);
+}
+
+// ---- batch API (device buffers)
+C_KZG_RET lwkzg_commit_and_prove_batch_device(void* d_commitments, void* d_proofs, const void* d_blobs, size_t n, const KZGSettings* s, void* stream, void* d_status) {
+  return device_batch(Mode::CommitProve, s, n, d_blobs, nullptr, d_commitments, d_proofs, d_status, (cudaStream_t)stream);
+}
+C_KZG_RET lwkzg_blob_to_kzg_commitment_batch_device(void* d_commitments, const void* d_blobs, size_t n, const KZGSettings* s, void* stream) {
+  return device_batch(Mode::Commit, s, n, d_blobs, nullptr, d_commitments, nullptr, nullptr, (cudaStream_t)stream);
+}
+C_KZG_RET lwkzg_compute_blob_kzg_proof_batch_device(void* d_proofs, const void* d_blobs, const void* d_commitments, size_t n, const KZGSettings* s, void* stream, void* d_status) {
+  return device_batch(Mode::BlobProof, s, n, d_blobs, d_commitments, nullptr, d_proofs, d_status, (cudaStream_t)stream);
+}
+
+C_KZG_RET lwkzg_synth_blobs_device(void* d_blobs, uint64_t first_blob, size_t n, void* stream) {
+  lw::launch_synth_blobs(d_blobs, first_blob, n, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? C_KZG_OK : C_KZG_ERROR;
+}
+
+// ---- the c-kzg-4844 single-item entry points = the n = 1 case of the batch drivers
+C_KZG_RET blob_to_kzg_commitment(KZGCommitment* out, const Blob* blob, const KZGSettings* s) {
+  return host_batch(Mode::Commit, s, 1, blob, nullptr, nullptr, out, nullptr, nullptr, nullptr);
+}
+C_KZG_RET compute_kzg_proof(KZGProof* proof_out, Bytes32* y_out, const Blob* blob, const Bytes32* z_bytes, const KZGSettings* s) {
+  return host_batch(Mode::PointProof, s, 1, blob, nullptr, z_bytes, nullptr, proof_out, y_out, nullptr);
+}
+C_KZG_RET compute_blob_kzg_proof(KZGProof* out, const Blob* blob, const Bytes48* commitment_bytes, const KZGSettings* s) {
+  return host_batch(Mode::BlobProof, s, 1, blob, commitment_bytes, nullptr, nullptr, out, nullptr, nullptr);
+}
+
+}  // extern "C"

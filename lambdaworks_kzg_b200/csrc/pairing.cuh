@@ -1,0 +1,237 @@
+// Optimal-ate pairing check on BLS12-381.
+//
+// Replaces lambdaworks-math's BLS12381AtePairing::compute_batch as reached
+// through KZG::verify (/root/reference/src/lib.rs:444, 496, 691; SURVEY App.
+// A.7, D.5, D.6).  Only the boolean "product of pairings == 1" is observable,
+// so any correct pairing yields identical results.
+//
+// Tower: Fp2 = Fp[u]/(u^2+1), Fp6 = Fp2[v]/(v^3 - xi), xi = 1+u,
+//        Fp12 = Fp6[w]/(w^2 - v)     (so w^6 = xi).
+// The twist E': y^2 = x^3 + 4 xi is of M type: psi(x', y') = (x'/w^2, y'/w^3).
+//
+// B200-first choice: the G2 arguments of every check are the two FIXED setup
+// points g2[0], g2[1], so all G2 arithmetic of the Miller loop is hoisted to
+// setup time: g2_prepare() stores, for each of the 63 doubling and 5 addition
+// steps, the affine tangent/chord (lambda, mu = lambda x_T - y_T).  The line
+// through psi(T) evaluated at P = (xP, yP) in G1, scaled by w^3 (which lies in
+// a proper subfield and is erased by the final exponentiation), is
+//        l(P) = mu  +  (-lambda xP) v  +  yP v w
+// -- a sparse Fp12 element with only the coefficients (c0.c0, c0.c1, c1.c1)
+// set.  A pairing check then costs no G2 work at all on the hot path.
+#pragma once
+#include "fp2.cuh"
+#include "g1.cuh"
+
+namespace lw {
+
+struct Fp6 {
+  Fp2 c0, c1, c2;
+};
+struct Fp12 {
+  Fp6 c0, c1;
+};
+
+// ---------------------------------------------------------------- Fp6
+LW_DEV inline Fp6 fp6_zero() { Fp6 r; r.c0 = fp2_zero(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); return r; }
+LW_DEV inline Fp6 fp6_one() { Fp6 r; r.c0 = fp2_one(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); return r; }
+LW_DEV inline Fp6 fp6_add(const Fp6& a, const Fp6& b) { Fp6 r; r.c0 = fp2_add(a.c0, b.c0); r.c1 = fp2_add(a.c1, b.c1); r.c2 = fp2_add(a.c2, b.c2); return r; }
+LW_DEV inline Fp6 fp6_sub(const Fp6& a, const Fp6& b) { Fp6 r; r.c0 = fp2_sub(a.c0, b.c0); r.c1 = fp2_sub(a.c1, b.c1); r.c2 = fp2_sub(a.c2, b.c2); return r; }
+LW_DEV inline Fp6 fp6_neg(const Fp6& a) { Fp6 r; r.c0 = fp2_neg(a.c0); r.c1 = fp2_neg(a.c1); r.c2 = fp2_neg(a.c2); return r; }
+LW_DEV inline bool fp6_eq(const Fp6& a, const Fp6& b) { return fp2_eq(a.c0, b.c0) && fp2_eq(a.c1, b.c1) && fp2_eq(a.c2, b.c2); }
+// a * v
+LW_DEV inline Fp6 fp6_mul_v(const Fp6& a) { Fp6 r; r.c0 = fp2_mul_xi(a.c2); r.c1 = a.c0; r.c2 = a.c1; return r; }
+
+LW_DEV inline Fp6 fp6_mul(const Fp6& a, const Fp6& b) {
+  Fp2 t0 = fp2_mul(a.c0, b.c0), t1 = fp2_mul(a.c1, b.c1), t2 = fp2_mul(a.c2, b.c2);
+  Fp6 r;
+  r.c0 = fp2_add(t0, fp2_mul_xi(fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2)), t1), t2)));
+  r.c1 = fp2_add(fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1)), t0), t1), fp2_mul_xi(t2));
+  r.c2 = fp2_add(fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2)), t0), t2), t1);
+  return r;
+}
+LW_DEV inline Fp6 fp6_inv(const Fp6& a) {
+  Fp2 c0 = fp2_sub(fp2_sqr(a.c0), fp2_mul_xi(fp2_mul(a.c1, a.c2)));
+  Fp2 c1 = fp2_sub(fp2_mul_xi(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
+  Fp2 c2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
+  Fp2 t = fp2_add(fp2_mul(a.c0, c0), fp2_mul_xi(fp2_add(fp2_mul(a.c2, c1), fp2_mul(a.c1, c2))));
+  Fp2 ti = fp2_inv(t);
+  Fp6 r;
+  r.c0 = fp2_mul(c0, ti); r.c1 = fp2_mul(c1, ti); r.c2 = fp2_mul(c2, ti);
+  return r;
+}
+
+// ---------------------------------------------------------------- Fp12
+LW_DEV inline Fp12 fp12_one() { Fp12 r; r.c0 = fp6_one(); r.c1 = fp6_zero(); return r; }
+LW_DEV inline bool fp12_eq(const Fp12& a, const Fp12& b) { return fp6_eq(a.c0, b.c0) && fp6_eq(a.c1, b.c1); }
+LW_DEV inline bool fp12_is_one(const Fp12& a) { return fp12_eq(a, fp12_one()); }
+LW_DEV inline Fp12 fp12_conj(const Fp12& a) { Fp12 r; r.c0 = a.c0; r.c1 = fp6_neg(a.c1); return r; }
+LW_DEV inline Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
+  Fp6 t0 = fp6_mul(a.c0, b.c0), t1 = fp6_mul(a.c1, b.c1);
+  Fp12 r;
+  r.c1 = fp6_sub(fp6_sub(fp6_mul(fp6_add(a.c0, a.c1), fp6_add(b.c0, b.c1)), t0), t1);
+  r.c0 = fp6_add(t0, fp6_mul_v(t1));
+  return r;
+}
+LW_DEV inline Fp12 fp12_sqr(const Fp12& a) {
+  Fp6 t = fp6_mul(a.c0, a.c1);
+  Fp12 r;
+  r.c0 = fp6_sub(fp6_sub(fp6_mul(fp6_add(a.c0, a.c1), fp6_add(a.c0, fp6_mul_v(a.c1))), t), fp6_mul_v(t));
+  r.c1 = fp6_add(t, t);
+  return r;
+}
+LW_DEV inline Fp12 fp12_inv(const Fp12& a) {
+  Fp6 d = fp6_sub(fp6_mul(a.c0, a.c0), fp6_mul_v(fp6_mul(a.c1, a.c1)));
+  Fp6 di = fp6_inv(d);
+  Fp12 r;
+  r.c0 = fp6_mul(a.c0, di);
+  r.c1 = fp6_neg(fp6_mul(a.c1, di));
+  return r;
+}
+// f * (s0 + s1 v + s4 v w): the sparse line element.  With f = f0 + f1 w and
+// l = l0 + l1 w, l0 = s0 + s1 v, l1 = s4 v.
+LW_DEV inline Fp6 fp6_mul_by_01(const Fp6& a, const Fp2& s0, const Fp2& s1) {
+  // (a0 + a1 v + a2 v^2)(s0 + s1 v)
+  Fp2 t0 = fp2_mul(a.c0, s0), t1 = fp2_mul(a.c1, s1);
+  Fp6 r;
+  r.c0 = fp2_add(t0, fp2_mul_xi(fp2_mul(a.c2, s1)));
+  r.c1 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c1), fp2_add(s0, s1)), t0), t1);
+  r.c2 = fp2_add(fp2_mul(a.c2, s0), t1);
+  return r;
+}
+LW_DEV inline Fp6 fp6_mul_by_1(const Fp6& a, const Fp2& s1) {
+  // (a0 + a1 v + a2 v^2)(s1 v) = xi a2 s1 + a0 s1 v + a1 s1 v^2
+  Fp6 r;
+  r.c0 = fp2_mul_xi(fp2_mul(a.c2, s1));
+  r.c1 = fp2_mul(a.c0, s1);
+  r.c2 = fp2_mul(a.c1, s1);
+  return r;
+}
+LW_DEV inline Fp12 fp12_mul_by_014(const Fp12& f, const Fp2& s0, const Fp2& s1, const Fp2& s4) {
+  Fp6 aa = fp6_mul_by_01(f.c0, s0, s1);   // f0 l0
+  Fp6 bb = fp6_mul_by_1(f.c1, s4);        // f1 l1
+  Fp2 s14 = fp2_add(s1, s4);
+  Fp12 r;
+  r.c1 = fp6_sub(fp6_sub(fp6_mul_by_01(fp6_add(f.c0, f.c1), s0, s14), aa), bb);  // (f0+f1)(l0+l1) - f0l0 - f1l1
+  r.c0 = fp6_add(aa, fp6_mul_v(bb));
+  return r;
+}
+
+LW_DEV inline Fp2 frob_gamma(int i) {
+  Fp2 g;
+  const uint32_t* c0; const uint32_t* c1;
+  switch (i) {
+    case 1: c0 = k::FROB_G1_C0; c1 = k::FROB_G1_C1; break;
+    case 2: c0 = k::FROB_G2_C0; c1 = k::FROB_G2_C1; break;
+    case 3: c0 = k::FROB_G3_C0; c1 = k::FROB_G3_C1; break;
+    case 4: c0 = k::FROB_G4_C0; c1 = k::FROB_G4_C1; break;
+    default: c0 = k::FROB_G5_C0; c1 = k::FROB_G5_C1; break;
+  }
+  for (int j = 0; j < 12; j++) { g.c0.l[j] = c0[j]; g.c1.l[j] = c1[j]; }
+  return g;
+}
+// f^p: coefficient a_i of w^i maps to conj(a_i) * xi^(i (p-1)/6)
+LW_DEV inline Fp12 fp12_frobenius(const Fp12& a) {
+  Fp12 r;
+  r.c0.c0 = fp2_conj(a.c0.c0);                            // w^0
+  r.c1.c0 = fp2_mul(fp2_conj(a.c1.c0), frob_gamma(1));    // w^1
+  r.c0.c1 = fp2_mul(fp2_conj(a.c0.c1), frob_gamma(2));    // w^2
+  r.c1.c1 = fp2_mul(fp2_conj(a.c1.c1), frob_gamma(3));    // w^3
+  r.c0.c2 = fp2_mul(fp2_conj(a.c0.c2), frob_gamma(4));    // w^4
+  r.c1.c2 = fp2_mul(fp2_conj(a.c1.c2), frob_gamma(5));    // w^5
+  return r;
+}
+
+// ---------------------------------------------------------------- G2 lines
+constexpr int MILLER_STEPS = 68;  // 63 doublings + 5 additions for |x| = 0xd201000000010000
+struct G2Line {
+  Fp2 lambda, mu;
+};
+struct G2Prepared {
+  G2Line line[MILLER_STEPS];
+  int infinity;
+};
+
+LW_DEV inline void g2_prepare(G2Prepared& out, const G2Affine& q) {
+  out.infinity = 0;
+  Fp2 tx = q.x, ty = q.y;
+  int n = 0;
+  for (int bit = 62; bit >= 0; bit--) {
+    // tangent at T
+    Fp2 x2 = fp2_sqr(tx);
+    Fp2 num = fp2_add(fp2_dbl(x2), x2);
+    Fp2 lam = fp2_mul(num, fp2_inv(fp2_dbl(ty)));
+    out.line[n].lambda = lam;
+    out.line[n].mu = fp2_sub(fp2_mul(lam, tx), ty);
+    n++;
+    Fp2 x3 = fp2_sub(fp2_sqr(lam), fp2_dbl(tx));
+    Fp2 y3 = fp2_sub(fp2_mul(lam, fp2_sub(tx, x3)), ty);
+    tx = x3; ty = y3;
+    if ((k::BLS_X_ABS >> bit) & 1ull) {
+      // chord through T and Q
+      Fp2 lam2 = fp2_mul(fp2_sub(q.y, ty), fp2_inv(fp2_sub(q.x, tx)));
+      out.line[n].lambda = lam2;
+      out.line[n].mu = fp2_sub(fp2_mul(lam2, tx), ty);
+      n++;
+      Fp2 x4 = fp2_sub(fp2_sub(fp2_sqr(lam2), tx), q.x);
+      Fp2 y4 = fp2_sub(fp2_mul(lam2, fp2_sub(tx, x4)), ty);
+      tx = x4; ty = y4;
+    }
+  }
+}
+
+LW_DEV inline Fp12 line_mul(const Fp12& f, const G2Line& ln, const G1Affine& p) {
+  Fp2 s1 = fp2_neg(fp2_mul_fp(ln.lambda, p.x));
+  Fp2 s4; s4.c0 = p.y; s4.c1 = fp_zero();
+  return fp12_mul_by_014(f, ln.mu, s1, s4);
+}
+
+// product of Miller loops over pairs (P_i, Q_i); pairs with an infinite member
+// contribute 1 (App. D.5).
+LW_DEV inline Fp12 miller_loop(const G1Affine* ps, const G2Prepared* qs, int npairs) {
+  Fp12 f = fp12_one();
+  int n = 0;
+  for (int bit = 62; bit >= 0; bit--) {
+    f = fp12_sqr(f);
+    for (int i = 0; i < npairs; i++)
+      if (!g1a_is_inf(ps[i]) && !qs[i].infinity) f = line_mul(f, qs[i].line[n], ps[i]);
+    n++;
+    if ((k::BLS_X_ABS >> bit) & 1ull) {
+      for (int i = 0; i < npairs; i++)
+        if (!g1a_is_inf(ps[i]) && !qs[i].infinity) f = line_mul(f, qs[i].line[n], ps[i]);
+      n++;
+    }
+  }
+  return fp12_conj(f);  // x < 0
+}
+
+// g^|x| by square-and-multiply, then conjugate (x < 0; g is unitary after the easy part)
+LW_DEV inline Fp12 fp12_pow_x(const Fp12& g) {
+  Fp12 acc = g;
+  for (int bit = 62; bit >= 0; bit--) {
+    acc = fp12_sqr(acc);
+    if ((k::BLS_X_ABS >> bit) & 1ull) acc = fp12_mul(acc, g);
+  }
+  return fp12_conj(acc);
+}
+
+// f^(3 (p^12-1)/r).  The factor 3 is coprime to r, so "== 1" is unaffected.
+// Hard part: 3 (p^4-p^2+1)/r = (x-1)^2 (x+p) (x^2+p^2-1) + 3   (checked in
+// tests/test_host_emul.py).
+LW_DEV inline Fp12 final_exponentiation(const Fp12& f) {
+  // easy part: f^((p^6-1)(p^2+1))
+  Fp12 g = fp12_mul(fp12_conj(f), fp12_inv(f));
+  g = fp12_mul(fp12_frobenius(fp12_frobenius(g)), g);
+  // hard part
+  Fp12 a = fp12_mul(fp12_pow_x(g), fp12_conj(g));      // g^(x-1)
+  a = fp12_mul(fp12_pow_x(a), fp12_conj(a));           // g^((x-1)^2)
+  Fp12 b = fp12_mul(fp12_pow_x(a), fp12_frobenius(a)); // a^(x+p)
+  Fp12 c = fp12_mul(fp12_mul(fp12_pow_x(fp12_pow_x(b)), fp12_frobenius(fp12_frobenius(b))), fp12_conj(b));  // b^(x^2+p^2-1)
+  Fp12 g3 = fp12_mul(fp12_sqr(g), g);
+  return fp12_mul(c, g3);
+}
+
+LW_DEV inline bool pairing_product_is_one(const G1Affine* ps, const G2Prepared* qs, int npairs) {
+  return fp12_is_one(final_exponentiation(miller_loop(ps, qs, npairs)));
+}
+
+}  // namespace lw

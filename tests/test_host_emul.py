@@ -1,0 +1,283 @@
+"""CPU tier: the device math headers (compiled for the host with the PTX
+primitives emulated) against the Python big-int oracle."""
+import ctypes
+import hashlib
+import random
+
+import pytest
+
+from oracle.py import bls, kzg
+from tests import _emul
+from tests._emul import aff_bytes, aff_from, from_u32, u32
+
+P, R = bls.P, bls.R
+RP, RR = 1 << 384, 1 << 256
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _emul.load()
+
+
+EDGE_P = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << 380), (1 << 380) - 1]
+EDGE_R = [0, 1, 2, R - 1, R - 2, (R - 1) // 2, (1 << 254), (1 << 254) - 1]
+
+
+def test_fp_ops(lib):
+    rnd = random.Random(1)
+    vals = EDGE_P + [rnd.randrange(P) for _ in range(200)]
+    out = (ctypes.c_uint32 * 12)()
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        lib.emul_fp_mul(out, u32(a, 12), u32(b, 12))
+        assert from_u32(out) == a * b * pow(RP, -1, P) % P
+        lib.emul_fp_add(out, u32(a, 12), u32(b, 12))
+        assert from_u32(out) == (a + b) % P
+        lib.emul_fp_sub(out, u32(a, 12), u32(b, 12))
+        assert from_u32(out) == (a - b) % P
+        lib.emul_fp_neg(out, u32(a, 12))
+        assert from_u32(out) == (-a) % P
+        lib.emul_fp_to_mont(out, u32(a, 12))
+        assert from_u32(out) == a * RP % P
+        lib.emul_fp_from_mont(out, u32(a, 12))
+        assert from_u32(out) == a * pow(RP, -1, P) % P
+
+
+def test_fr_ops(lib):
+    rnd = random.Random(2)
+    vals = EDGE_R + [rnd.randrange(R) for _ in range(200)]
+    out = (ctypes.c_uint32 * 8)()
+    for i, a in enumerate(vals):
+        b = vals[(i * 5 + 1) % len(vals)]
+        lib.emul_fr_mul(out, u32(a, 8), u32(b, 8))
+        assert from_u32(out) == a * b * pow(RR, -1, R) % R
+        lib.emul_fr_add(out, u32(a, 8), u32(b, 8))
+        assert from_u32(out) == (a + b) % R
+        lib.emul_fr_sub(out, u32(a, 8), u32(b, 8))
+        assert from_u32(out) == (a - b) % R
+
+
+def test_inversions(lib):
+    rnd = random.Random(3)
+    out = (ctypes.c_uint32 * 12)()
+    for a in [1, 2, P - 1, rnd.randrange(P), rnd.randrange(P)]:
+        lib.emul_fp_inv(out, u32(a * RP % P, 12))
+        assert from_u32(out) == pow(a, -1, P) * RP % P
+    out8 = (ctypes.c_uint32 * 8)()
+    for a in [1, 2, R - 1, rnd.randrange(R)]:
+        lib.emul_fr_inv(out8, u32(a * RR % R, 8))
+        assert from_u32(out8) == pow(a, -1, R) * RR % R
+
+
+def test_fr_from_be(lib):
+    rnd = random.Random(4)
+    out = (ctypes.c_uint32 * 8)()
+    cases = [0, 1, R - 1, R, R + 1, 2 * R - 1, 2 * R, 2 * R + 5, (1 << 256) - 1] + [rnd.randrange(1 << 256) for _ in range(100)]
+    for v in cases:
+        b = v.to_bytes(32, "big")
+        lib.emul_fr_from_be32(out, b)
+        assert from_u32(out) == v % R
+        lib.emul_fr_from_be_words(out, b)
+        assert from_u32(out) == v % R
+
+
+def _rand_pt(rnd):
+    return bls.g1_mul(bls.G1, rnd.randrange(1, R))
+
+
+def test_g1_ops(lib):
+    rnd = random.Random(5)
+    out = (ctypes.c_uint8 * 96)()
+    pts = [None, bls.G1, bls.g1_neg(bls.G1)] + [_rand_pt(rnd) for _ in range(6)]
+    for a in pts:
+        for b in pts + [a, bls.g1_neg(a)]:
+            want = bls.g1_add(a, b)
+            for op in (0, 1, 3):
+                lib.emul_g1_op(out, aff_bytes(a), aff_bytes(b), op)
+                assert aff_from(out) == want, (op, a is None, b is None)
+        lib.emul_g1_op(out, aff_bytes(a), aff_bytes(a), 2)
+        assert aff_from(out) == bls.g1_add(a, a)
+
+
+def test_g1_scalar_mul(lib):
+    rnd = random.Random(6)
+    out = (ctypes.c_uint8 * 96)()
+    p = _rand_pt(rnd)
+    for k in [0, 1, 2, 3, R - 1, R, rnd.randrange(R), rnd.randrange(1 << 256)]:
+        lib.emul_g1_mul(out, aff_bytes(p), u32(k, 8))
+        assert aff_from(out) == bls.g1_mul(p, k)
+
+
+def _curve_point_not_in_subgroup(rnd):
+    while True:
+        x = rnd.randrange(P)
+        y = bls.fp_sqrt(x * x * x + 4)
+        if y is not None:
+            pt = (x, y)
+            if not bls.g1_in_subgroup(pt):
+                return pt
+
+
+def test_subgroup_check(lib):
+    rnd = random.Random(7)
+    for _ in range(4):
+        assert lib.emul_g1_in_subgroup(aff_bytes(_rand_pt(rnd))) == 1
+    assert lib.emul_g1_in_subgroup(aff_bytes(None)) == 1
+    for _ in range(8):
+        pt = _curve_point_not_in_subgroup(rnd)
+        assert lib.emul_g1_on_curve(aff_bytes(pt)) == 1
+        assert lib.emul_g1_in_subgroup(aff_bytes(pt)) == 0
+    # small-order points: cofactor h = (x-1)^2/3; [r*h/3 ...] -- take h-torsion
+    h = (bls.BLS_X + 1) ** 2 // 3  # (x-1)^2/3 with x negative
+    pt = _curve_point_not_in_subgroup(rnd)
+    tors = bls.g1_mul(pt, R)  # kills the G1 component, leaves the cofactor part
+    assert tors is not None and bls.g1_mul(tors, h) is None
+    assert lib.emul_g1_in_subgroup(aff_bytes(tors)) == 0
+    assert lib.emul_g1_on_curve(aff_bytes((0, 2))) == 1  # compression.rs:160-165
+    assert lib.emul_g1_in_subgroup(aff_bytes((0, 2))) == 0
+
+
+def test_codec(lib):
+    rnd = random.Random(8)
+    out48 = (ctypes.c_uint8 * 48)()
+    out96 = (ctypes.c_uint8 * 96)()
+    for pt in [None, bls.G1, bls.g1_neg(bls.G1)] + [_rand_pt(rnd) for _ in range(5)]:
+        lib.emul_g1_compress(out48, aff_bytes(pt))
+        assert bytes(out48) == bls.g1_compress(pt)
+        assert lib.emul_g1_decompress(out96, bytes(out48)) == 1
+        assert aff_from(out96) == pt
+    # rejection / laxness parity with the Python restatement of compression.rs
+    bad = [bytes(48), bytes([0x40]) + bytes(47), bytes([0x80]) + bytes(47), bytes([0xE0]) + b"\x01" * 47]
+    x_off = next(x for x in range(2, 50) if bls.fp_sqrt(x**3 + 4) is None)
+    bad.append(bytes([0x80]) + x_off.to_bytes(47, "big"))
+    ns = _curve_point_not_in_subgroup(rnd)
+    bad.append(bls.g1_compress(ns))
+    xg = bls.G1_X + P  # non-canonical x >= p (accepted & reduced by the reference)
+    if xg < (1 << 381):
+        b = bytearray(xg.to_bytes(48, "big")); b[0] |= 0x80; bad.append(bytes(b))
+    for b in bad:
+        try:
+            want = bls.g1_decompress(b)
+            ok = 1
+        except bls.PointError:
+            want, ok = None, 0
+        got = lib.emul_g1_decompress(out96, b)
+        assert got == ok, b.hex()
+        if ok:
+            assert aff_from(out96) == want
+
+
+def test_sha256(lib):
+    rnd = random.Random(9)
+    out = (ctypes.c_uint8 * 32)()
+    for ln in [0, 1, 55, 56, 63, 64, 65, 119, 120, 127, 128, 1000, 131152]:
+        msg = bytes(rnd.randrange(256) for _ in range(ln))
+        lib.emul_sha256(out, msg, ctypes.c_size_t(ln))
+        assert bytes(out) == hashlib.sha256(msg).digest()
+
+
+@pytest.mark.parametrize("c", [4, 8, 10, 12, 13, 14, 15, 16])
+def test_recode(lib, c):
+    rnd = random.Random(10 + c)
+    nwin = 255 // c + 1
+    digits = (ctypes.c_int32 * nwin)()
+    for k in [0, 1, R - 1, R - 2, (1 << 254) - 1] + [rnd.randrange(R) for _ in range(200)]:
+        lib.emul_recode(digits, u32(k, 8), c, nwin)
+        d = list(digits)
+        assert sum(x << (c * j) for j, x in enumerate(d)) == k
+        assert all(-(1 << (c - 1)) < x <= (1 << (c - 1)) for x in d)
+
+
+@pytest.mark.parametrize("chunks", [1, 4, 32, 128])
+def test_poly_eval_quot(lib, chunks):
+    rnd = random.Random(11)
+    n = 4096
+    for trial in range(2):
+        coeffs = [rnd.randrange(R) for _ in range(n)]
+        if trial == 1:
+            coeffs[100:] = [0] * (n - 100)
+        z = rnd.randrange(R)
+        arr = (ctypes.c_uint32 * (8 * n))()
+        for i, cf in enumerate(coeffs):
+            for j in range(8):
+                arr[8 * i + j] = (cf >> (32 * j)) & 0xFFFFFFFF
+        y8 = (ctypes.c_uint32 * 8)()
+        q = (ctypes.c_uint32 * (8 * n))()
+        lib.emul_poly_eval_quot(y8, q, arr, n, u32(z, 8), chunks)
+        assert from_u32(y8) == kzg.horner(coeffs, z)
+        want = kzg.ruffini(coeffs, z) + [0]
+        got = [from_u32(q[8 * i : 8 * i + 8]) for i in range(n)]
+        assert got == want
+
+
+# ------------------------------------------------------------------ pairing
+def _g2_bytes(q):
+    (x0, x1), (y0, y1) = q
+    return b"".join(v.to_bytes(48, "big") for v in (x0, x1, y0, y1))
+
+
+def _tower_to_flat(raw576):
+    """emul Fp12 memory order: c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2 (each Fp2 = c0, c1)
+    -> coefficients of the flat basis of oracle/py/pairing.py."""
+    vals = [int.from_bytes(raw576[48 * i : 48 * i + 48], "big") for i in range(12)]
+    wpow = [0, 2, 4, 1, 3, 5]
+    flat = [0] * 12
+    for slot, i in enumerate(wpow):
+        a0, a1 = vals[2 * slot], vals[2 * slot + 1]
+        flat[i] = (flat[i] + a0 - a1) % P
+        flat[i + 6] = (flat[i + 6] + a1) % P
+    return tuple(flat)
+
+
+def test_hard_part_identity():
+    x = -bls.BLS_X
+    assert 3 * ((P**4 - P**2 + 1) // R) == (x - 1) ** 2 * (x + P) * (x * x + P * P - 1) + 3
+
+
+def test_g2_decompress(lib, setup_text):
+    lines = setup_text.splitlines()
+    out = (ctypes.c_uint8 * 192)()
+    for ln in lines[2 + 4096 : 2 + 4096 + 4]:
+        raw = bytes.fromhex(ln)
+        assert lib.emul_g2_decompress(out, raw) == 1
+        q = bls.g2_decompress(raw)
+        assert bytes(out) == _g2_bytes(q)
+        # flipped sign bit -> negated y
+        raw2 = bytes([raw[0] ^ 0x20]) + raw[1:]
+        assert lib.emul_g2_decompress(out, raw2) == 1
+        assert bytes(out) == _g2_bytes(bls.g2_neg(q))
+    assert lib.emul_g2_decompress(out, bytes([0xC0]) + bytes(95)) == 2
+    assert lib.emul_g2_decompress(out, bytes(96)) == 0
+
+
+def test_pairing_matches_oracle(lib, py_setup):
+    from oracle.py import pairing as pr
+
+    rnd = random.Random(12)
+    out = (ctypes.c_uint8 * 576)()
+    q = py_setup.g2[0]
+    for k in (1, rnd.randrange(R)):
+        p = bls.g1_mul(bls.G1, k)
+        lib.emul_pairing_gt(out, aff_bytes(p), _g2_bytes(q))
+        got = _tower_to_flat(bytes(out))
+        e = pr.pairing(p, q)
+        # device: conj(f)^(3 (p^12-1)/r) == e^-3
+        assert pr.mul(got, pr.fpow(e, 3)) == pr.ONE
+
+
+def test_pairing_check(lib, py_setup):
+    rnd = random.Random(13)
+    g2_0, g2_1 = py_setup.g2[0], py_setup.g2[1]
+    tau = py_setup.tau
+    for _ in range(2):
+        a = rnd.randrange(1, R)
+        A = bls.g1_mul(bls.G1, a)
+        tA = bls.g1_mul(A, tau)
+        # e(tau A, g2_0) * e(-A, g2_1) == 1
+        assert lib.emul_pairing_check(aff_bytes(tA), _g2_bytes(g2_0), aff_bytes(bls.g1_neg(A)), _g2_bytes(g2_1)) == 1
+        assert lib.emul_pairing_check(aff_bytes(tA), _g2_bytes(g2_0), aff_bytes(A), _g2_bytes(g2_1)) == 0
+        wrong = bls.g1_mul(A, tau + 1)
+        assert lib.emul_pairing_check(aff_bytes(wrong), _g2_bytes(g2_0), aff_bytes(bls.g1_neg(A)), _g2_bytes(g2_1)) == 0
+    # infinity pairs contribute 1
+    assert lib.emul_pairing_check(aff_bytes(None), _g2_bytes(g2_0), aff_bytes(None), _g2_bytes(g2_1)) == 1
+    assert lib.emul_pairing_check(aff_bytes(bls.G1), _g2_bytes(g2_0), aff_bytes(None), _g2_bytes(g2_1)) == 0
