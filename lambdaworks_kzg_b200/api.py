@@ -1,0 +1,315 @@
+"""ctypes binding of include/lwkzg.h (see package docstring)."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+C_KZG_OK, C_KZG_BADARGS, C_KZG_ERROR, C_KZG_MALLOC = 0, 1, 2, 3
+BYTES_PER_BLOB = 4096 * 32
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class KzgError(Exception):
+    """A C ABI call returned something other than C_KZG_OK."""
+
+    def __init__(self, code: int, where: str, detail: str = ""):
+        super().__init__("%s -> C_KZG_RET %d%s" % (where, code, (": " + detail) if detail else ""))
+        self.code = code
+
+
+class _FFTSettings(ctypes.Structure):
+    _fields_ = [("max_width", ctypes.c_uint64), ("expanded_roots_of_unity", ctypes.c_void_p),
+                ("reverse_roots_of_unity", ctypes.c_void_p), ("roots_of_unity", ctypes.c_void_p)]
+
+
+class CKZGSettings(ctypes.Structure):
+    """KZGSettings, /root/reference/src/lib.rs:210-222."""
+    _fields_ = [("fs", ctypes.c_void_p), ("g1_values", ctypes.c_void_p), ("g2_values", ctypes.c_void_p)]
+
+
+def lib_path() -> str:
+    return os.environ.get("LWKZG_LIB", os.path.join(_HERE, "liblwkzg_b200.so"))
+
+
+def load_library() -> ctypes.CDLL:
+    """Load liblwkzg_b200.so; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    vp, sz, ip = ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)
+    sp = ctypes.POINTER(CKZGSettings)
+    bp = ctypes.POINTER(ctypes.c_bool)
+    sig = {
+        "load_trusted_setup": [sp, vp, sz, vp, sz],
+        "load_trusted_setup_file": [sp, vp],
+        "free_trusted_setup": [sp],
+        "blob_to_kzg_commitment": [vp, vp, sp],
+        "compute_kzg_proof": [vp, vp, vp, vp, sp],
+        "compute_blob_kzg_proof": [vp, vp, vp, sp],
+        "verify_kzg_proof": [bp, vp, vp, vp, vp, sp],
+        "verify_blob_kzg_proof": [bp, vp, vp, vp, sp],
+        "verify_blob_kzg_proof_batch": [bp, vp, vp, vp, sz, sp],
+        "lwkzg_blob_to_kzg_commitment_batch": [vp, vp, sz, sp, ip],
+        "lwkzg_compute_blob_kzg_proof_batch": [vp, vp, vp, sz, sp, ip],
+        "lwkzg_compute_kzg_proof_batch": [vp, vp, vp, vp, sz, sp, ip],
+        "lwkzg_commit_and_prove_batch": [vp, vp, vp, sz, sp, ip],
+        "lwkzg_commit_and_prove_batch_device": [vp, vp, vp, sz, sp, vp, vp],
+        "lwkzg_blob_to_kzg_commitment_batch_device": [vp, vp, sz, sp, vp],
+        "lwkzg_compute_blob_kzg_proof_batch_device": [vp, vp, vp, sz, sp, vp, vp],
+        "lwkzg_g1_lincomb": [vp, vp, vp, sz],
+        "lwkzg_verify_batch_phase1": [vp, vp, vp, vp, sz, sp],
+        "lwkzg_verify_batch_phase2": [vp, vp, sz, sz, sz, sp],
+        "lwkzg_verify_batch_phase3": [bp, vp, sz, sp],
+        "lwkzg_synth_blobs_device": [vp, ctypes.c_uint64, sz, vp],
+        "lwkzg_synth_blob_host": [vp, ctypes.c_uint64],
+        "lwkzg_set_option": [ctypes.c_char_p, ctypes.c_long],
+        "lwkzg_get_option": [ctypes.c_char_p],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    lib.lwkzg_synth_blob_host.restype = None
+    lib.lwkzg_get_option.restype = ctypes.c_long
+    lib.lwkzg_imad_peak.argtypes = [ctypes.c_int]
+    lib.lwkzg_imad_peak.restype = ctypes.c_double
+    lib.lwkzg_kernel_launches.argtypes = []
+    lib.lwkzg_kernel_launches.restype = ctypes.c_uint64
+    lib.lwkzg_last_error.argtypes = []
+    lib.lwkzg_last_error.restype = ctypes.c_char_p
+    lib.lwkzg_version.argtypes = []
+    lib.lwkzg_version.restype = ctypes.c_char_p
+    _LIB = lib
+    return lib
+
+
+def last_error() -> str:
+    return load_library().lwkzg_last_error().decode()
+
+
+def _check(code: int, where: str):
+    if code != C_KZG_OK:
+        raise KzgError(code, where, last_error())
+
+
+def set_option(name: str, value: int):
+    if load_library().lwkzg_set_option(name.encode(), int(value)) != 0:
+        raise ValueError("bad option %s=%r" % (name, value))
+
+
+def get_option(name: str) -> int:
+    return int(load_library().lwkzg_get_option(name.encode()))
+
+
+def kernel_launches() -> int:
+    return int(load_library().lwkzg_kernel_launches())
+
+
+def imad_peak(variant: int = 0) -> float:
+    """Measured MAC32/s of the integer pipe (roofline denominator R_int)."""
+    return float(load_library().lwkzg_imad_peak(variant))
+
+
+class Settings:
+    """Owns a C ``KZGSettings`` produced by the library's loaders."""
+
+    def __init__(self):
+        self.c = CKZGSettings()
+        self._loaded = False
+
+    @property
+    def ptr(self):
+        return ctypes.byref(self.c)
+
+    def free(self):
+        if self._loaded:
+            load_library().free_trusted_setup(self.ptr)
+            self._loaded = False
+
+    def g1_values_bytes(self) -> bytes:
+        return ctypes.string_at(self.c.g1_values, 4096 * 144)
+
+    def g2_values_bytes(self) -> bytes:
+        return ctypes.string_at(self.c.g2_values, 65 * 288)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def load_trusted_setup_file(path: str) -> Settings:
+    """load_trusted_setup_file(KZGSettings*, FILE*) -- lib.rs:779-802."""
+    lib = load_library()
+    libc = ctypes.CDLL(None)
+    libc.fopen.restype = ctypes.c_void_p
+    libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    libc.fclose.argtypes = [ctypes.c_void_p]
+    fp = libc.fopen(path.encode(), b"rb")
+    if not fp:
+        raise FileNotFoundError(path)
+    s = Settings()
+    try:
+        _check(lib.load_trusted_setup_file(s.ptr, fp), "load_trusted_setup_file")
+    finally:
+        libc.fclose(fp)
+    s._loaded = True
+    return s
+
+
+def load_trusted_setup(g1_bytes: bytes, g2_bytes: bytes, n1: Optional[int] = None, n2: Optional[int] = None) -> Settings:
+    """load_trusted_setup -- lib.rs:709-776."""
+    lib = load_library()
+    n1 = len(g1_bytes) // 48 if n1 is None else n1
+    n2 = len(g2_bytes) // 96 if n2 is None else n2
+    s = Settings()
+    _check(lib.load_trusted_setup(s.ptr, g1_bytes, n1, g2_bytes, n2), "load_trusted_setup")
+    s._loaded = True
+    return s
+
+
+def _sp(s):
+    return s.ptr if isinstance(s, Settings) else ctypes.byref(s)
+
+
+def blob_to_kzg_commitment(blob: bytes, s) -> bytes:
+    assert len(blob) == BYTES_PER_BLOB
+    out = ctypes.create_string_buffer(48)
+    _check(load_library().blob_to_kzg_commitment(out, blob, _sp(s)), "blob_to_kzg_commitment")
+    return out.raw
+
+
+def compute_kzg_proof(blob: bytes, z_bytes: bytes, s) -> Tuple[bytes, bytes]:
+    assert len(blob) == BYTES_PER_BLOB and len(z_bytes) == 32
+    proof = ctypes.create_string_buffer(48)
+    y = ctypes.create_string_buffer(32)
+    _check(load_library().compute_kzg_proof(proof, y, blob, z_bytes, _sp(s)), "compute_kzg_proof")
+    return proof.raw, y.raw
+
+
+def compute_blob_kzg_proof(blob: bytes, commitment: bytes, s) -> bytes:
+    assert len(blob) == BYTES_PER_BLOB and len(commitment) == 48
+    out = ctypes.create_string_buffer(48)
+    _check(load_library().compute_blob_kzg_proof(out, blob, commitment, _sp(s)), "compute_blob_kzg_proof")
+    return out.raw
+
+
+def verify_kzg_proof(commitment: bytes, z_bytes: bytes, y_bytes: bytes, proof: bytes, s) -> bool:
+    ok = ctypes.c_bool(False)
+    _check(load_library().verify_kzg_proof(ctypes.byref(ok), commitment, z_bytes, y_bytes, proof, _sp(s)), "verify_kzg_proof")
+    return bool(ok.value)
+
+
+def verify_blob_kzg_proof(blob: bytes, commitment: bytes, proof: bytes, s) -> bool:
+    ok = ctypes.c_bool(False)
+    _check(load_library().verify_blob_kzg_proof(ctypes.byref(ok), blob, commitment, proof, _sp(s)), "verify_blob_kzg_proof")
+    return bool(ok.value)
+
+
+def _cat(items: Sequence[bytes], each: int) -> bytes:
+    b = b"".join(items)
+    assert len(b) == each * len(items)
+    return b
+
+
+def verify_blob_kzg_proof_batch(blobs: Sequence[bytes], commitments: Sequence[bytes], proofs: Sequence[bytes], s) -> bool:
+    n = len(blobs)
+    ok = ctypes.c_bool(False)
+    code = load_library().verify_blob_kzg_proof_batch(ctypes.byref(ok), _cat(blobs, BYTES_PER_BLOB), _cat(commitments, 48), _cat(proofs, 48), n, _sp(s))
+    _check(code, "verify_blob_kzg_proof_batch")
+    return bool(ok.value)
+
+
+# ------------------------------------------------------------------ batch extensions (host buffers)
+def _status_list(n):
+    return (ctypes.c_int * max(n, 1))()
+
+
+def blob_to_kzg_commitment_batch(blobs: bytes, n: int, s) -> Tuple[List[bytes], List[int]]:
+    out = ctypes.create_string_buffer(48 * max(n, 1))
+    st = _status_list(n)
+    _check(load_library().lwkzg_blob_to_kzg_commitment_batch(out, blobs, n, _sp(s), st), "lwkzg_blob_to_kzg_commitment_batch")
+    return [out.raw[48 * i: 48 * i + 48] for i in range(n)], list(st)[:n]
+
+
+def compute_blob_kzg_proof_batch(blobs: bytes, commitments: bytes, n: int, s) -> Tuple[List[bytes], List[int]]:
+    out = ctypes.create_string_buffer(48 * max(n, 1))
+    st = _status_list(n)
+    _check(load_library().lwkzg_compute_blob_kzg_proof_batch(out, blobs, commitments, n, _sp(s), st), "lwkzg_compute_blob_kzg_proof_batch")
+    return [out.raw[48 * i: 48 * i + 48] for i in range(n)], list(st)[:n]
+
+
+def compute_kzg_proof_batch(blobs: bytes, zs: bytes, n: int, s):
+    proofs = ctypes.create_string_buffer(48 * max(n, 1))
+    ys = ctypes.create_string_buffer(32 * max(n, 1))
+    st = _status_list(n)
+    _check(load_library().lwkzg_compute_kzg_proof_batch(proofs, ys, blobs, zs, n, _sp(s), st), "lwkzg_compute_kzg_proof_batch")
+    return ([proofs.raw[48 * i: 48 * i + 48] for i in range(n)], [ys.raw[32 * i: 32 * i + 32] for i in range(n)], list(st)[:n])
+
+
+def commit_and_prove_batch(blobs, n: int, s, out_commitments=None, out_proofs=None):
+    """blobs / outputs may be bytes-like objects or integer host addresses
+    (e.g. a pinned torch tensor's data_ptr())."""
+    lib = load_library()
+    own = out_commitments is None
+    if own:
+        out_commitments = ctypes.create_string_buffer(48 * max(n, 1))
+        out_proofs = ctypes.create_string_buffer(48 * max(n, 1))
+    st = _status_list(n)
+    _check(lib.lwkzg_commit_and_prove_batch(out_commitments, out_proofs, blobs, n, _sp(s), st), "lwkzg_commit_and_prove_batch")
+    if own:
+        return ([out_commitments.raw[48 * i: 48 * i + 48] for i in range(n)],
+                [out_proofs.raw[48 * i: 48 * i + 48] for i in range(n)], list(st)[:n])
+    return list(st)[:n]
+
+
+def g1_lincomb(points_xy_be: bytes, scalars_be: bytes, n: int) -> bytes:
+    out = ctypes.create_string_buffer(48)
+    _check(load_library().lwkzg_g1_lincomb(out, points_xy_be, scalars_be, n), "lwkzg_g1_lincomb")
+    return out.raw
+
+
+# ------------------------------------------------------------------ device-pointer helpers
+def commit_and_prove_batch_device(d_commitments: int, d_proofs: int, d_blobs: int, n: int, s, stream: int = 0, d_status: int = 0):
+    """All arguments are raw device addresses (torch: tensor.data_ptr()) and a
+    cudaStream_t handle (torch: torch.cuda.current_stream().cuda_stream)."""
+    _check(load_library().lwkzg_commit_and_prove_batch_device(d_commitments, d_proofs, d_blobs, n, _sp(s), stream, d_status),
+           "lwkzg_commit_and_prove_batch_device")
+
+
+def synth_blobs_device(d_blobs: int, first_blob: int, n: int, stream: int = 0):
+    _check(load_library().lwkzg_synth_blobs_device(d_blobs, first_blob, n, stream), "lwkzg_synth_blobs_device")
+
+
+def synth_blob_host(k: int) -> bytes:
+    buf = ctypes.create_string_buffer(BYTES_PER_BLOB)
+    load_library().lwkzg_synth_blob_host(buf, k)
+    return buf.raw
+
+
+# ------------------------------------------------------------------ multi-GPU verification phases
+def verify_batch_phase1(blobs: bytes, commitments: bytes, proofs: bytes, n_local: int, s) -> bytes:
+    out = ctypes.create_string_buffer(160 * max(n_local, 1))
+    _check(load_library().lwkzg_verify_batch_phase1(out, blobs, commitments, proofs, n_local, _sp(s)), "lwkzg_verify_batch_phase1")
+    return out.raw[: 160 * n_local]
+
+
+def verify_batch_phase2(all_tuples: bytes, n_total: int, first: int, n_local: int, s) -> bytes:
+    out = ctypes.create_string_buffer(288)
+    _check(load_library().lwkzg_verify_batch_phase2(out, all_tuples, n_total, first, n_local, _sp(s)), "lwkzg_verify_batch_phase2")
+    return out.raw
+
+
+def verify_batch_phase3(partials: bytes, n_ranks: int, s) -> bool:
+    ok = ctypes.c_bool(False)
+    _check(load_library().lwkzg_verify_batch_phase3(ctypes.byref(ok), partials, n_ranks, _sp(s)), "lwkzg_verify_batch_phase3")
+    return bool(ok.value)

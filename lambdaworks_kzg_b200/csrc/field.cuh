@@ -43,15 +43,10 @@ LW_INL Fp fp_cneg(const Fp& a, bool neg) {
 }
 
 // Out-of-line variants for cold, code-size-heavy callers (tower fields, pow).
-#if defined(LWKZG_HOST_EMUL)
-#define LW_NOINLINE
-#else
-#define LW_NOINLINE __device__ __noinline__
-#endif
-LW_NOINLINE void fp_mul_ni(Fp& r, const Fp& a, const Fp& b) { Fp t; mont_mul<FpCfg>(t.l, a.l, b.l); r = t; }
-LW_NOINLINE void fp_sqr_ni(Fp& r, const Fp& a) { Fp t; mont_sqr<FpCfg>(t.l, a.l); r = t; }
+LW_COLD void fp_mul_ni(Fp& r, const Fp& a, const Fp& b) { Fp t; mont_mul<FpCfg>(t.l, a.l, b.l); r = t; }
+LW_COLD void fp_sqr_ni(Fp& r, const Fp& a) { Fp t; mont_sqr<FpCfg>(t.l, a.l); r = t; }
 
-LW_DEV inline Fp fp_pow_const(const Fp& a, const uint32_t* e, int ne) {
+LW_COLD Fp fp_pow_const(const Fp& a, const uint32_t* e, int ne) {
   Fp acc = fp_one();
   bool started = false;
   for (int w = ne - 1; w >= 0; w--) {
@@ -66,9 +61,9 @@ LW_DEV inline Fp fp_pow_const(const Fp& a, const uint32_t* e, int ne) {
   }
   return acc;
 }
-LW_DEV inline Fp fp_inv(const Fp& a) { return fp_pow_const(a, k::FP_P_MINUS_2, 12); }  // 0 -> 0
+LW_COLD Fp fp_inv(const Fp& a) { return fp_pow_const(a, k::FP_P_MINUS_2, 12); }  // 0 -> 0
 // sqrt candidate a^((p+1)/4); caller must check candidate^2 == a
-LW_DEV inline Fp fp_sqrt_candidate(const Fp& a) { return fp_pow_const(a, k::FP_SQRT_EXP, 12); }
+LW_COLD Fp fp_sqrt_candidate(const Fp& a) { return fp_pow_const(a, k::FP_SQRT_EXP, 12); }
 
 LW_INL Fp fp_to_mont(const Fp& a) { Fp r2, r; for (int i = 0; i < 12; i++) r2.l[i] = k::FP_R2[i]; mont_mul<FpCfg>(r.l, a.l, r2.l); return r; }
 LW_INL Fp fp_from_mont(const Fp& a) { Fp one = fp_zero(), r; one.l[0] = 1; mont_mul<FpCfg>(r.l, a.l, one.l); return r; }
@@ -113,7 +108,7 @@ LW_INL Fr fr_sqr(const Fr& a) { Fr r; mont_sqr<FrCfg>(r.l, a.l); return r; }
 LW_INL Fr fr_to_mont(const Fr& a) { Fr r2, r; for (int i = 0; i < 8; i++) r2.l[i] = k::FR_R2[i]; mont_mul<FrCfg>(r.l, a.l, r2.l); return r; }
 LW_INL Fr fr_from_mont(const Fr& a) { Fr one = fr_zero(), r; one.l[0] = 1; mont_mul<FrCfg>(r.l, a.l, one.l); return r; }
 
-LW_DEV inline Fr fr_pow_const(const Fr& a, const uint32_t* e, int ne) {
+LW_COLD Fr fr_pow_const(const Fr& a, const uint32_t* e, int ne) {
   Fr acc = fr_one();
   bool started = false;
   for (int w = ne - 1; w >= 0; w--) {
@@ -125,7 +120,7 @@ LW_DEV inline Fr fr_pow_const(const Fr& a, const uint32_t* e, int ne) {
   }
   return acc;
 }
-LW_DEV inline Fr fr_inv(const Fr& a) { return fr_pow_const(a, k::FR_R_MINUS_2, 8); }
+LW_COLD Fr fr_inv(const Fr& a) { return fr_pow_const(a, k::FR_R_MINUS_2, 8); }
 
 // 8 big-endian u32 words as they sit in memory (w[0] = most significant 4
 // bytes, still in memory byte order) -> canonical Fr integer, reduced mod r

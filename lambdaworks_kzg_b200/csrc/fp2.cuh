@@ -23,7 +23,7 @@ LW_INL Fp2 fp2_dbl(const Fp2& a) { Fp2 r; r.c0 = fp_dbl(a.c0); r.c1 = fp_dbl(a.c
 LW_INL Fp2 fp2_conj(const Fp2& a) { Fp2 r; r.c0 = a.c0; r.c1 = fp_neg(a.c1); return r; }
 
 // (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u
-LW_DEV inline Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+LW_COLD Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
   Fp t0, t1, t2;
   fp_mul_ni(t0, a.c0, b.c0);
   fp_mul_ni(t1, a.c1, b.c1);
@@ -35,7 +35,7 @@ LW_DEV inline Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
   return r;
 }
 // (a0 + a1 u)^2 = (a0 + a1)(a0 - a1) + 2 a0 a1 u
-LW_DEV inline Fp2 fp2_sqr(const Fp2& a) {
+LW_COLD Fp2 fp2_sqr(const Fp2& a) {
   Fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t0, t1;
   fp_mul_ni(t0, s, d);
   fp_mul_ni(t1, a.c0, a.c1);
@@ -44,7 +44,7 @@ LW_DEV inline Fp2 fp2_sqr(const Fp2& a) {
   r.c1 = fp_dbl(t1);
   return r;
 }
-LW_DEV inline Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) {
+LW_COLD Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) {
   Fp2 r;
   fp_mul_ni(r.c0, a.c0, k);
   fp_mul_ni(r.c1, a.c1, k);
@@ -52,7 +52,7 @@ LW_DEV inline Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) {
 }
 // multiply by the non-residue xi = 1 + u:  (a0 - a1) + (a0 + a1) u
 LW_INL Fp2 fp2_mul_xi(const Fp2& a) { Fp2 r; r.c0 = fp_sub(a.c0, a.c1); r.c1 = fp_add(a.c0, a.c1); return r; }
-LW_DEV inline Fp2 fp2_inv(const Fp2& a) {
+LW_COLD Fp2 fp2_inv(const Fp2& a) {
   Fp t0, t1;
   fp_sqr_ni(t0, a.c0);
   fp_sqr_ni(t1, a.c1);
@@ -66,7 +66,7 @@ LW_DEV inline Fp2 fp2_inv(const Fp2& a) {
 }
 
 // Square root in Fp; returns false if `a` is a non-residue.
-LW_DEV inline bool fp_sqrt(Fp& out, const Fp& a) {
+LW_COLD bool fp_sqrt(Fp& out, const Fp& a) {
   Fp s = fp_sqrt_candidate(a), chk;
   fp_sqr_ni(chk, s);
   if (!fp_eq(chk, a)) return false;
@@ -75,7 +75,7 @@ LW_DEV inline bool fp_sqrt(Fp& out, const Fp& a) {
 }
 
 // A square root in Fp2 (complex method), false if none exists.
-LW_DEV inline bool fp2_sqrt(Fp2& out, const Fp2& a) {
+LW_COLD bool fp2_sqrt(Fp2& out, const Fp2& a) {
   if (fp_is_zero(a.c1)) {
     Fp s;
     if (fp_sqrt(s, a.c0)) { out.c0 = s; out.c1 = fp_zero(); return true; }
@@ -107,19 +107,19 @@ struct G2Affine {
   Fp2 x, y;
 };
 
-LW_DEV inline Fp2 g2_curve_b() {
+LW_COLD Fp2 g2_curve_b() {
   Fp2 b;
   for (int i = 0; i < 12; i++) { b.c0.l[i] = k::FP_B[i]; b.c1.l[i] = k::FP_B[i]; }
   return b;
 }
-LW_DEV inline bool g2a_on_curve(const G2Affine& p) {
+LW_COLD bool g2a_on_curve(const G2Affine& p) {
   Fp2 lhs = fp2_sqr(p.y);
   Fp2 rhs = fp2_add(fp2_mul(fp2_sqr(p.x), p.x), g2_curve_b());
   return fp2_eq(lhs, rhs);
 }
 
 // ZCash lexicographic "largest" for Fp2: compare c1 first, then c0 (canonical values).
-LW_DEV inline bool fp2_is_lex_large(const Fp2& y) {
+LW_COLD bool fp2_is_lex_large(const Fp2& y) {
   Fp c1 = fp_from_mont(y.c1);
   if (!fp_is_zero(c1)) return fp_canon_is_lex_large(c1);
   return fp_canon_is_lex_large(fp_from_mont(y.c0));
@@ -129,7 +129,7 @@ LW_DEV inline bool fp2_is_lex_large(const Fp2& y) {
 // src/compression.rs:105-139: bit7 required, bit6 -> infinity, x reduced mod p,
 // no subgroup check.  The sign bit (bit5) is honoured (ZCash rule); the
 // reference ignores it, which coincides for the shipped setups.
-LW_DEV inline bool g2_decompress(G2Affine& out, bool& is_inf, const uint8_t* in96) {
+LW_COLD bool g2_decompress(G2Affine& out, bool& is_inf, const uint8_t* in96) {
   is_inf = false;
   uint8_t b0 = in96[0];
   if (!(b0 & 0x80)) return false;

@@ -137,8 +137,14 @@ LW_INL void xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
   a.y = Y3;
 }
 
+// Out-of-line copies of the group law for cold callers (scalar-mul ladders,
+// verification, setup): the hot MSM loop keeps the force-inlined versions.
+LW_COLD void xyzz_madd_ni(G1Xyzz& acc, const G1Affine& p) { xyzz_madd(acc, p); }
+LW_COLD void xyzz_add_ni(G1Xyzz& a, const G1Xyzz& b) { xyzz_add(a, b); }
+LW_COLD void xyzz_dbl_ni(G1Xyzz& a) { a = xyzz_dbl(a); }
+
 // XYZZ -> affine (one inversion); infinity -> (0,0)
-LW_DEV inline G1Affine xyzz_to_affine(const G1Xyzz& p) {
+LW_COLD G1Affine xyzz_to_affine(const G1Xyzz& p) {
   if (xyzz_is_inf(p)) return g1a_inf();
   Fp zzz_inv = fp_inv(p.zzz);
   Fp t = fp_mul(p.zz, zzz_inv);  // ZZ/ZZZ = 1/sqrt(ZZ)
@@ -158,14 +164,14 @@ LW_INL bool xyzz_eq(const G1Xyzz& a, const G1Xyzz& b) {
 
 // [k]p for a canonical 256-bit little-endian scalar (8 x u32), MSB-first
 // double-and-add.  Cold path (verification, table seeding).
-LW_DEV inline G1Xyzz g1_mul_scalar(const G1Affine& p, const uint32_t* kk, int nlimbs) {
+LW_COLD G1Xyzz g1_mul_scalar(const G1Affine& p, const uint32_t* kk, int nlimbs) {
   G1Xyzz acc = xyzz_inf();
   bool started = false;
   for (int w = nlimbs - 1; w >= 0; w--) {
     uint32_t word = kk[w];
     for (int bit = 31; bit >= 0; bit--) {
-      if (started) acc = xyzz_dbl(acc);
-      if ((word >> bit) & 1u) { xyzz_madd(acc, p); started = true; }
+      if (started) xyzz_dbl_ni(acc);
+      if ((word >> bit) & 1u) { xyzz_madd_ni(acc, p); started = true; }
     }
   }
   return acc;
@@ -173,7 +179,7 @@ LW_DEV inline G1Xyzz g1_mul_scalar(const G1Affine& p, const uint32_t* kk, int nl
 
 // ---------------------------------------------------------------- codecs
 // /root/reference/src/compression.rs:33-60
-LW_DEV inline void g1_compress(uint8_t* out48, const G1Affine& p) {
+LW_COLD void g1_compress(uint8_t* out48, const G1Affine& p) {
   if (g1a_is_inf(p)) {
     out48[0] = 0xC0;
     for (int i = 1; i < 48; i++) out48[i] = 0;
@@ -191,16 +197,16 @@ LW_DEV inline void g1_compress(uint8_t* out48, const G1Affine& p) {
 // where phi(x,y) = (beta x, y)  (Scott, "A note on group membership tests for
 // G1, G2 and GT on BLS pairing-friendly curves", 2021).  [x^2]P costs two
 // 64-bit double-and-add ladders instead of a 255-bit one.
-LW_DEV inline G1Xyzz g1_mul_u64(const G1Xyzz& p, unsigned long long e) {
+LW_COLD G1Xyzz g1_mul_u64(const G1Xyzz& p, unsigned long long e) {
   G1Xyzz acc = xyzz_inf();
   bool started = false;
   for (int bit = 63; bit >= 0; bit--) {
-    if (started) acc = xyzz_dbl(acc);
-    if ((e >> bit) & 1ull) { xyzz_add(acc, p); started = true; }
+    if (started) xyzz_dbl_ni(acc);
+    if ((e >> bit) & 1ull) { xyzz_add_ni(acc, p); started = true; }
   }
   return acc;
 }
-LW_DEV inline bool g1_in_subgroup(const G1Affine& p) {
+LW_COLD bool g1_in_subgroup(const G1Affine& p) {
   if (g1a_is_inf(p)) return true;
   G1Xyzz P = xyzz_from_affine(p);
   G1Xyzz t = g1_mul_u64(g1_mul_u64(P, k::BLS_X_ABS), k::BLS_X_ABS);  // [x^2]P
@@ -212,7 +218,7 @@ LW_DEV inline bool g1_in_subgroup(const G1Affine& p) {
 
 // /root/reference/src/compression.rs:62-103.  Returns false
 // on any rejection.  *out is affine; infinity -> (0,0).
-LW_DEV inline bool g1_decompress(G1Affine& out, const uint8_t* in48) {
+LW_COLD bool g1_decompress(G1Affine& out, const uint8_t* in48) {
   uint8_t b0 = in48[0];
   if (!(b0 & 0x80)) return false;
   if (b0 & 0x40) { out = g1a_inf(); return true; }  // remaining bits unchecked, like the reference

@@ -62,6 +62,8 @@ struct G2PreparedDev;  // opaque: line coefficients of one G2 point
 size_t g2_prepared_bytes();
 // canonical LE limbs x.c0,x.c1,y.c0,y.c1 (48 u32) -> prepared lines; flag = 1 if not on the twist
 void launch_g2_prepare(void* d_prepared, int* d_bad, const void* d_canon_in, cudaStream_t st);
+// bad[i] = 1 if g2 value i (canonical limbs, 48 u32 each) is not on the twist
+void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st);
 // single verification: C - y*g1_0 + z*pi  vs  pi  (bilinear rearrangement)
 // inputs: affine Montgomery C, pi; canonical z, y.  ok written as int.
 void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,

@@ -97,6 +97,9 @@ struct Ctx {
   void* d_prep0;      // prepared g2[0] / g2[1] line coefficients
   void* d_prep1;
   Slot slot[NSLOT];
+  // batched-verification workspace (sized for the largest batch seen)
+  DevBuf vb_cin, vb_pin, vb_caff, vb_piaff, vb_c48r, vb_p48r, vb_z, vb_y, vb_tuples, vb_status, vb_r, vb_partial, vb_scratch, vb_ok, vb_zy_in;
+  size_t vb_n = 0;  // items currently held by the workspace (phase1 -> phase2)
   std::mutex mu;
 };
 
@@ -140,6 +143,9 @@ void destroy_ctx(Ctx* c) {
     if (s.st) cudaStreamDestroy(s.st);
     if (s.aux) cudaStreamDestroy(s.aux);
   }
+  for (DevBuf* b : {&c->vb_cin, &c->vb_pin, &c->vb_caff, &c->vb_piaff, &c->vb_c48r, &c->vb_p48r, &c->vb_z, &c->vb_y, &c->vb_tuples, &c->vb_status,
+                    &c->vb_r, &c->vb_partial, &c->vb_scratch, &c->vb_ok, &c->vb_zy_in})
+    b->release();
   if (c->d_srs) cudaFree(c->d_srs);
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_prep0) cudaFree(c->d_prep0);
@@ -190,8 +196,8 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2) {
   // ---- G2: g2[0], g2[1] -> prepared Miller-loop lines
   c->g2_valid = false;
   {
-    uint32_t g2canon[2][48];
-    for (int k = 0; k < 2; k++) {
+    static uint32_t g2canon[TRUSTED_SETUP_NUM_G2_POINTS][48];
+    for (int k = 0; k < TRUSTED_SETUP_NUM_G2_POINTS; k++) {
       blst_fp_to_canon(&g2canon[k][0], &g2[k].x.fp[0]);
       blst_fp_to_canon(&g2canon[k][12], &g2[k].x.fp[1]);
       blst_fp_to_canon(&g2canon[k][24], &g2[k].y.fp[0]);
@@ -200,18 +206,24 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2) {
     void* d_g2 = nullptr;
     int* d_bad = nullptr;
     CU_TRY(cudaMalloc(&d_g2, sizeof(g2canon)));
-    CU_TRY(cudaMalloc(&d_bad, 2 * sizeof(int)));
+    CU_TRY(cudaMalloc(&d_bad, (2 + TRUSTED_SETUP_NUM_G2_POINTS) * sizeof(int)));
     CU_TRY(cudaMalloc(&c->d_prep0, g2_prepared_bytes()));
     CU_TRY(cudaMalloc(&c->d_prep1, g2_prepared_bytes()));
     CU_TRY(cudaMemcpyAsync(d_g2, g2canon, sizeof(g2canon), cudaMemcpyHostToDevice, st));
     launch_g2_prepare(c->d_prep0, d_bad, d_g2, st);
     launch_g2_prepare(c->d_prep1, d_bad + 1, (const uint8_t*)d_g2 + 48 * 4, st);
-    int bad[2] = {1, 1};
+    launch_g2_check(d_bad + 2, d_g2, TRUSTED_SETUP_NUM_G2_POINTS, st);
+    int bad[2 + TRUSTED_SETUP_NUM_G2_POINTS];
+    for (int& b : bad) b = 1;
     CU_TRY(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     cudaFree(d_g2);
     cudaFree(d_bad);
     c->g2_valid = !bad[0] && !bad[1];
+    // the reference re-hydrates all 65 G2 values on every call and fails if any
+    // is off the twist (src/srs.rs:258-280)
+    for (int k = 0; k < TRUSTED_SETUP_NUM_G2_POINTS; k++)
+      if (bad[2 + k]) c->srs_valid = false;
   }
 
   if (!c->srs_valid) return true;  // usable only to report C_KZG_ERROR, like the reference
@@ -298,7 +310,7 @@ Ctx* ctx_of(const KZGSettings* s) {
   LazyKey key{s->g1_values, s->g2_values, 0};
   key.hash = fnv1a(s->g1_values, sizeof(g1_t) * N_POINTS);
   key.hash = fnv1a(s->g2_values, sizeof(g2_t) * 2, key.hash);
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::unique_lock<std::mutex> lk(g_mu);
   auto it = lazy_map().find(key);
   if (it != lazy_map().end()) return it->second;
   // drop stale contexts registered for the same pointers
@@ -310,9 +322,9 @@ Ctx* ctx_of(const KZGSettings* s) {
       ++j;
     }
   }
-  g_mu.unlock();
+  lk.unlock();
   Ctx* c = build_ctx(s->g1_values, s->g2_values);
-  g_mu.lock();
+  lk.lock();
   if (c) lazy_map()[key] = c;
   return c;
 }
@@ -604,6 +616,88 @@ C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, si
   return C_KZG_OK;
 }
 
+// ------------------------------------------------------------------ verification
+bool vb_reserve(Ctx* c, size_t n) {
+  return c->vb_cin.ensure(n * 48) && c->vb_pin.ensure(n * 48) && c->vb_caff.ensure(n * AFFINE_BYTES) && c->vb_piaff.ensure(n * AFFINE_BYTES) &&
+         c->vb_c48r.ensure(n * 48) && c->vb_p48r.ensure(n * 48) && c->vb_z.ensure(n * 32) && c->vb_y.ensure(n * 32) && c->vb_tuples.ensure(n * 160) &&
+         c->vb_status.ensure(n * sizeof(int)) && c->vb_r.ensure(32) && c->vb_partial.ensure(288) && c->vb_ok.ensure(sizeof(int)) &&
+         c->vb_zy_in.ensure(n * 64) && c->vb_scratch.ensure(batch_partials_scratch_bytes((int)n));
+}
+
+// Per-blob preparation of a batched verification (lib.rs:562-596): decode C_i
+// and pi_i, z_i = challenge(blob_i, C_i), y_i = p_i(z_i); everything stays in
+// the context's verify workspace.  Host blobs are streamed through the two
+// slots in chunks.  Returns false on CUDA failure; invalid items are reported
+// through vb_status.
+bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n) {
+  if (!vb_reserve(c, n)) return false;
+  long chunk;
+  {
+    std::lock_guard<std::mutex> lk2(g_mu);
+    chunk = std::max(1L, opts().chunk_blobs);
+  }
+  cudaStream_t s0 = c->slot[0].st;
+  CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitments, n * 48, cudaMemcpyHostToDevice, s0));
+  CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proofs, n * 48, cudaMemcpyHostToDevice, s0));
+  launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0);
+  // proofs: decode status into the (still unused) tuples buffer, then merge
+  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, s0);
+  launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, (int)n, s0);
+  CU_TRY(cudaStreamSynchronize(s0));
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    int m = (int)std::min<size_t>(chunk, n - off);
+    Slot& sl = c->slot[k % NSLOT];
+    CU_TRY(cudaStreamSynchronize(sl.st));
+    if (!slot_reserve(sl, m, 1, true)) return false;
+    CU_TRY(cudaMemcpyAsync(sl.blobs.p, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, sl.st));
+    CU_TRY(cudaEventRecord(sl.ev_fork, sl.st));
+    CU_TRY(cudaStreamWaitEvent(sl.aux, sl.ev_fork, 0));
+    launch_challenge_midstate(sl.states.p, sl.blobs.p, m, sl.aux);
+    CU_TRY(cudaEventRecord(sl.ev_aux, sl.aux));
+    CU_TRY(cudaStreamWaitEvent(sl.st, sl.ev_aux, 0));
+    launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, sl.states.p, sl.blobs.p, (const uint8_t*)c->vb_c48r.p + off * 48, m, sl.st);
+    launch_poly_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, sl.blobs.p, (const uint8_t*)c->vb_z.p + off * 32, m, sl.st);
+  }
+  for (auto& sl : c->slot) {
+    CU_TRY(cudaStreamSynchronize(sl.st));
+    CU_TRY(cudaStreamSynchronize(sl.aux));
+  }
+  launch_make_tuples(c->vb_tuples.p, c->vb_c48r.p, c->vb_z.p, c->vb_y.p, c->vb_p48r.p, (int)n, s0);
+  CU_TRY(cudaStreamSynchronize(s0));
+  CU_TRY(cudaGetLastError());
+  c->vb_n = n;
+  return true;
+}
+
+bool any_bad_status(Ctx* c, size_t n, bool& bad) {
+  std::vector<int> st(n);
+  CU_TRY(cudaMemcpy(st.data(), c->vb_status.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  bad = false;
+  for (int v : st)
+    if (v) bad = true;
+  return true;
+}
+
+// single-proof verification with everything already decoded in the workspace (item 0)
+bool verify_single_from_workspace(Ctx* c, bool& ok) {
+  cudaStream_t s0 = c->slot[0].st;
+  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->d_srs, c->d_prep0, c->d_prep1, s0);
+  int okv = 0;
+  CU_TRY(cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
+  CU_TRY(cudaStreamSynchronize(s0));
+  CU_TRY(cudaGetLastError());
+  ok = okv != 0;
+  return true;
+}
+
+struct CtxLock {
+  Ctx* c;
+  std::unique_lock<std::mutex> lk;
+  DeviceGuard dg;
+  explicit CtxLock(Ctx* ctx) : c(ctx), lk(ctx->mu), dg(ctx->device) {}
+};
+
 }  // namespace
 
 // =================================================================== C ABI
@@ -732,6 +826,182 @@ C_KZG_RET compute_kzg_proof(KZGProof* proof_out, Bytes32* y_out, const Blob* blo
 }
 C_KZG_RET compute_blob_kzg_proof(KZGProof* out, const Blob* blob, const Bytes48* commitment_bytes, const KZGSettings* s) {
   return host_batch(Mode::BlobProof, s, 1, blob, commitment_bytes, nullptr, nullptr, out, nullptr, nullptr);
+}
+
+// ---- verification
+C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Bytes32* z_bytes, const Bytes32* y_bytes, const Bytes48* proof_bytes,
+                           const KZGSettings* s) {
+  if (!ok) return C_KZG_ERROR;
+  *ok = false;  // lib.rs:415-417
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  CtxLock L(c);
+  if (!vb_reserve(c, 1)) return C_KZG_ERROR;
+  cudaStream_t s0 = c->slot[0].st;
+  uint8_t zy[64];
+  memcpy(zy, z_bytes, 32);
+  memcpy(zy + 32, y_bytes, 32);
+  bool good = [&]() -> bool {
+    CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitment_bytes, 48, cudaMemcpyHostToDevice, s0));
+    CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proof_bytes, 48, cudaMemcpyHostToDevice, s0));
+    CU_TRY(cudaMemcpyAsync(c->vb_zy_in.p, zy, 64, cudaMemcpyHostToDevice, s0));
+    launch_g1_decompress(c->vb_caff.p, nullptr, (int*)c->vb_status.p, c->vb_cin.p, 1, s0);
+    launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, s0);
+    launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, 1, s0);
+    launch_fr_from_be(c->vb_z.p, c->vb_zy_in.p, 1, s0);
+    launch_fr_from_be(c->vb_y.p, (const uint8_t*)c->vb_zy_in.p + 32, 1, s0);
+    CU_TRY(cudaStreamSynchronize(s0));
+    return true;
+  }();
+  if (!good) return C_KZG_ERROR;
+  bool bad = false;
+  if (!any_bad_status(c, 1, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  bool res = false;
+  if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
+  *ok = res;
+  return C_KZG_OK;
+}
+
+C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s) {
+  if (!ok) return C_KZG_ERROR;
+  *ok = false;  // lib.rs:463-465
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  CtxLock L(c);
+  if (!verify_prepare(c, blob, commitment_bytes, proof_bytes, 1)) return C_KZG_ERROR;
+  bool bad = false;
+  if (!any_bad_status(c, 1, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  bool res = false;
+  if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
+  *ok = res;
+  return C_KZG_OK;
+}
+
+C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
+                                      const KZGSettings* s) {
+  if (!ok) return C_KZG_ERROR;
+  *ok = false;  // lib.rs:533-535
+  if (n == 0) return C_KZG_OK;  // lib.rs:538-543: *ok stays false
+  if (n == 1) return verify_blob_kzg_proof(ok, blobs, commitments_bytes, proofs_bytes, s);  // lib.rs:544
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  CtxLock L(c);
+  if (!verify_prepare(c, blobs, commitments_bytes, proofs_bytes, n)) return C_KZG_ERROR;
+  bool bad = false;
+  if (!any_bad_status(c, n, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  cudaStream_t s0 = c->slot[0].st;
+  launch_batch_challenge(c->vb_r.p, c->vb_tuples.p, n, s0);
+  launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, 0, (int)n, c->vb_scratch.p, s0);
+  launch_batch_final((int*)c->vb_ok.p, c->vb_partial.p, 1, c->d_prep0, c->d_prep1, s0);
+  int okv = 0;
+  if (cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0) != cudaSuccess || cudaStreamSynchronize(s0) != cudaSuccess ||
+      cudaGetLastError() != cudaSuccess) {
+    set_err("CUDA failure in batch verification");
+    return C_KZG_ERROR;
+  }
+  *ok = okv != 0;
+  return C_KZG_OK;
+}
+
+// ---- multi-GPU batched verification phases
+C_KZG_RET lwkzg_verify_batch_phase1(uint8_t* tuples160, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n_local,
+                                    const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  CtxLock L(c);
+  c->vb_n = 0;
+  if (n_local == 0) return C_KZG_OK;
+  if (!verify_prepare(c, blobs, commitments, proofs, n_local)) return C_KZG_ERROR;
+  bool bad = false;
+  if (!any_bad_status(c, n_local, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  if (cudaMemcpy(tuples160, c->vb_tuples.p, n_local * 160, cudaMemcpyDeviceToHost) != cudaSuccess) { set_err("D2H failed"); return C_KZG_ERROR; }
+  return C_KZG_OK;
+}
+
+C_KZG_RET lwkzg_verify_batch_phase2(uint8_t* partial288, const uint8_t* all_tuples160, size_t n_total, size_t first, size_t n_local,
+                                    const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  CtxLock L(c);
+  if (c->vb_n != n_local || first + n_local > n_total) { set_err("phase2 does not match the preceding phase1"); return C_KZG_BADARGS; }
+  cudaStream_t s0 = c->slot[0].st;
+  void* d_all = nullptr;
+  if (cudaMalloc(&d_all, std::max<size_t>(n_total, 1) * 160) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
+  bool good = [&]() -> bool {
+    CU_TRY(cudaMemcpyAsync(d_all, all_tuples160, n_total * 160, cudaMemcpyHostToDevice, s0));
+    if (!c->vb_r.ensure(32) || !c->vb_partial.ensure(288) || !c->vb_scratch.ensure(batch_partials_scratch_bytes((int)std::max<size_t>(n_local, 1)))) return false;
+    launch_batch_challenge(c->vb_r.p, d_all, n_total, s0);
+    launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, first, (int)n_local, c->vb_scratch.p, s0);
+    CU_TRY(cudaMemcpyAsync(partial288, c->vb_partial.p, 288, cudaMemcpyDeviceToHost, s0));
+    CU_TRY(cudaStreamSynchronize(s0));
+    CU_TRY(cudaGetLastError());
+    return true;
+  }();
+  cudaFree(d_all);
+  return good ? C_KZG_OK : C_KZG_ERROR;
+}
+
+C_KZG_RET lwkzg_verify_batch_phase3(bool* ok, const uint8_t* partials288, size_t n_ranks, const KZGSettings* s) {
+  if (!ok) return C_KZG_ERROR;
+  *ok = false;
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  CtxLock L(c);
+  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  cudaStream_t s0 = c->slot[0].st;
+  void* d_p = nullptr;
+  if (cudaMalloc(&d_p, std::max<size_t>(n_ranks, 1) * 288) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
+  int okv = 0;
+  bool good = [&]() -> bool {
+    if (!c->vb_ok.ensure(sizeof(int))) return false;
+    CU_TRY(cudaMemcpyAsync(d_p, partials288, n_ranks * 288, cudaMemcpyHostToDevice, s0));
+    launch_batch_final((int*)c->vb_ok.p, d_p, (int)n_ranks, c->d_prep0, c->d_prep1, s0);
+    CU_TRY(cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CU_TRY(cudaStreamSynchronize(s0));
+    CU_TRY(cudaGetLastError());
+    return true;
+  }();
+  cudaFree(d_p);
+  if (!good) return C_KZG_ERROR;
+  *ok = okv != 0;
+  return C_KZG_OK;
+}
+
+// ---- generic linear combination (g1_lincomb, lib.rs:241-243)
+C_KZG_RET lwkzg_g1_lincomb(Bytes48* out, const uint8_t* points_xy_be, const uint8_t* scalars_be, size_t n) {
+  if (!out) return C_KZG_ERROR;
+  void *d_pts = nullptr, *d_sc = nullptr, *d_scratch = nullptr, *d_out = nullptr;
+  int bad = 0;
+  bool good = [&]() -> bool {
+    size_t nn = std::max<size_t>(n, 1);
+    CU_TRY(cudaMalloc(&d_pts, nn * 96));
+    CU_TRY(cudaMalloc(&d_sc, nn * 32));
+    CU_TRY(cudaMalloc(&d_scratch, var_msm_scratch_bytes(nn)));
+    CU_TRY(cudaMalloc(&d_out, 48));
+    if (n) {
+      CU_TRY(cudaMemcpy(d_pts, points_xy_be, n * 96, cudaMemcpyHostToDevice));
+      CU_TRY(cudaMemcpy(d_sc, scalars_be, n * 32, cudaMemcpyHostToDevice));
+    }
+    launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, 0);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, d_out, 48, cudaMemcpyDeviceToHost));
+    size_t blocks = std::max<size_t>((n + 63) / 64, 1);
+    CU_TRY(cudaMemcpy(&bad, (uint8_t*)d_scratch + blocks * XYZZ_BYTES, sizeof(int), cudaMemcpyDeviceToHost));
+    return true;
+  }();
+  cudaFree(d_pts); cudaFree(d_sc); cudaFree(d_scratch); cudaFree(d_out);
+  if (!good) return C_KZG_ERROR;
+  if (bad) { set_err("point not on the curve"); return C_KZG_BADARGS; }
+  return C_KZG_OK;
 }
 
 }  // extern "C"

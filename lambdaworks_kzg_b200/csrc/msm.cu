@@ -156,7 +156,7 @@ msm_finalize_kernel(uint8_t* __restrict__ out48, G1Affine* __restrict__ aff_out,
   G1Xyzz acc = p[0];
   for (int i = 1; i < parts; i++) {
     G1Xyzz o = p[i];
-    xyzz_add(acc, o);
+    xyzz_add_ni(acc, o);
   }
   G1Affine a = xyzz_to_affine(acc);
   if (aff_out) aff_out[blob] = a;

@@ -32,16 +32,16 @@ struct Fp12 {
 };
 
 // ---------------------------------------------------------------- Fp6
-LW_DEV inline Fp6 fp6_zero() { Fp6 r; r.c0 = fp2_zero(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); return r; }
-LW_DEV inline Fp6 fp6_one() { Fp6 r; r.c0 = fp2_one(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); return r; }
-LW_DEV inline Fp6 fp6_add(const Fp6& a, const Fp6& b) { Fp6 r; r.c0 = fp2_add(a.c0, b.c0); r.c1 = fp2_add(a.c1, b.c1); r.c2 = fp2_add(a.c2, b.c2); return r; }
-LW_DEV inline Fp6 fp6_sub(const Fp6& a, const Fp6& b) { Fp6 r; r.c0 = fp2_sub(a.c0, b.c0); r.c1 = fp2_sub(a.c1, b.c1); r.c2 = fp2_sub(a.c2, b.c2); return r; }
-LW_DEV inline Fp6 fp6_neg(const Fp6& a) { Fp6 r; r.c0 = fp2_neg(a.c0); r.c1 = fp2_neg(a.c1); r.c2 = fp2_neg(a.c2); return r; }
-LW_DEV inline bool fp6_eq(const Fp6& a, const Fp6& b) { return fp2_eq(a.c0, b.c0) && fp2_eq(a.c1, b.c1) && fp2_eq(a.c2, b.c2); }
+LW_COLD Fp6 fp6_zero() { Fp6 r; r.c0 = fp2_zero(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); return r; }
+LW_COLD Fp6 fp6_one() { Fp6 r; r.c0 = fp2_one(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); return r; }
+LW_COLD Fp6 fp6_add(const Fp6& a, const Fp6& b) { Fp6 r; r.c0 = fp2_add(a.c0, b.c0); r.c1 = fp2_add(a.c1, b.c1); r.c2 = fp2_add(a.c2, b.c2); return r; }
+LW_COLD Fp6 fp6_sub(const Fp6& a, const Fp6& b) { Fp6 r; r.c0 = fp2_sub(a.c0, b.c0); r.c1 = fp2_sub(a.c1, b.c1); r.c2 = fp2_sub(a.c2, b.c2); return r; }
+LW_COLD Fp6 fp6_neg(const Fp6& a) { Fp6 r; r.c0 = fp2_neg(a.c0); r.c1 = fp2_neg(a.c1); r.c2 = fp2_neg(a.c2); return r; }
+LW_COLD bool fp6_eq(const Fp6& a, const Fp6& b) { return fp2_eq(a.c0, b.c0) && fp2_eq(a.c1, b.c1) && fp2_eq(a.c2, b.c2); }
 // a * v
-LW_DEV inline Fp6 fp6_mul_v(const Fp6& a) { Fp6 r; r.c0 = fp2_mul_xi(a.c2); r.c1 = a.c0; r.c2 = a.c1; return r; }
+LW_COLD Fp6 fp6_mul_v(const Fp6& a) { Fp6 r; r.c0 = fp2_mul_xi(a.c2); r.c1 = a.c0; r.c2 = a.c1; return r; }
 
-LW_DEV inline Fp6 fp6_mul(const Fp6& a, const Fp6& b) {
+LW_COLD Fp6 fp6_mul(const Fp6& a, const Fp6& b) {
   Fp2 t0 = fp2_mul(a.c0, b.c0), t1 = fp2_mul(a.c1, b.c1), t2 = fp2_mul(a.c2, b.c2);
   Fp6 r;
   r.c0 = fp2_add(t0, fp2_mul_xi(fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2)), t1), t2)));
@@ -49,7 +49,7 @@ LW_DEV inline Fp6 fp6_mul(const Fp6& a, const Fp6& b) {
   r.c2 = fp2_add(fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2)), t0), t2), t1);
   return r;
 }
-LW_DEV inline Fp6 fp6_inv(const Fp6& a) {
+LW_COLD Fp6 fp6_inv(const Fp6& a) {
   Fp2 c0 = fp2_sub(fp2_sqr(a.c0), fp2_mul_xi(fp2_mul(a.c1, a.c2)));
   Fp2 c1 = fp2_sub(fp2_mul_xi(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
   Fp2 c2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
@@ -61,25 +61,25 @@ LW_DEV inline Fp6 fp6_inv(const Fp6& a) {
 }
 
 // ---------------------------------------------------------------- Fp12
-LW_DEV inline Fp12 fp12_one() { Fp12 r; r.c0 = fp6_one(); r.c1 = fp6_zero(); return r; }
-LW_DEV inline bool fp12_eq(const Fp12& a, const Fp12& b) { return fp6_eq(a.c0, b.c0) && fp6_eq(a.c1, b.c1); }
-LW_DEV inline bool fp12_is_one(const Fp12& a) { return fp12_eq(a, fp12_one()); }
-LW_DEV inline Fp12 fp12_conj(const Fp12& a) { Fp12 r; r.c0 = a.c0; r.c1 = fp6_neg(a.c1); return r; }
-LW_DEV inline Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
+LW_COLD Fp12 fp12_one() { Fp12 r; r.c0 = fp6_one(); r.c1 = fp6_zero(); return r; }
+LW_COLD bool fp12_eq(const Fp12& a, const Fp12& b) { return fp6_eq(a.c0, b.c0) && fp6_eq(a.c1, b.c1); }
+LW_COLD bool fp12_is_one(const Fp12& a) { return fp12_eq(a, fp12_one()); }
+LW_COLD Fp12 fp12_conj(const Fp12& a) { Fp12 r; r.c0 = a.c0; r.c1 = fp6_neg(a.c1); return r; }
+LW_COLD Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
   Fp6 t0 = fp6_mul(a.c0, b.c0), t1 = fp6_mul(a.c1, b.c1);
   Fp12 r;
   r.c1 = fp6_sub(fp6_sub(fp6_mul(fp6_add(a.c0, a.c1), fp6_add(b.c0, b.c1)), t0), t1);
   r.c0 = fp6_add(t0, fp6_mul_v(t1));
   return r;
 }
-LW_DEV inline Fp12 fp12_sqr(const Fp12& a) {
+LW_COLD Fp12 fp12_sqr(const Fp12& a) {
   Fp6 t = fp6_mul(a.c0, a.c1);
   Fp12 r;
   r.c0 = fp6_sub(fp6_sub(fp6_mul(fp6_add(a.c0, a.c1), fp6_add(a.c0, fp6_mul_v(a.c1))), t), fp6_mul_v(t));
   r.c1 = fp6_add(t, t);
   return r;
 }
-LW_DEV inline Fp12 fp12_inv(const Fp12& a) {
+LW_COLD Fp12 fp12_inv(const Fp12& a) {
   Fp6 d = fp6_sub(fp6_mul(a.c0, a.c0), fp6_mul_v(fp6_mul(a.c1, a.c1)));
   Fp6 di = fp6_inv(d);
   Fp12 r;
@@ -89,7 +89,7 @@ LW_DEV inline Fp12 fp12_inv(const Fp12& a) {
 }
 // f * (s0 + s1 v + s4 v w): the sparse line element.  With f = f0 + f1 w and
 // l = l0 + l1 w, l0 = s0 + s1 v, l1 = s4 v.
-LW_DEV inline Fp6 fp6_mul_by_01(const Fp6& a, const Fp2& s0, const Fp2& s1) {
+LW_COLD Fp6 fp6_mul_by_01(const Fp6& a, const Fp2& s0, const Fp2& s1) {
   // (a0 + a1 v + a2 v^2)(s0 + s1 v)
   Fp2 t0 = fp2_mul(a.c0, s0), t1 = fp2_mul(a.c1, s1);
   Fp6 r;
@@ -98,7 +98,7 @@ LW_DEV inline Fp6 fp6_mul_by_01(const Fp6& a, const Fp2& s0, const Fp2& s1) {
   r.c2 = fp2_add(fp2_mul(a.c2, s0), t1);
   return r;
 }
-LW_DEV inline Fp6 fp6_mul_by_1(const Fp6& a, const Fp2& s1) {
+LW_COLD Fp6 fp6_mul_by_1(const Fp6& a, const Fp2& s1) {
   // (a0 + a1 v + a2 v^2)(s1 v) = xi a2 s1 + a0 s1 v + a1 s1 v^2
   Fp6 r;
   r.c0 = fp2_mul_xi(fp2_mul(a.c2, s1));
@@ -106,7 +106,7 @@ LW_DEV inline Fp6 fp6_mul_by_1(const Fp6& a, const Fp2& s1) {
   r.c2 = fp2_mul(a.c1, s1);
   return r;
 }
-LW_DEV inline Fp12 fp12_mul_by_014(const Fp12& f, const Fp2& s0, const Fp2& s1, const Fp2& s4) {
+LW_COLD Fp12 fp12_mul_by_014(const Fp12& f, const Fp2& s0, const Fp2& s1, const Fp2& s4) {
   Fp6 aa = fp6_mul_by_01(f.c0, s0, s1);   // f0 l0
   Fp6 bb = fp6_mul_by_1(f.c1, s4);        // f1 l1
   Fp2 s14 = fp2_add(s1, s4);
@@ -116,7 +116,7 @@ LW_DEV inline Fp12 fp12_mul_by_014(const Fp12& f, const Fp2& s0, const Fp2& s1, 
   return r;
 }
 
-LW_DEV inline Fp2 frob_gamma(int i) {
+LW_COLD Fp2 frob_gamma(int i) {
   Fp2 g;
   const uint32_t* c0; const uint32_t* c1;
   switch (i) {
@@ -130,7 +130,7 @@ LW_DEV inline Fp2 frob_gamma(int i) {
   return g;
 }
 // f^p: coefficient a_i of w^i maps to conj(a_i) * xi^(i (p-1)/6)
-LW_DEV inline Fp12 fp12_frobenius(const Fp12& a) {
+LW_COLD Fp12 fp12_frobenius(const Fp12& a) {
   Fp12 r;
   r.c0.c0 = fp2_conj(a.c0.c0);                            // w^0
   r.c1.c0 = fp2_mul(fp2_conj(a.c1.c0), frob_gamma(1));    // w^1
@@ -151,7 +151,7 @@ struct G2Prepared {
   int infinity;
 };
 
-LW_DEV inline void g2_prepare(G2Prepared& out, const G2Affine& q) {
+LW_COLD void g2_prepare(G2Prepared& out, const G2Affine& q) {
   out.infinity = 0;
   Fp2 tx = q.x, ty = q.y;
   int n = 0;
@@ -179,7 +179,7 @@ LW_DEV inline void g2_prepare(G2Prepared& out, const G2Affine& q) {
   }
 }
 
-LW_DEV inline Fp12 line_mul(const Fp12& f, const G2Line& ln, const G1Affine& p) {
+LW_COLD Fp12 line_mul(const Fp12& f, const G2Line& ln, const G1Affine& p) {
   Fp2 s1 = fp2_neg(fp2_mul_fp(ln.lambda, p.x));
   Fp2 s4; s4.c0 = p.y; s4.c1 = fp_zero();
   return fp12_mul_by_014(f, ln.mu, s1, s4);
@@ -187,7 +187,7 @@ LW_DEV inline Fp12 line_mul(const Fp12& f, const G2Line& ln, const G1Affine& p) 
 
 // product of Miller loops over pairs (P_i, Q_i); pairs with an infinite member
 // contribute 1 (App. D.5).
-LW_DEV inline Fp12 miller_loop(const G1Affine* ps, const G2Prepared* qs, int npairs) {
+LW_COLD Fp12 miller_loop(const G1Affine* ps, const G2Prepared* qs, int npairs) {
   Fp12 f = fp12_one();
   int n = 0;
   for (int bit = 62; bit >= 0; bit--) {
@@ -205,7 +205,7 @@ LW_DEV inline Fp12 miller_loop(const G1Affine* ps, const G2Prepared* qs, int npa
 }
 
 // g^|x| by square-and-multiply, then conjugate (x < 0; g is unitary after the easy part)
-LW_DEV inline Fp12 fp12_pow_x(const Fp12& g) {
+LW_COLD Fp12 fp12_pow_x(const Fp12& g) {
   Fp12 acc = g;
   for (int bit = 62; bit >= 0; bit--) {
     acc = fp12_sqr(acc);
@@ -217,7 +217,7 @@ LW_DEV inline Fp12 fp12_pow_x(const Fp12& g) {
 // f^(3 (p^12-1)/r).  The factor 3 is coprime to r, so "== 1" is unaffected.
 // Hard part: 3 (p^4-p^2+1)/r = (x-1)^2 (x+p) (x^2+p^2-1) + 3   (checked in
 // tests/test_host_emul.py).
-LW_DEV inline Fp12 final_exponentiation(const Fp12& f) {
+LW_COLD Fp12 final_exponentiation(const Fp12& f) {
   // easy part: f^((p^6-1)(p^2+1))
   Fp12 g = fp12_mul(fp12_conj(f), fp12_inv(f));
   g = fp12_mul(fp12_frobenius(fp12_frobenius(g)), g);
@@ -230,7 +230,7 @@ LW_DEV inline Fp12 final_exponentiation(const Fp12& f) {
   return fp12_mul(c, g3);
 }
 
-LW_DEV inline bool pairing_product_is_one(const G1Affine* ps, const G2Prepared* qs, int npairs) {
+LW_COLD bool pairing_product_is_one(const G1Affine* ps, const G2Prepared* qs, int npairs) {
   return fp12_is_one(final_exponentiation(miller_loop(ps, qs, npairs)));
 }
 

@@ -17,11 +17,15 @@
 #define LW_HD
 #define LW_INL inline
 #define LW_CONST static const
+#define LW_COLD static inline
 #else
 #define LW_DEV __device__
 #define LW_HD __host__ __device__
 #define LW_INL __device__ __forceinline__
 #define LW_CONST __device__ __constant__ const
+// cold, code-size-heavy helpers: out of line so the tower-field / pairing code
+// does not explode at compile time
+#define LW_COLD static __device__ __noinline__
 #endif
 
 namespace lw {

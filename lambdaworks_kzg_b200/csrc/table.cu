@@ -39,7 +39,7 @@ __global__ void table_bases_kernel(G1Affine* __restrict__ bases, const G1Affine*
     G1Affine a = (j == 0) ? p : xyzz_to_affine(acc);
     bases[(size_t)j * npoints + i] = a;
     if (j + 1 < nwin)
-      for (int k = 0; k < c; k++) acc = xyzz_dbl(acc);
+      for (int k = 0; k < c; k++) xyzz_dbl_ni(acc);
   }
 }
 

@@ -1,0 +1,405 @@
+// Verification kernels: single-proof check, random-linear-combination batch
+// check and the generic G1 linear combination.
+//   verify_kzg_proof / verify_blob_kzg_proof     /root/reference/src/lib.rs:407-505
+//   verify_blob_kzg_proof_batch / verify_kzg_proof_batch          src/lib.rs:525-692
+//   compute_r_powers                                              src/utils.rs:156-206
+//   g1_lincomb                                                    src/lib.rs:241-243
+// The pairing equation e(C - y g1[0], g2[0]) e(-pi, g2[1] - z g2[0]) == 1 is
+// evaluated in the bilinearly equivalent form
+//        e(C - y g1[0] + z pi, g2[0]) * e(-pi, g2[1]) == 1
+// so that both G2 arguments are the FIXED setup points whose Miller-loop lines
+// were precomputed at load time (pairing.cuh): no G2 arithmetic at verify time.
+#include "kernels.h"
+#include "pairing.cuh"
+#include "sha256.cuh"
+
+namespace lw {
+
+struct G2PreparedDev {
+  G2Prepared p;
+};
+size_t g2_prepared_bytes() { return sizeof(G2Prepared); }
+
+// canonical x.c0,x.c1,y.c0,y.c1 -> prepared lines.  bad = 1 if the point is not
+// on the twist (blst_p2_to_g2_point's from_affine, src/srs.rs:215-247; the
+// all-zero encoding of infinity fails that check too).
+__global__ void g2_prepare_kernel(G2Prepared* __restrict__ out, int* __restrict__ bad, const uint32_t* __restrict__ canon48) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fp c[4];
+  for (int j = 0; j < 4; j++) {
+    for (int k = 0; k < 12; k++) c[j].l[k] = canon48[j * 12 + k];
+    mod_reduce_small<FpCfg, 9>(c[j].l);
+    c[j] = fp_to_mont(c[j]);
+  }
+  G2Affine q;
+  q.x.c0 = c[0]; q.x.c1 = c[1]; q.y.c0 = c[2]; q.y.c1 = c[3];
+  if (!g2a_on_curve(q)) { *bad = 1; out->infinity = 1; return; }
+  *bad = 0;
+  g2_prepare(*out, q);
+}
+
+// on-curve check of all 65 g2 values (the reference re-hydrates -- and so
+// validates -- every one of them on every call: src/srs.rs:258-280)
+__global__ void g2_check_kernel(int* __restrict__ bad, const uint32_t* __restrict__ canon48, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp c[4];
+  for (int j = 0; j < 4; j++) {
+    for (int k = 0; k < 12; k++) c[j].l[k] = canon48[i * 48 + j * 12 + k];
+    mod_reduce_small<FpCfg, 9>(c[j].l);
+    c[j] = fp_to_mont(c[j]);
+  }
+  G2Affine q;
+  q.x.c0 = c[0]; q.x.c1 = c[1]; q.y.c0 = c[2]; q.y.c1 = c[3];
+  bad[i] = g2a_on_curve(q) ? 0 : 1;
+}
+
+// ---- two-pairing check: lanes 0 and 1 run one Miller loop each, lane 0 merges.
+__device__ __forceinline__ bool two_pairing_check(const G1Affine& a, const G1Affine& b, const G2Prepared* prep0, const G2Prepared* prep1, Fp12* sh /* shared, 1 elem */) {
+  const int lane = threadIdx.x;
+  Fp12 f;
+  if (lane == 0) f = miller_loop(&a, prep0, 1);
+  if (lane == 1) {
+    f = miller_loop(&b, prep1, 1);
+    *sh = f;
+  }
+  __syncthreads();
+  bool ok = false;
+  if (lane == 0) {
+    f = fp12_mul(f, *sh);
+    ok = fp12_is_one(final_exponentiation(f));
+  }
+  return ok;
+}
+
+// ok = [ e(C - y g1_0 + z pi, g2_0) * e(-pi, g2_1) == 1 ]
+__global__ void __launch_bounds__(32) verify_single_kernel(int* __restrict__ ok_out, const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
+                                                            const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
+                                                            const G1Affine* __restrict__ g1_0, const G2Prepared* __restrict__ prep0,
+                                                            const G2Prepared* __restrict__ prep1) {
+  __shared__ G1Xyzz sh_pt[2];
+  __shared__ Fp12 sh_f;
+  __shared__ G1Affine sh_lhs;
+  const int lane = threadIdx.x;
+  G1Affine C = *c_aff, PI = *pi_aff;
+  if (lane < 2) {
+    uint32_t k[8];
+    for (int i = 0; i < 8; i++) k[i] = lane == 0 ? y[i] : z[i];
+    G1Affine base = lane == 0 ? *g1_0 : PI;
+    sh_pt[lane] = g1_mul_scalar(base, k, 8);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    G1Xyzz acc = xyzz_from_affine(C);
+    xyzz_add_ni(acc, xyzz_neg(sh_pt[0]));
+    xyzz_add_ni(acc, sh_pt[1]);
+    sh_lhs = xyzz_to_affine(acc);
+  }
+  __syncthreads();
+  G1Affine lhs = sh_lhs;
+  bool ok = two_pairing_check(lhs, g1a_neg(PI), prep0, prep1, &sh_f);
+  if (lane == 0) *ok_out = ok ? 1 : 0;
+}
+
+// tuple_i = compress(C_i) || be32(z_i) || be32(y_i) || compress(pi_i)  (utils.rs:183-201)
+__global__ void make_tuples_kernel(uint8_t* __restrict__ tuples, const uint8_t* __restrict__ c48, const uint32_t* __restrict__ z,
+                                   const uint32_t* __restrict__ y, const uint8_t* __restrict__ pi48, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t* t = tuples + (size_t)i * 160;
+  for (int k = 0; k < 48; k++) t[k] = c48[(size_t)i * 48 + k];
+  Fr zz, yy;
+  for (int k = 0; k < 8; k++) { zz.l[k] = z[i * 8 + k]; yy.l[k] = y[i * 8 + k]; }
+  fr_canon_to_be32(t + 48, zz);
+  fr_canon_to_be32(t + 80, yy);
+  for (int k = 0; k < 48; k++) t[112 + k] = pi48[(size_t)i * 48 + k];
+}
+
+// r = H("RCKZGBATCH___V1_" || le64(4096) || le64(n) || tuples), read big-endian, mod r.
+// Sequential by nature (one SHA-256 stream): single thread.
+__global__ void batch_challenge_kernel(uint32_t* __restrict__ r_out, const uint8_t* __restrict__ tuples, unsigned long long n_total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Sha256State s;
+  sha256_init(s);
+  uint32_t w[16];
+  // header: 32 bytes; then 160 n bytes.  Stream bytes through a 64-byte window.
+  uint8_t head[32] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_', 0, 0x10, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 8; i++) head[24 + i] = (uint8_t)(n_total >> (8 * i));
+  const unsigned long long total = 32ull + 160ull * n_total;
+  auto byte_at = [&](unsigned long long off) -> uint8_t { return off < 32 ? head[off] : tuples[off - 32]; };
+  unsigned long long off = 0;
+  for (; off + 64 <= total; off += 64) {
+    if (off >= 32 && ((off - 32) & 3) == 0) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(tuples + (off - 32));
+      for (int i = 0; i < 16; i++) w[i] = bswap32(src[i]);
+    } else {
+      for (int i = 0; i < 16; i++)
+        w[i] = ((uint32_t)byte_at(off + 4 * i) << 24) | ((uint32_t)byte_at(off + 4 * i + 1) << 16) | ((uint32_t)byte_at(off + 4 * i + 2) << 8) | byte_at(off + 4 * i + 3);
+    }
+    sha256_compress(s, w);
+  }
+  uint8_t tail[128];
+  int rem = (int)(total - off);
+  for (int i = 0; i < rem; i++) tail[i] = byte_at(off + i);
+  tail[rem] = 0x80;
+  int tl = (rem + 9 <= 64) ? 64 : 128;
+  for (int i = rem + 1; i < tl; i++) tail[i] = 0;
+  unsigned long long bits = total * 8ull;
+  for (int i = 0; i < 8; i++) tail[tl - 1 - i] = (uint8_t)(bits >> (8 * i));
+  for (int o = 0; o < tl; o += 64) {
+    for (int i = 0; i < 16; i++)
+      w[i] = ((uint32_t)tail[o + 4 * i] << 24) | ((uint32_t)tail[o + 4 * i + 1] << 16) | ((uint32_t)tail[o + 4 * i + 2] << 8) | tail[o + 4 * i + 3];
+    sha256_compress(s, w);
+  }
+  Fr r;
+  for (int i = 0; i < 8; i++) r.l[i] = s.h[7 - i];
+  mod_reduce_small<FrCfg, 2>(r.l);
+  for (int i = 0; i < 8; i++) r_out[i] = r.l[i];
+}
+
+// XYZZ block reduction helpers (same SoA shared-memory layout as msm.cu)
+__device__ __forceinline__ void xyzz_to_smem(uint32_t* smem, int stride, int t, const G1Xyzz& p) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&p);
+#pragma unroll
+  for (int i = 0; i < 48; i++) smem[i * stride + t] = w[i];
+}
+__device__ __forceinline__ G1Xyzz xyzz_from_smem(const uint32_t* smem, int stride, int t) {
+  G1Xyzz p;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&p);
+#pragma unroll
+  for (int i = 0; i < 48; i++) w[i] = smem[i * stride + t];
+  return p;
+}
+template <int THREADS>
+__device__ __forceinline__ void block_reduce_xyzz(G1Xyzz& acc, uint32_t* red) {
+  const int tid = threadIdx.x;
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if (tid >= s && tid < 2 * s) xyzz_to_smem(red, THREADS / 2, tid - s, acc);
+    __syncthreads();
+    if (tid < s) {
+      G1Xyzz o = xyzz_from_smem(red, THREADS / 2, tid);
+      xyzz_add_ni(acc, o);
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int BV_THREADS = 64;
+
+// grid = (blocks, 3).  which = blockIdx.y:
+//   0: sum r^i pi_i      1: sum (r^i z_i) pi_i      2: sum r^i C_i - (sum r^i y_i) G
+// One thread per blob (double-and-add by a 255-bit scalar), block tree, one
+// XYZZ partial per block into scratch[which][block].
+__global__ void __launch_bounds__(BV_THREADS) batch_partials_kernel(G1Xyzz* __restrict__ scratch, const uint32_t* __restrict__ r_in,
+                                                                     const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
+                                                                     const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
+                                                                     unsigned long long first, int n_local) {
+  __shared__ uint32_t red[48 * (BV_THREADS / 2)];
+  __shared__ uint32_t ysum[BV_THREADS][8];
+  const int which = blockIdx.y;
+  const int i = blockIdx.x * BV_THREADS + threadIdx.x;
+  G1Xyzz acc = xyzz_inf();
+  Fr ys = fr_zero();  // canonical
+  if (i < n_local) {
+    Fr rc;
+    for (int k = 0; k < 8; k++) rc.l[k] = r_in[k];
+    Fr rm = fr_to_mont(rc);
+    // r^(first + i), Montgomery
+    unsigned long long e = first + (unsigned long long)i;
+    Fr pw = fr_one();
+    bool started = false;
+    for (int bit = 63; bit >= 0; bit--) {
+      if (started) pw = fr_sqr(pw);
+      if ((e >> bit) & 1ull) { pw = fr_mul(pw, rm); started = true; }
+    }
+    Fr sc;  // canonical scalar
+    G1Affine base;
+    if (which == 0) {
+      sc = fr_from_mont(pw);
+      base = pi_aff[i];
+    } else if (which == 1) {
+      Fr zc;
+      for (int k = 0; k < 8; k++) zc.l[k] = z[i * 8 + k];
+      sc = fr_mul(pw, zc);  // mont(r^i) * canonical z = canonical r^i z
+      base = pi_aff[i];
+    } else {
+      sc = fr_from_mont(pw);
+      base = c_aff[i];
+      Fr yc;
+      for (int k = 0; k < 8; k++) yc.l[k] = y[i * 8 + k];
+      ys = fr_mul(pw, yc);  // canonical r^i y_i
+    }
+    acc = g1_mul_scalar(base, sc.l, 8);
+  }
+  if (which == 2) {
+    for (int k = 0; k < 8; k++) ysum[threadIdx.x][k] = ys.l[k];
+  }
+  block_reduce_xyzz<BV_THREADS>(acc, red);
+  if (threadIdx.x == 0) {
+    if (which == 2) {
+      Fr tot = fr_zero();
+      for (int t = 0; t < BV_THREADS; t++) {
+        Fr v;
+        for (int k = 0; k < 8; k++) v.l[k] = ysum[t][k];
+        tot = fr_add(tot, v);
+      }
+      uint32_t* ys_out = reinterpret_cast<uint32_t*>(scratch + (size_t)3 * gridDim.x) + (size_t)blockIdx.x * 8;
+      for (int k = 0; k < 8; k++) ys_out[k] = tot.l[k];
+    }
+    scratch[(size_t)which * gridDim.x + blockIdx.x] = acc;
+  }
+}
+
+// 3 threads: sum the block partials, normalise, emit canonical big-endian affine (96 B each)
+__global__ void batch_partials_finish_kernel(uint8_t* __restrict__ out288, const G1Xyzz* __restrict__ scratch, int blocks) {
+  int which = threadIdx.x;
+  if (which >= 3) return;
+  G1Xyzz acc = xyzz_inf();
+  for (int b = 0; b < blocks; b++) {
+    G1Xyzz o = scratch[(size_t)which * blocks + b];
+    xyzz_add_ni(acc, o);
+  }
+  if (which == 2) {
+    // subtract (sum r^i y_i) G, G = the curve generator (lib.rs:661-668): one
+    // scalar multiplication for the whole range instead of one per blob
+    const uint32_t* ys = reinterpret_cast<const uint32_t*>(scratch + (size_t)3 * blocks);
+    Fr tot = fr_zero();
+    for (int b = 0; b < blocks; b++) {
+      Fr v;
+      for (int k = 0; k < 8; k++) v.l[k] = ys[(size_t)b * 8 + k];
+      tot = fr_add(tot, v);
+    }
+    G1Xyzz yg = g1_mul_scalar(g1a_generator(), tot.l, 8);
+    xyzz_add_ni(acc, xyzz_neg(yg));
+  }
+  G1Affine a = xyzz_to_affine(acc);
+  uint8_t* o = out288 + 96 * which;
+  if (g1a_is_inf(a)) {
+    for (int k = 0; k < 96; k++) o[k] = 0;
+  } else {
+    fp_canon_to_be48(o, fp_from_mont(a.x));
+    fp_canon_to_be48(o + 48, fp_from_mont(a.y));
+  }
+}
+
+__device__ __forceinline__ G1Affine affine_from_be96(const uint8_t* b) {
+  bool z = true;
+  for (int k = 0; k < 96; k++) z = z && (b[k] == 0);
+  if (z) return g1a_inf();
+  G1Affine p;
+  p.x = fp_from_be48(b);
+  p.y = fp_from_be48(b + 48);
+  return p;
+}
+
+// partials: n_ranks x (proof_lincomb, proof_z_lincomb, c_minus_y_lincomb), canonical BE affine.
+// ok = [ e(c_minus_y + proof_z, g2_0) == e(proof_lincomb, g2_1) ]   (lib.rs:679-691)
+__global__ void __launch_bounds__(32) batch_final_kernel(int* __restrict__ ok_out, const uint8_t* __restrict__ partials, int n_ranks,
+                                                          const G2Prepared* __restrict__ prep0, const G2Prepared* __restrict__ prep1) {
+  __shared__ Fp12 sh_f;
+  __shared__ G1Affine sh_pts[2];
+  const int lane = threadIdx.x;
+  if (lane < 2) {
+    G1Xyzz acc = xyzz_inf();
+    for (int r = 0; r < n_ranks; r++) {
+      const uint8_t* base = partials + (size_t)r * 288;
+      if (lane == 0) {
+        xyzz_madd_ni(acc, affine_from_be96(base + 96));   // proof_z_lincomb
+        xyzz_madd_ni(acc, affine_from_be96(base + 192));  // c_minus_y_lincomb
+      } else {
+        xyzz_madd_ni(acc, affine_from_be96(base));        // proof_lincomb
+      }
+    }
+    G1Affine a = xyzz_to_affine(acc);
+    sh_pts[lane] = lane == 0 ? a : g1a_neg(a);
+  }
+  __syncthreads();
+  G1Affine rhs = sh_pts[0], npl = sh_pts[1];
+  bool ok = two_pairing_check(rhs, npl, prep0, prep1, &sh_f);
+  if (lane == 0) *ok_out = ok ? 1 : 0;
+}
+
+// ---- generic G1 linear combination (g1_lincomb): thread per point
+// double-and-add, block tree, serial finish.  Correct for any inputs; a sorted
+// bucket MSM for the 2^12..2^22 sweep is the planned replacement.
+constexpr int VM_THREADS = 64;
+__global__ void __launch_bounds__(VM_THREADS) var_msm_kernel(G1Xyzz* __restrict__ scratch, int* __restrict__ bad, const uint8_t* __restrict__ pts_be,
+                                                              const uint8_t* __restrict__ sc_be, unsigned long long n) {
+  __shared__ uint32_t red[48 * (VM_THREADS / 2)];
+  unsigned long long i = (unsigned long long)blockIdx.x * VM_THREADS + threadIdx.x;
+  G1Xyzz acc = xyzz_inf();
+  if (i < n) {
+    G1Affine p = affine_from_be96(pts_be + i * 96);
+    if (!g1a_is_inf(p) && !g1a_on_curve(p)) atomicExch(bad, 1);
+    Fr k = fr_canon_from_be32(sc_be + i * 32);
+    acc = g1_mul_scalar(p, k.l, 8);
+  }
+  block_reduce_xyzz<VM_THREADS>(acc, red);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = acc;
+}
+__global__ void var_msm_finish_kernel(uint8_t* __restrict__ out48, const G1Xyzz* __restrict__ scratch, int blocks) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G1Xyzz acc = xyzz_inf();
+  for (int b = 0; b < blocks; b++) {
+    G1Xyzz o = scratch[b];
+    xyzz_add_ni(acc, o);
+  }
+  g1_compress(out48, xyzz_to_affine(acc));
+}
+
+// ------------------------------------------------------------------ launchers
+void launch_g2_prepare(void* d_prepared, int* d_bad, const void* d_canon_in, cudaStream_t st) {
+  g2_prepare_kernel<<<1, 32, 0, st>>>((G2Prepared*)d_prepared, d_bad, (const uint32_t*)d_canon_in);
+  count_launch();
+}
+void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st) {
+  g2_check_kernel<<<(n + 31) / 32, 32, 0, st>>>(d_bad, (const uint32_t*)d_canon_in, n);
+  count_launch();
+}
+void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y, const void* d_g1_0_aff,
+                          const void* d_prep0, const void* d_prep1, cudaStream_t st) {
+  verify_single_kernel<<<1, 32, 0, st>>>(d_ok, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
+                                         (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
+  count_launch();
+}
+void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st) {
+  if (n <= 0) return;
+  make_tuples_kernel<<<(n + 63) / 64, 64, 0, st>>>((uint8_t*)d_tuples160, (const uint8_t*)d_c48, (const uint32_t*)d_z, (const uint32_t*)d_y, (const uint8_t*)d_pi48, n);
+  count_launch();
+}
+void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st) {
+  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (const uint8_t*)d_tuples160, (unsigned long long)n_total);
+  count_launch();
+}
+size_t batch_partials_scratch_bytes(int n_local) {
+  size_t blocks = (size_t)((n_local + BV_THREADS - 1) / BV_THREADS);
+  if (blocks < 1) blocks = 1;
+  return blocks * (3 * sizeof(G1Xyzz) + 32);
+}
+void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
+                           size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st) {
+  int blocks = (n_local + BV_THREADS - 1) / BV_THREADS;
+  if (blocks < 1) blocks = 1;
+  dim3 grid(blocks, 3);
+  batch_partials_kernel<<<grid, BV_THREADS, 0, st>>>((G1Xyzz*)d_scratch_xyzz, (const uint32_t*)d_r, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff,
+                                                    (const uint32_t*)d_z, (const uint32_t*)d_y, (unsigned long long)first, n_local);
+  batch_partials_finish_kernel<<<1, 32, 0, st>>>((uint8_t*)d_partial288, (const G1Xyzz*)d_scratch_xyzz, blocks);
+  count_launch(2);
+}
+void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const void* d_prep0, const void* d_prep1, cudaStream_t st) {
+  batch_final_kernel<<<1, 32, 0, st>>>(d_ok, (const uint8_t*)d_partials288, n_ranks, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
+  count_launch();
+}
+size_t var_msm_scratch_bytes(size_t n) { return ((n + VM_THREADS - 1) / VM_THREADS + 1) * sizeof(G1Xyzz) + 16; }
+void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st) {
+  int blocks = (int)((n + VM_THREADS - 1) / VM_THREADS);
+  if (blocks < 1) blocks = 1;
+  G1Xyzz* sc = (G1Xyzz*)d_scratch;
+  int* bad = (int*)((uint8_t*)d_scratch + (size_t)blocks * sizeof(G1Xyzz));
+  cudaMemsetAsync(bad, 0, sizeof(int), st);
+  var_msm_kernel<<<blocks, VM_THREADS, 0, st>>>(sc, bad, (const uint8_t*)d_points_xy_be, (const uint8_t*)d_scalars_be, (unsigned long long)n);
+  var_msm_finish_kernel<<<1, 32, 0, st>>>((uint8_t*)d_out48, sc, blocks);
+  count_launch(2);
+}
+
+}  // namespace lw

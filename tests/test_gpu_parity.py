@@ -1,0 +1,426 @@
+"""GPU tier: the CUDA path, called through the C ABI (ctypes), against the
+oracle on the same inputs.  Bit-exact: every output is integer/byte data.
+
+Re-expresses the reference's own tests (tests/lib_test.rs, src/compression.rs
+unit tests) and adds the oracle-differential cases SURVEY.md §4 derives.
+"""
+import ctypes
+import json
+import os
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.py import bls, kzg  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+R = bls.R
+GEN_HEX = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+
+
+@pytest.fixture(scope="module")
+def lw():
+    import lambdaworks_kzg_b200 as m
+
+    m.load_library()
+    return m
+
+
+@pytest.fixture(scope="module")
+def settings8(lw):
+    """Settings with an 8-bit fixed-base window (1.6 GB table: quick to build)."""
+    lw.set_option("window_bits", 8)
+    s = lw.load_trusted_setup_file(os.path.join(GOLDEN, "trusted_setup.txt"))
+    yield s
+    s.free()
+
+
+@pytest.fixture(scope="module")
+def settings13(lw):
+    """The shipping configuration: 13-bit window (32 GiB table)."""
+    lw.set_option("window_bits", 13)
+    s = lw.load_trusted_setup_file(os.path.join(GOLDEN, "trusted_setup.txt"))
+    yield s
+    s.free()
+
+
+@pytest.fixture(scope="module")
+def ref(py_setup):
+    return kzg.RefMode(py_setup)
+
+
+def blob_from_coeffs(coeffs):
+    b = b"".join((c % (1 << 256)).to_bytes(32, "big") for c in coeffs)
+    return b + bytes(kzg.BYTES_PER_BLOB - len(b))
+
+
+def edge_blobs():
+    rnd = random.Random(4844)
+    out = {
+        "zero": bytes(kzg.BYTES_PER_BLOB),
+        "one": blob_from_coeffs([1]),
+        "x": blob_from_coeffs([0, 1]),
+        "top_only": blob_from_coeffs([0] * 4095 + [7]),
+        "all_ff": b"\xff" * kzg.BYTES_PER_BLOB,               # every word >= r (reduced mod r, App. A.1)
+        "r_minus_1": blob_from_coeffs([R - 1] * 4096),
+        "exactly_r": blob_from_coeffs([R] * 4096),              # == all-zero polynomial
+        "r_plus_1": blob_from_coeffs([R + 1, 2 * R + 3, 2 * R - 1] + [0] * 10 + [R]),
+        "random_full": bytes(rnd.randrange(256) for _ in range(kzg.BYTES_PER_BLOB)),
+        "sparse": blob_from_coeffs([rnd.randrange(R) if i % 97 == 0 else 0 for i in range(4096)]),
+        "repeat_digit": blob_from_coeffs([0x0101010101010101010101010101010101010101010101010101010101010101 % R] * 4096),
+    }
+    return out
+
+
+# ------------------------------------------------------------------ setup
+def test_setup_layout(lw, settings8, py_setup):
+    g1 = settings8.g1_values_bytes()
+    for i in (0, 1, 2, 4095):
+        x, y = py_setup.g1[i]
+        want = b"".join(int(v).to_bytes(8, "little") for v in _be_limbs(x)) + b"".join(int(v).to_bytes(8, "little") for v in _be_limbs(y)) + \
+            b"".join(int(v).to_bytes(8, "little") for v in [0, 0, 0, 0, 0, 1])
+        assert g1[144 * i: 144 * i + 144] == want, i
+    g2 = settings8.g2_values_bytes()
+    (x0, x1), (y0, y1) = py_setup.g2[1]
+    want = b"".join(b"".join(int(v).to_bytes(8, "little") for v in _be_limbs(c)) for c in (x0, x1, y0, y1, 1, 0))
+    assert g2[288:576] == want
+    assert settings8.c.fs is not None
+
+
+def _be_limbs(v):
+    """u64 limbs, most significant first (src/srs.rs:131-153)."""
+    return [(v >> (64 * (5 - k))) & 0xFFFFFFFFFFFFFFFF for k in range(6)]
+
+
+def test_load_trusted_setup_bytes_and_badargs(lw, setup_text):
+    lines = setup_text.splitlines()
+    g1 = b"".join(bytes.fromhex(x) for x in lines[2: 2 + 4096])
+    g2 = b"".join(bytes.fromhex(x) for x in lines[2 + 4096: 2 + 4096 + 65])
+    with pytest.raises(lw.KzgError) as e:
+        lw.load_trusted_setup(g1, g2, n1=4095, n2=65)
+    assert e.value.code == lw.C_KZG_BADARGS  # lib.rs:716-718
+    lw.set_option("window_bits", 8)
+    s = lw.load_trusted_setup(g1, g2)
+    try:
+        assert lw.blob_to_kzg_commitment(blob_from_coeffs([0, 1]), s).hex() == lines[3]
+    finally:
+        s.free()
+    bad = bytearray(g1)
+    bad[48] ^= 0x01  # second point no longer on the curve / in the subgroup
+    with pytest.raises(lw.KzgError) as e:
+        lw.load_trusted_setup(bytes(bad), g2)
+    assert e.value.code == lw.C_KZG_ERROR
+
+
+def test_trusted_setup_4_parses_but_cannot_compute(lw):
+    # src/srs.rs:282-295 only asserts that the short setup parses
+    s = lw.load_trusted_setup_file(os.path.join(GOLDEN, "trusted_setup_4.txt"))
+    try:
+        with pytest.raises(lw.KzgError) as e:
+            lw.blob_to_kzg_commitment(bytes(kzg.BYTES_PER_BLOB), s)
+        assert e.value.code == lw.C_KZG_ERROR
+    finally:
+        s.free()
+
+
+# ------------------------------------------------------------------ reference tests re-expressed
+def test_lib_test_simple_poly_1(lw, settings8):
+    """tests/lib_test.rs:19-87: p = 1, z = 1 -> y = 1, proof = infinity, verifies."""
+    blob = blob_from_coeffs([1])
+    z = (1).to_bytes(32, "big")
+    proof, y = lw.compute_kzg_proof(blob, z, settings8)
+    assert int.from_bytes(y, "big") == 1
+    assert proof == bytes([0xC0]) + bytes(47)
+    commitment = bytes.fromhex(GEN_HEX)  # commit(1) = G for any SRS
+    assert lw.verify_kzg_proof(commitment, z, y, proof, settings8) is True
+
+
+def test_lib_test_simple_poly_2(lw, settings8, setup_text):
+    """tests/lib_test.rs:89-167: p = X, z = 2 -> y = 2, proof = g1[0], commitment = g1[1]."""
+    lines = setup_text.splitlines()
+    blob = blob_from_coeffs([0, 1])
+    z = (2).to_bytes(32, "big")
+    proof, y = lw.compute_kzg_proof(blob, z, settings8)
+    assert y == z
+    assert proof.hex() == lines[2]
+    commitment = lw.blob_to_kzg_commitment(blob, settings8)
+    assert commitment.hex() == lines[3]
+    assert lw.verify_kzg_proof(commitment, z, y, proof, settings8) is True
+
+
+def test_lib_test_batch_proof(lw, settings8, ref):
+    """tests/lib_test.rs:169-260: both pairs through verify_blob_kzg_proof_batch(n = 2).
+    (The reference test feeds compute_kzg_proof outputs at z = 1, 2 -- valid for any
+    Fiat-Shamir z because deg <= 1: the quotient is constant.)"""
+    b1, b2 = blob_from_coeffs([1]), blob_from_coeffs([0, 1])
+    p1, _ = lw.compute_kzg_proof(b1, (1).to_bytes(32, "big"), settings8)
+    p2, _ = lw.compute_kzg_proof(b2, (2).to_bytes(32, "big"), settings8)
+    c1, c2 = lw.blob_to_kzg_commitment(b1, settings8), lw.blob_to_kzg_commitment(b2, settings8)
+    assert lw.verify_blob_kzg_proof_batch([b1, b2], [c1, c2], [p1, p2], settings8) is True
+    assert ref.verify_blob_kzg_proof_batch([b1, b2], [c1, c2], [p1, p2]) is True
+
+
+def test_lib_test_read_srs(lw, settings8):
+    """tests/lib_test.rs:262-291: first SRS point compresses to the generator."""
+    assert lw.blob_to_kzg_commitment(blob_from_coeffs([1]), settings8).hex() == GEN_HEX
+
+
+def test_compression_kats(lw, settings8):
+    """src/compression.rs:168-221 through the ABI: generator / 2G / infinity / KAT point round trips."""
+    s = settings8
+    two_g = bls.g1_compress(bls.g1_mul(bls.G1, 2))
+    kat = bytes.fromhex("8d0c6eeadd3f8529d67246f77404a4ac2d9d7fd7d50cf103d3e6abb9003e5e36d8f322663ebced6707a7f46d97b7566d")
+    for enc in (bytes.fromhex(GEN_HEX), two_g, bytes([0xC0]) + bytes(47), kat):
+        # compute_blob_kzg_proof decodes (and validates) the commitment; for the zero
+        # blob the proof is infinity whatever the commitment is
+        assert lw.compute_blob_kzg_proof(bytes(kzg.BYTES_PER_BLOB), enc, s) == bytes([0xC0]) + bytes(47)
+    for bad in (bytes(48), bytes([0x80]) + bytes(47), bls.g1_compress((0, 2))):  # (0,2): on curve, not in G1
+        with pytest.raises(lw.KzgError) as e:
+            lw.compute_blob_kzg_proof(bytes(kzg.BYTES_PER_BLOB), bad, s)
+        assert e.value.code == lw.C_KZG_ERROR
+
+
+# ------------------------------------------------------------------ oracle differential
+def test_ref_mode_kats(lw, settings8):
+    kats = json.load(open(os.path.join(GOLDEN, "ref_mode_kats.json")))
+    idx = json.load(open(os.path.join(GOLDEN, "ckzg_le_vectors.json")))["blobs"]
+    blobs_bin = open(os.path.join(GOLDEN, "ckzg_le_blobs.bin"), "rb").read()
+    for k in kats:
+        off, ln = idx[k["blob"]]
+        blob = blobs_bin[off: off + ln]
+        com = lw.blob_to_kzg_commitment(blob, settings8)
+        assert com.hex() == k["commitment"], k["name"]
+        proof, y = lw.compute_kzg_proof(blob, (2).to_bytes(32, "big"), settings8)
+        assert (proof.hex(), y.hex()) == (k["z2_proof"], k["z2_y"]), k["name"]
+        bp = lw.compute_blob_kzg_proof(blob, com, settings8)
+        assert bp.hex() == k["blob_proof"], k["name"]
+        assert lw.verify_blob_kzg_proof(blob, com, bp, settings8) is True
+        assert lw.verify_kzg_proof(com, bytes.fromhex(k["fs_z"]), bytes.fromhex(k["fs_y"]), bp, settings8) is True
+
+
+@pytest.mark.parametrize("which", ["settings8", "settings13"])
+def test_edge_blobs_vs_oracle(lw, ref, request, which):
+    s = request.getfixturevalue(which)
+    blobs = edge_blobs()
+    names = list(blobs)
+    cat = b"".join(blobs[n] for n in names)
+    coms, proofs, st = lw.commit_and_prove_batch(cat, len(names), s)
+    assert st == [0] * len(names)
+    for n, c, p in zip(names, coms, proofs):
+        want_c = ref.blob_to_kzg_commitment(blobs[n])
+        assert c == want_c, n
+        assert p == ref.compute_blob_kzg_proof(blobs[n], want_c), n
+        assert lw.blob_to_kzg_commitment(blobs[n], s) == want_c, n
+    ok = lw.verify_blob_kzg_proof_batch([blobs[n] for n in names], coms, proofs, s)
+    assert ok is True
+
+
+def test_synthetic_batch_vs_oracle(lw, settings13, ref):
+    n = 24
+    blobs = [lw.synth_blob_host(k) for k in range(n)]
+    coms, proofs, st = lw.commit_and_prove_batch(b"".join(blobs), n, settings13)
+    assert st == [0] * n
+    for k in range(n):
+        c = ref.blob_to_kzg_commitment(blobs[k])
+        assert coms[k] == c, k
+        assert proofs[k] == ref.compute_blob_kzg_proof(blobs[k], c), k
+    # the separate entry points give the same bytes
+    coms2, st2 = lw.blob_to_kzg_commitment_batch(b"".join(blobs), n, settings13)
+    proofs2, st3 = lw.compute_blob_kzg_proof_batch(b"".join(blobs), b"".join(coms), n, settings13)
+    assert coms2 == coms and proofs2 == proofs and st2 == st3 == [0] * n
+    zs = [(k * 7919 + 1).to_bytes(32, "big") for k in range(n)]
+    pp, yy, st4 = lw.compute_kzg_proof_batch(b"".join(blobs), b"".join(zs), n, settings13)
+    for k in range(0, n, 5):
+        wp, wy = ref.compute_kzg_proof(blobs[k], zs[k])
+        assert (pp[k], yy[k]) == (wp, wy)
+
+
+def test_fuzz_corpus_differential(lw, settings8, ref):
+    meta = json.load(open(os.path.join(GOLDEN, "fuzz_corpus.json")))
+    raw = open(os.path.join(GOLDEN, "fuzz_corpus.bin"), "rb").read()
+    B = kzg.BYTES_PER_BLOB
+
+    def both(fn_gpu, fn_ref):
+        try:
+            want = ("ok", fn_ref())
+        except kzg.KzgError as e:
+            want = ("err", e.code)
+        try:
+            got = ("ok", fn_gpu())
+        except lw.KzgError as e:
+            got = ("err", e.code)
+        assert got == want
+
+    for case in meta["cases"]:
+        off, ln = meta["blobs"][case["data"]]
+        d = raw[off: off + ln]
+        suite = case["suite"]
+        if suite == "blob_to_kzg_commitment":
+            both(lambda: lw.blob_to_kzg_commitment(d, settings8), lambda: ref.blob_to_kzg_commitment(d))
+        elif suite == "compute_kzg_proof":
+            both(lambda: lw.compute_kzg_proof(d[:B], d[B:], settings8), lambda: ref.compute_kzg_proof(d[:B], d[B:]))
+        elif suite == "compute_blob_kzg_proof":
+            both(lambda: lw.compute_blob_kzg_proof(d[:B], d[B:], settings8), lambda: ref.compute_blob_kzg_proof(d[:B], d[B:]))
+        elif suite == "verify_kzg_proof":
+            both(lambda: lw.verify_kzg_proof(d[:48], d[48:80], d[80:112], d[112:], settings8),
+                 lambda: ref.verify_kzg_proof(d[:48], d[48:80], d[80:112], d[112:]))
+        elif suite == "verify_blob_kzg_proof":
+            both(lambda: lw.verify_blob_kzg_proof(d[:B], d[B:B + 48], d[B + 48:], settings8),
+                 lambda: ref.verify_blob_kzg_proof(d[:B], d[B:B + 48], d[B + 48:]))
+        elif suite == "verify_blob_kzg_proof_batch":
+            n = case["n"]
+            blobs = [d[i * B:(i + 1) * B] for i in range(n)]
+            cs = [d[n * B + 48 * i: n * B + 48 * i + 48] for i in range(n)]
+            ps = [d[n * B + 48 * n + 48 * i: n * B + 48 * n + 48 * i + 48] for i in range(n)]
+            both(lambda: lw.verify_blob_kzg_proof_batch(blobs, cs, ps, settings8), lambda: ref.verify_blob_kzg_proof_batch(blobs, cs, ps))
+
+
+# ------------------------------------------------------------------ verification outcomes
+def test_verify_negative_and_errors(lw, settings8, ref):
+    rnd = random.Random(99)
+    blob = lw.synth_blob_host(12345)
+    com = lw.blob_to_kzg_commitment(blob, settings8)
+    proof = lw.compute_blob_kzg_proof(blob, com, settings8)
+    assert lw.verify_blob_kzg_proof(blob, com, proof, settings8) is True
+    g = bytes.fromhex(GEN_HEX)
+    assert lw.verify_blob_kzg_proof(blob, com, g, settings8) is False
+    assert lw.verify_blob_kzg_proof(blob, g, proof, settings8) is False
+    blob2 = bytearray(blob); blob2[77] ^= 1
+    assert lw.verify_blob_kzg_proof(bytes(blob2), com, proof, settings8) is False
+    z = rnd.randrange(R).to_bytes(32, "big")
+    p2, y2 = lw.compute_kzg_proof(blob, z, settings8)
+    assert lw.verify_kzg_proof(com, z, y2, p2, settings8) is True
+    ybad = ((int.from_bytes(y2, "big") + 1) % R).to_bytes(32, "big")
+    assert lw.verify_kzg_proof(com, z, ybad, p2, settings8) is False
+    # non-canonical y (y + r) is reduced, not rejected (App. A.1)
+    ynon = int.from_bytes(y2, "big") + R
+    if ynon < 1 << 256:
+        assert lw.verify_kzg_proof(com, z, ynon.to_bytes(32, "big"), p2, settings8) is True
+    for badpt in (bytes(48), bls.g1_compress((0, 2))):
+        with pytest.raises(lw.KzgError):
+            lw.verify_kzg_proof(badpt, z, y2, p2, settings8)
+        with pytest.raises(lw.KzgError):
+            lw.verify_blob_kzg_proof(blob, com, badpt, settings8)
+    # infinity proof / commitment are legal encodings
+    inf = bytes([0xC0]) + bytes(47)
+    assert lw.verify_kzg_proof(inf, z, bytes(32), inf, settings8) is True  # p = 0
+    assert lw.verify_kzg_proof(com, z, y2, inf, settings8) is ref.verify_kzg_proof(com, z, y2, inf)
+
+
+def test_batch_verify_outcomes(lw, settings8, ref):
+    n = 5
+    blobs = [lw.synth_blob_host(1000 + k) for k in range(n)]
+    coms, proofs, _ = lw.commit_and_prove_batch(b"".join(blobs), n, settings8)
+    assert lw.verify_blob_kzg_proof_batch(blobs, coms, proofs, settings8) is True
+    assert lw.verify_blob_kzg_proof_batch([], [], [], settings8) is False          # lib.rs:538-543
+    assert lw.verify_blob_kzg_proof_batch(blobs[:1], coms[:1], proofs[:1], settings8) is True
+    bad = list(proofs); bad[3] = bytes.fromhex(GEN_HEX)
+    assert lw.verify_blob_kzg_proof_batch(blobs, coms, bad, settings8) is False
+    assert ref.verify_blob_kzg_proof_batch(blobs, coms, bad) is False
+    swapped = [proofs[1], proofs[0]] + proofs[2:]
+    assert lw.verify_blob_kzg_proof_batch(blobs, coms, swapped, settings8) is False
+    inval = list(coms); inval[2] = bytes(48)
+    with pytest.raises(lw.KzgError) as e:
+        lw.verify_blob_kzg_proof_batch(blobs, inval, proofs, settings8)
+    assert e.value.code == lw.C_KZG_ERROR
+    # phases == monolithic call, for 1, 2 and 3 simulated ranks
+    for world in (1, 2, 3):
+        tuples, shards = [], []
+        for r in range(world):
+            first, cnt = lw.shard_range(n, world, r)
+            shards.append((first, cnt))
+        # single process: phase1 of a rank must be followed by its phase2, so gather tuples first
+        for first, cnt in shards:
+            tuples.append(lw.verify_batch_phase1(b"".join(blobs[first:first + cnt]), b"".join(coms[first:first + cnt]),
+                                                 b"".join(proofs[first:first + cnt]), cnt, settings8))
+        all_t = b"".join(tuples)
+        parts = []
+        for first, cnt in shards:
+            lw.verify_batch_phase1(b"".join(blobs[first:first + cnt]), b"".join(coms[first:first + cnt]),
+                                   b"".join(proofs[first:first + cnt]), cnt, settings8)
+            parts.append(lw.verify_batch_phase2(all_t, n, first, cnt, settings8) if cnt else bytes(288))
+        assert lw.verify_batch_phase3(b"".join(parts), world, settings8) is True
+
+
+def test_g1_lincomb(lw, py_setup):
+    rnd = random.Random(5)
+    n = 37
+    pts = [py_setup.g1[rnd.randrange(4096)] for _ in range(n)]
+    pts[3] = None
+    sc = [rnd.randrange(1 << 256) for _ in range(n)]
+    sc[5] = 0
+    pb = b"".join(bytes(96) if p is None else p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big") for p in pts)
+    sb = b"".join(s.to_bytes(32, "big") for s in sc)
+    want = bls.g1_compress(bls.g1_msm(pts, [s % R for s in sc]))
+    assert lw.g1_lincomb(pb, sb, n) == want
+    assert lw.g1_lincomb(b"", b"", 0) == bytes([0xC0]) + bytes(47)
+
+
+# ------------------------------------------------------------------ hand-built settings (fs == NULL) and bad SRS
+def test_hand_built_settings(lw, settings8, py_setup):
+    from lambdaworks_kzg_b200.api import CKZGSettings
+
+    g1 = ctypes.create_string_buffer(settings8.g1_values_bytes(), 4096 * 144)
+    g2 = ctypes.create_string_buffer(settings8.g2_values_bytes(), 65 * 288)
+    s = CKZGSettings(None, ctypes.cast(g1, ctypes.c_void_p), ctypes.cast(g2, ctypes.c_void_p))
+    lw.set_option("window_bits", 8)
+    blob = lw.synth_blob_host(7)
+    assert lw.blob_to_kzg_commitment(blob, s) == lw.blob_to_kzg_commitment(blob, settings8)
+    # swap two SRS points in place: content hash changes -> new context, new result
+    raw = bytearray(g1.raw)
+    raw[0:144], raw[144:288] = raw[144:288], raw[0:144]
+    ctypes.memmove(g1, bytes(raw), len(raw))
+    swapped = kzg.Setup(g1=[py_setup.g1[1], py_setup.g1[0]] + py_setup.g1[2:], g2=py_setup.g2, tau=None)
+    small = blob_from_coeffs([5, 9, 11])
+    assert lw.blob_to_kzg_commitment(small, s) == kzg.RefMode(swapped, generic=True).blob_to_kzg_commitment(small)
+    # an infinity / off-curve g1 value makes every call fail (SRS re-hydration, srs.rs:155-172)
+    raw[288:288 + 96] = bytes(96)
+    ctypes.memmove(g1, bytes(raw), len(raw))
+    with pytest.raises(lw.KzgError) as e:
+        lw.blob_to_kzg_commitment(small, s)
+    assert e.value.code == lw.C_KZG_ERROR
+
+
+# ------------------------------------------------------------------ device API + full-size properties
+def test_device_api_and_large_batch_properties(lw, settings13, ref):
+    import torch
+
+    n = 1024
+    dev = torch.device("cuda", 0)
+    blobs = torch.empty(n * kzg.BYTES_PER_BLOB, dtype=torch.uint8, device=dev)
+    lw.synth_blobs_device(blobs.data_ptr(), 0, n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = bytes(blobs[: 2 * kzg.BYTES_PER_BLOB].cpu().numpy().tobytes())
+    assert host[: kzg.BYTES_PER_BLOB] == lw.synth_blob_host(0) and host[kzg.BYTES_PER_BLOB:] == lw.synth_blob_host(1)
+    coms = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+    proofs = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+    status = torch.ones(n, dtype=torch.int32, device=dev)
+    lw.commit_and_prove_batch_device(coms.data_ptr(), proofs.data_ptr(), blobs.data_ptr(), n, settings13,
+                                     torch.cuda.current_stream().cuda_stream, status.data_ptr())
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    cb, pb = bytes(coms.cpu().numpy().tobytes()), bytes(proofs.cpu().numpy().tobytes())
+    for k in (0, 1, 511, 512, 1023):
+        blob = lw.synth_blob_host(k)
+        c = ref.blob_to_kzg_commitment(blob)
+        assert cb[48 * k: 48 * k + 48] == c, k
+        assert pb[48 * k: 48 * k + 48] == ref.compute_blob_kzg_proof(blob, c), k
+    # size-independent property at the full batch: every (blob, C, pi) verifies, and one
+    # corrupted proof flips the batch result
+    all_blobs = bytes(blobs.cpu().numpy().tobytes())
+    bl = [all_blobs[i * kzg.BYTES_PER_BLOB:(i + 1) * kzg.BYTES_PER_BLOB] for i in range(n)]
+    cl = [cb[48 * i: 48 * i + 48] for i in range(n)]
+    pl = [pb[48 * i: 48 * i + 48] for i in range(n)]
+    assert lw.verify_blob_kzg_proof_batch(bl, cl, pl, settings13) is True
+    pl[777] = bytes.fromhex(GEN_HEX)
+    assert lw.verify_blob_kzg_proof_batch(bl, cl, pl, settings13) is False
+    # checksum of checksums: sum of commitments == commitment of the summed blob (linearity)
+    total = [0] * 4096
+    for k in range(8):
+        for i in range(4096):
+            total[i] += int.from_bytes(bl[k][32 * i: 32 * i + 32], "big")
+    summed = blob_from_coeffs([t % R for t in total])
+    want = bls.g1_compress(bls.g1_sum(bls.g1_decompress(cl[k]) for k in range(8)))
+    assert lw.blob_to_kzg_commitment(summed, settings13) == want
