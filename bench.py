@@ -1,0 +1,262 @@
+#!/usr/bin/env python3
+"""Benchmark of the EIP-4844 commit+proof hot path (BASELINE.json metric:
+blobs/sec commit+proof at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one pass of the hot path over one batch: for each of 1024 synthetic
+blobs per GPU (SURVEY §8d generator), commitment = blob_to_kzg_commitment(blob)
+and proof = compute_blob_kzg_proof(blob, commitment), through the library's
+batch entry point.  Blob batches shard across GPUs with no collective (weak
+scaling: every rank processes its own 1024 blobs); the only distributed calls
+are the barriers / max-reduction of the timing itself.
+
+Printed JSON line (rank 0): `value` = whole-job blobs/s with blobs resident in
+HBM; `e2e` = the same metric through the host-buffer C ABI call
+(lwkzg_commit_and_prove_batch) from pinned host memory, H2D/D2H inside the
+timed region; `roofline` = the dominant kernel (batched fixed-base MSM gather)
+against the integer-multiply (IMAD) peak measured in this run, plus its HBM
+figure; `cpu_baseline` = the C restatement of the reference's CPU path
+(oracle/c) on a bounded sample of the same workload.
+
+--impl reference times that CPU restatement alone (the reference's own Rust
+code cannot be built here: no cargo, un-vendored git dependencies).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOBS_PER_GPU = 1024
+BLOB_BYTES = 4096 * 32
+SETUP = os.path.join(ROOT, "tests", "golden", "trusted_setup.txt")
+MAC32_PER_MSM = 2.80e8  # fixed-base signed-digit MSM-4096, c = 13: 933 888 Fp mul x 300 MAC32
+MAC32_PER_BLOB = 2 * MAC32_PER_MSM
+METRIC = "blobs/sec commit+proof"
+UNIT = "blobs/s"
+
+
+def workload_name(n, wb):
+    return ("commit+proof (blob_to_kzg_commitment + compute_blob_kzg_proof) of %d synthetic 4096-element blobs per GPU, "
+            "tests/golden/trusted_setup.txt (monomial, tau=1337), fixed-base window %d bits" % (n, wb))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0]
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_run(steps, warmup, sample_blobs=None):
+    """Time the C restatement of the reference's CPU path with all host threads."""
+    from oracle import c_oracle
+    import lambdaworks_kzg_b200 as lw
+
+    oracle = c_oracle.COracle(open(SETUP).read())
+    cores = oracle.max_threads()
+    n = sample_blobs or max(16, 2 * cores)
+    blobs = b"".join(lw.synth_blob_host(k) for k in range(n))
+    for _ in range(min(warmup, 1)):
+        oracle.commit_and_prove_batch(blobs[: BLOB_BYTES * min(n, cores)], min(n, cores), cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rc, _, _ = oracle.commit_and_prove_batch(blobs, n, cores)
+        assert rc == 0
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d synthetic blobs per step (same generator as the GPU arm), one blob per thread, %d threads; "
+                      "C restatement of the reference algorithm (per-call SRS re-hydration, Pippenger w=9, projective)" % (n, cores)}, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--blobs", type=int, default=BLOBS_PER_GPU)
+    ap.add_argument("--window-bits", type=int, default=13)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n = args.blobs
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        base, dt = cpu_reference_run(steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64 (6x64-bit Montgomery limbs)", "data": "synthetic",
+                "config": {"workload": workload_name(n, args.window_bits) + "; CPU arm: bounded sample per step, see cpu_baseline.sample"},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import lambdaworks_kzg_b200 as lw
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lw.set_option("window_bits", args.window_bits)
+    settings = lw.load_trusted_setup_file(SETUP)
+    wb = lw.window_bits(settings)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- device-resident inputs: this rank's shard of the global synthetic batch
+    blobs = torch.empty(n * BLOB_BYTES, dtype=torch.uint8, device=dev)
+    lw.synth_blobs_device(blobs.data_ptr(), rank * n, n, stream)
+    coms = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+    proofs = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def step():
+        lw.commit_and_prove_batch_device(coms.data_ptr(), proofs.data_ptr(), blobs.data_ptr(), n, settings, stream, status.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lw.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lw.kernel_launches() - launches0
+    ms = e0.elapsed_time(e1)
+    assert int(status.abs().sum()) == 0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI call (pinned host memory)
+    h_blobs = torch.empty(n * BLOB_BYTES, dtype=torch.uint8).pin_memory()
+    h_blobs.copy_(blobs)
+    h_coms = torch.zeros(n * 48, dtype=torch.uint8).pin_memory()
+    h_proofs = torch.zeros(n * 48, dtype=torch.uint8).pin_memory()
+    for _ in range(min(args.warmup, 2)):
+        lw.commit_and_prove_batch(h_blobs.data_ptr(), n, settings, h_coms.data_ptr(), h_proofs.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = lw.commit_and_prove_batch(h_blobs.data_ptr(), n, settings, h_coms.data_ptr(), h_proofs.data_ptr())
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    assert not any(st)
+    assert bytes(h_coms.numpy().tobytes()) == bytes(coms.cpu().numpy().tobytes()), "host-API and device-API commitments differ"
+    assert bytes(h_proofs.numpy().tobytes()) == bytes(proofs.cpu().numpy().tobytes()), "host-API and device-API proofs differ"
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (measured alone, CUDA events on its own stream)
+    roofline = cpu_base = None
+    if rank == 0:
+        k_ms = lw.bench_msm_kernel(blobs.data_ptr(), n, settings, 0, 5)
+        peak = max(lw.imad_peak(1), lw.imad_peak(0))
+        achieved = n * MAC32_PER_MSM / (k_ms * 1e-3)
+        nwin = 255 // wb + 1
+        alg_bytes = n * (BLOB_BYTES + 4096 * nwin * 96)  # scalars streamed once + one 96 B table entry per (point, window)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline = {"bound": "int32-imad", "kernel": "msm_gather_kernel<BE>", "achieved": achieved / 1e12, "peak": peak / 1e12,
+                    "unit": "TMAC32/s", "frac": achieved / peak,
+                    "peak_source": "lwkzg_imad_peak(): dependency-free mad.wide.u32 probe run in this process (burst)",
+                    "alg_mac32_per_launch": n * MAC32_PER_MSM, "kernel_ms": k_ms,
+                    "kernel_share_of_step": 2 * k_ms / ms_per_step,
+                    "traffic": None,
+                    "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "alg_bytes_per_launch": alg_bytes,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
+        if world == 1:
+            cpu_base, _ = cpu_reference_run(1, 1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 (12x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic",
+                "config": {"workload": workload_name(n, wb), "blobs_per_gpu": n, "global_blobs": world * n, "parallelism": "blob-sharded x%d, no collective" % world,
+                           "l2_policy": "inputs larger than L2: 128 MiB of blobs + random gathers from a %.1f GiB table per step" % (
+                               (255 // wb + 1) * 4096 * (1 << (wb - 1)) * 96 / 2**30)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * BLOB_BYTES, "d2h_bytes_per_step": n * (48 + 48 + 4),
+                        "api": "lwkzg_commit_and_prove_batch (host buffers, pinned)"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
+        print(json.dumps(line))
+    settings.free()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -190,6 +190,16 @@ void lwkzg_synth_blob_host(uint8_t *blob, uint64_t k);
  * second) for variant 0 = mad.lo.cc/madc.hi.cc pairs, 1 = mad.wide.u32. */
 double lwkzg_imad_peak(int variant);
 
+/* Measurement hook for the roofline: launches the dominant kernel (the batched
+ * fixed-base MSM gather over n device-resident blobs) alone, `iters` times
+ * after one warm-up, bracketed by CUDA events on its own stream; returns the
+ * average milliseconds per launch (< 0 on error).  blocks_per_blob 0 = auto. */
+double lwkzg_bench_msm_kernel(const void *d_blobs, size_t n, int blocks_per_blob, int iters,
+                              const KZGSettings *s);
+/* fixed-base window actually in use for these settings (may be smaller than
+ * the "window_bits" option if HBM was short), -1 on error */
+int lwkzg_window_bits(const KZGSettings *s);
+
 /* Options: "window_bits" (fixed-base table window c, 4..15; default 13; must
  * be set before the settings are first used), "msm_blocks_per_blob" (0 = auto),
  * "chunk_blobs" (host-batch pipeline chunk, default 256).  Returns 0 on success. */

@@ -17,6 +17,8 @@ from .api import (  # noqa: F401
     C_KZG_MALLOC,
     C_KZG_OK,
     KzgError,
+    bench_msm_kernel,
+    window_bits,
     Settings,
     blob_to_kzg_commitment,
     blob_to_kzg_commitment_batch,

@@ -81,6 +81,10 @@ def load_library() -> ctypes.CDLL:
     lib.lwkzg_get_option.restype = ctypes.c_long
     lib.lwkzg_imad_peak.argtypes = [ctypes.c_int]
     lib.lwkzg_imad_peak.restype = ctypes.c_double
+    lib.lwkzg_bench_msm_kernel.argtypes = [vp, sz, ctypes.c_int, ctypes.c_int, sp]
+    lib.lwkzg_bench_msm_kernel.restype = ctypes.c_double
+    lib.lwkzg_window_bits.argtypes = [sp]
+    lib.lwkzg_window_bits.restype = ctypes.c_int
     lib.lwkzg_kernel_launches.argtypes = []
     lib.lwkzg_kernel_launches.restype = ctypes.c_uint64
     lib.lwkzg_last_error.argtypes = []
@@ -284,6 +288,18 @@ def commit_and_prove_batch_device(d_commitments: int, d_proofs: int, d_blobs: in
     cudaStream_t handle (torch: torch.cuda.current_stream().cuda_stream)."""
     _check(load_library().lwkzg_commit_and_prove_batch_device(d_commitments, d_proofs, d_blobs, n, _sp(s), stream, d_status),
            "lwkzg_commit_and_prove_batch_device")
+
+
+def bench_msm_kernel(d_blobs: int, n: int, s, blocks_per_blob: int = 0, iters: int = 5) -> float:
+    """Average ms per launch of the dominant kernel alone (roofline leg)."""
+    ms = float(load_library().lwkzg_bench_msm_kernel(d_blobs, n, blocks_per_blob, iters, _sp(s)))
+    if ms < 0:
+        raise KzgError(C_KZG_ERROR, "lwkzg_bench_msm_kernel", last_error())
+    return ms
+
+
+def window_bits(s) -> int:
+    return int(load_library().lwkzg_window_bits(_sp(s)))
 
 
 def synth_blobs_device(d_blobs: int, first_blob: int, n: int, stream: int = 0):

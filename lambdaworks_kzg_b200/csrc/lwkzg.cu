@@ -975,6 +975,36 @@ C_KZG_RET lwkzg_verify_batch_phase3(bool* ok, const uint8_t* partials288, size_t
   return C_KZG_OK;
 }
 
+// ---- measurement hook: the dominant kernel alone, timed with CUDA events on
+// the stream it is launched on (bench.py's roofline leg)
+double lwkzg_bench_msm_kernel(const void* d_blobs, size_t n, int blocks_per_blob, int iters, const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  if (!c || !c->srs_valid || n == 0 || iters <= 0) return -1.0;
+  CtxLock L(c);
+  Slot& sl = c->slot[0];
+  int bpb = blocks_per_blob > 0 ? blocks_per_blob : auto_bpb((int)n);
+  cudaStreamSynchronize(sl.st);
+  if (!slot_reserve(sl, (int)n, bpb, false)) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  launch_msm_gather(sl.partials.p, c->d_table, c->c, d_blobs, true, (int)n, bpb, sl.st);  // warm-up
+  cudaEventRecord(e0, sl.st);
+  for (int i = 0; i < iters; i++) launch_msm_gather(sl.partials.p, c->d_table, c->c, d_blobs, true, (int)n, bpb, sl.st);
+  cudaEventRecord(e1, sl.st);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  return (double)ms / iters;
+}
+int lwkzg_window_bits(const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  return c ? c->c : -1;
+}
+
 // ---- generic linear combination (g1_lincomb, lib.rs:241-243)
 C_KZG_RET lwkzg_g1_lincomb(Bytes48* out, const uint8_t* points_xy_be, const uint8_t* scalars_be, size_t n) {
   if (!out) return C_KZG_ERROR;
