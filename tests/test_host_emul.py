@@ -281,3 +281,4 @@ def test_pairing_check(lib, py_setup):
     # infinity pairs contribute 1
     assert lib.emul_pairing_check(aff_bytes(None), _g2_bytes(g2_0), aff_bytes(None), _g2_bytes(g2_1)) == 1
     assert lib.emul_pairing_check(aff_bytes(bls.G1), _g2_bytes(g2_0), aff_bytes(None), _g2_bytes(g2_1)) == 0
+
