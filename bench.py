@@ -232,8 +232,12 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         roofline = {"bound": "int32-imad", "kernel": "msm_gather_kernel<BE>", "achieved": achieved / 1e12, "peak": peak / 1e12,
                     "unit": "TMAC32/s", "frac": achieved / peak,
-                    "peak_source": "lwkzg_imad_peak(): dependency-free mad.wide.u32 probe run in this process (burst)",
+                    "peak_source": "lwkzg_imad_peak(): memory-free IMAD.WIDE probe with distinct operand registers, run in this process "
+                                   "(burst; best of carry-chain and carry-less variants; see profiles/r01_pipe_probe.md)",
                     "alg_mac32_per_launch": n * MAC32_PER_MSM, "kernel_ms": k_ms,
+                    # what the kernel really executes: one 10-multiplication mixed addition per (point, window), 300 MAC32 each
+                    "executed_mac32_per_launch": n * 4096 * nwin * 10 * 300.0,
+                    "frac_executed": n * 4096 * nwin * 10 * 300.0 / (k_ms * 1e-3) / peak,
                     "kernel_share_of_step": 2 * k_ms / ms_per_step,
                     "traffic": None,
                     "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -185,9 +185,11 @@ C_KZG_RET lwkzg_synth_blobs_device(void *d_blobs, uint64_t first_blob, size_t n,
 /* same generator on the host (tests / CPU baseline feed) */
 void lwkzg_synth_blob_host(uint8_t *blob, uint64_t k);
 
-/* Integer-pipe peak probe: runs a dependency-free IMAD micro-kernel on the
- * current device and returns MAC32/s (32x32+64 multiply-accumulates per
- * second) for variant 0 = mad.lo.cc/madc.hi.cc pairs, 1 = mad.wide.u32. */
+/* Integer-pipe peak probe (the roofline denominator R_int): runs a memory-free
+ * IMAD micro-kernel with DISTINCT operand registers per MAC on the current
+ * device and returns MAC32/s (32x32+64 multiply-accumulates per second).
+ * variant 0 = carry chain of mad.lo.cc/madc.hi.cc pairs (IMAD.WIDE.U32.X, one
+ * row of the Montgomery product), 1 = carry-less 64-bit columns (IMAD.WIDE.U32). */
 double lwkzg_imad_peak(int variant);
 
 /* Measurement hook for the roofline: launches the dominant kernel (the batched

@@ -53,44 +53,53 @@ extern "C" void lwkzg_synth_blob_host(uint8_t* blob, uint64_t k) {
   for (uint32_t i = 0; i < 4096; i++) synth_word(blob + 32 * i, k, i);
 }
 
-// ---- IMAD peak probe: CHAINS independent accumulator chains per thread, no
-// memory traffic.  variant 0: mad.lo.cc + madc.hi pairs (what the field code is
-// written in; ptxas fuses them to IMAD.WIDE.U32), variant 1: mad.wide.u32.
-constexpr int PROBE_CHAINS = 8;
-constexpr int PROBE_ITERS = 4096;
+// ---- IMAD peak probe (roofline denominator R_int).  Operands are DISTINCT
+// registers per MAC, as in a real multi-limb product: with a single shared
+// multiplicand pair the operand-reuse cache makes IMAD.WIDE look twice as fast
+// as it is in practice (profiles/r01_pipe_probe.md).
+// variant 0: a carry chain of fused mad.lo.cc/madc.hi.cc pairs (IMAD.WIDE.U32.X,
+//            exactly one row of the Montgomery product in mont.cuh)
+// variant 1: carry-less 64-bit column accumulation (IMAD.WIDE.U32)
+constexpr int PROBE_LIMBS = 12;
+constexpr int PROBE_ITERS = 2048;
 
-__global__ void __launch_bounds__(256) imad_probe_pairs(uint32_t* out, uint32_t seed) {
-  uint32_t lo[PROBE_CHAINS], hi[PROBE_CHAINS];
-  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+__global__ void __launch_bounds__(256) imad_probe_chain(uint32_t* out, uint32_t seed) {
+  uint32_t a[PROBE_LIMBS], t[2 * PROBE_LIMBS];
+  uint32_t b = seed * 3u + blockIdx.x + 1u;
 #pragma unroll
-  for (int c = 0; c < PROBE_CHAINS; c++) { lo[c] = a + c; hi[c] = b + c; }
+  for (int i = 0; i < PROBE_LIMBS; i++) a[i] = seed + threadIdx.x * 31u + i * 977u;
+#pragma unroll
+  for (int i = 0; i < 2 * PROBE_LIMBS; i++) t[i] = i + threadIdx.x;
   for (int it = 0; it < PROBE_ITERS; it++) {
+    t[0] = ptx::mad_lo_cc(a[0], b, t[0]);
+    t[1] = ptx::madc_hi_cc(a[0], b, t[1]);
 #pragma unroll
-    for (int c = 0; c < PROBE_CHAINS; c++) {
-      lo[c] = ptx::mad_lo_cc(a, b, lo[c]);
-      hi[c] = ptx::madc_hi(a, b, hi[c]);
+    for (int j = 1; j < PROBE_LIMBS; j++) {
+      t[2 * j] = ptx::madc_lo_cc(a[j], b, t[2 * j]);
+      t[2 * j + 1] = ptx::madc_hi_cc(a[j], b, t[2 * j + 1]);
     }
-    a += hi[0];
+    b += t[3];
   }
   uint32_t acc = 0;
 #pragma unroll
-  for (int c = 0; c < PROBE_CHAINS; c++) acc ^= lo[c] ^ hi[c];
+  for (int i = 0; i < 2 * PROBE_LIMBS; i++) acc ^= t[i];
   if (acc == 0x12345678u) out[0] = acc;  // keep the chains alive
 }
 
 __global__ void __launch_bounds__(256) imad_probe_wide(uint32_t* out, uint32_t seed) {
-  unsigned long long acc[PROBE_CHAINS];
-  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  uint32_t a[PROBE_LIMBS];
+  unsigned long long c[PROBE_LIMBS];
+  uint32_t b = seed * 3u + blockIdx.x + 1u;
 #pragma unroll
-  for (int c = 0; c < PROBE_CHAINS; c++) acc[c] = a + c;
+  for (int i = 0; i < PROBE_LIMBS; i++) { a[i] = seed + threadIdx.x * 31u + i * 977u; c[i] = i + threadIdx.x; }
   for (int it = 0; it < PROBE_ITERS; it++) {
 #pragma unroll
-    for (int c = 0; c < PROBE_CHAINS; c++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
-    a += (uint32_t)acc[0];
+    for (int j = 0; j < PROBE_LIMBS; j++) c[j] += (unsigned long long)a[j] * b;
+    b += (uint32_t)c[3];
   }
   unsigned long long x = 0;
 #pragma unroll
-  for (int c = 0; c < PROBE_CHAINS; c++) x ^= acc[c];
+  for (int i = 0; i < PROBE_LIMBS; i++) x ^= c[i];
   if (x == 0x12345678ull) out[0] = (uint32_t)x;
 }
 
@@ -107,7 +116,7 @@ double run_imad_peak(int variant) {
   for (int rep = 0; rep < 6; rep++) {
     cudaEventRecord(e0);
     for (int k = 0; k < 4; k++) {
-      if (variant == 0) imad_probe_pairs<<<blocks, threads>>>(d_out, 12345u + rep);
+      if (variant == 0) imad_probe_chain<<<blocks, threads>>>(d_out, 12345u + rep);
       else imad_probe_wide<<<blocks, threads>>>(d_out, 12345u + rep);
     }
     cudaEventRecord(e1);
@@ -120,7 +129,7 @@ double run_imad_peak(int variant) {
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(d_out);
   if (cudaGetLastError() != cudaSuccess) return 0.0;
-  double macs = 4.0 * (double)blocks * threads * (double)PROBE_ITERS * PROBE_CHAINS;
+  double macs = 4.0 * (double)blocks * threads * (double)PROBE_ITERS * PROBE_LIMBS;
   return macs / (best * 1e-3);
 }
 
