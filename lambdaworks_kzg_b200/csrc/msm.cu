@@ -70,7 +70,7 @@ __device__ __forceinline__ void block_reduce_xyzz(G1Xyzz& acc, uint32_t* red /* 
     __syncthreads();
     if (tid < s) {
       G1Xyzz o = xyzz_from_smem(red, THREADS / 2, tid);
-      xyzz_add(acc, o);
+      xyzz_add_ni(acc, o);
     }
     __syncthreads();
   }
@@ -136,7 +136,7 @@ msm_gather_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table
       }
       if (d != 0) {
         cur.y = fp_cneg(cur.y, d < 0);
-        xyzz_madd(acc, cur);
+        xyzz_madd_hot(acc, cur);
       }
       cur = nxt; d = dn;
     }
