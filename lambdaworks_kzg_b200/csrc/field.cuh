@@ -43,8 +43,15 @@ LW_INL Fp fp_cneg(const Fp& a, bool neg) {
 }
 
 // Out-of-line variants for cold, code-size-heavy callers (tower fields, pow).
-LW_COLD void fp_mul_ni(Fp& r, const Fp& a, const Fp& b) { Fp t; mont_mul<FpCfg>(t.l, a.l, b.l); r = t; }
-LW_COLD void fp_sqr_ni(Fp& r, const Fp& a) { Fp t; mont_sqr<FpCfg>(t.l, a.l); r = t; }
+// ONE out-of-line multiplier whose operands and result travel in registers
+// (by-value structs: ptxas keeps them out of local memory).
+#if defined(LWKZG_HOST_EMUL)
+inline Fp fp_mul_nv(Fp a, Fp b) { return fp_mul(a, b); }
+#else
+static __device__ __noinline__ Fp fp_mul_nv(Fp a, Fp b) { Fp r; mont_mul<FpCfg>(r.l, a.l, b.l); return r; }
+#endif
+LW_INL void fp_mul_ni(Fp& r, const Fp& a, const Fp& b) { r = fp_mul_nv(a, b); }
+LW_INL void fp_sqr_ni(Fp& r, const Fp& a) { r = fp_mul_nv(a, a); }
 
 LW_COLD Fp fp_pow_const(const Fp& a, const uint32_t* e, int ne) {
   Fp acc = fp_one();

@@ -143,11 +143,6 @@ LW_INL void xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
 // ~69 KB to ~12 KB of SASS, which removes the instruction-cache misses that ncu
 // showed as 19 % stall_no_inst (profiles/r01_ncu_msm_summary.md), and the rare
 // equal-x cases go through the out-of-line generic formulas.
-#if defined(LWKZG_HOST_EMUL)
-inline Fp fp_mul_nv(Fp a, Fp b) { return fp_mul(a, b); }
-#else
-static __device__ __noinline__ Fp fp_mul_nv(Fp a, Fp b) { Fp r; mont_mul<FpCfg>(r.l, a.l, b.l); return r; }
-#endif
 LW_COLD void xyzz_madd_rare(G1Xyzz& acc, const G1Affine& p) { xyzz_madd(acc, p); }
 LW_INL void xyzz_madd_hot(G1Xyzz& acc, const G1Affine& p) {
   if (g1a_is_inf(p)) return;

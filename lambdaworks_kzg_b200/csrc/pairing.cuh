@@ -204,11 +204,39 @@ LW_COLD Fp12 miller_loop(const G1Affine* ps, const G2Prepared* qs, int npairs) {
   return fp12_conj(f);  // x < 0
 }
 
+// Granger-Scott squaring for elements of the cyclotomic subgroup (anything after
+// the easy part of the final exponentiation): 3 Fp4 squarings = 18 Fp products
+// instead of 36.  With the six Fp2 coefficients z0..z5 = (c0.c0, c1.c1, c1.c0,
+// c0.c2, c0.c1, c1.c2) the pairs (z0,z1), (z2,z3), (z4,z5) are Fp4 elements.
+LW_COLD void fp4_square(Fp2& c0, Fp2& c1, const Fp2& a, const Fp2& b) {
+  Fp2 t0 = fp2_sqr(a), t1 = fp2_sqr(b);
+  c0 = fp2_add(fp2_mul_xi(t1), t0);
+  c1 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(a, b)), t0), t1);
+}
+LW_COLD Fp12 fp12_cyclotomic_sqr(const Fp12& f) {
+  Fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+  Fp2 t0, t1, t2, t3;
+  fp4_square(t0, t1, z0, z1);
+  z0 = fp2_sub(t0, z0); z0 = fp2_add(fp2_dbl(z0), t0);
+  z1 = fp2_add(t1, z1); z1 = fp2_add(fp2_dbl(z1), t1);
+  fp4_square(t0, t1, z2, z3);
+  fp4_square(t2, t3, z4, z5);
+  z4 = fp2_sub(t0, z4); z4 = fp2_add(fp2_dbl(z4), t0);
+  z5 = fp2_add(t1, z5); z5 = fp2_add(fp2_dbl(z5), t1);
+  t0 = fp2_mul_xi(t3);
+  z2 = fp2_add(t0, z2); z2 = fp2_add(fp2_dbl(z2), t0);
+  z3 = fp2_sub(t2, z3); z3 = fp2_add(fp2_dbl(z3), t2);
+  Fp12 r;
+  r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
+  r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
+  return r;
+}
+
 // g^|x| by square-and-multiply, then conjugate (x < 0; g is unitary after the easy part)
 LW_COLD Fp12 fp12_pow_x(const Fp12& g) {
   Fp12 acc = g;
   for (int bit = 62; bit >= 0; bit--) {
-    acc = fp12_sqr(acc);
+    acc = fp12_cyclotomic_sqr(acc);
     if ((k::BLS_X_ABS >> bit) & 1ull) acc = fp12_mul(acc, g);
   }
   return fp12_conj(acc);
@@ -226,7 +254,7 @@ LW_COLD Fp12 final_exponentiation(const Fp12& f) {
   a = fp12_mul(fp12_pow_x(a), fp12_conj(a));           // g^((x-1)^2)
   Fp12 b = fp12_mul(fp12_pow_x(a), fp12_frobenius(a)); // a^(x+p)
   Fp12 c = fp12_mul(fp12_mul(fp12_pow_x(fp12_pow_x(b)), fp12_frobenius(fp12_frobenius(b))), fp12_conj(b));  // b^(x^2+p^2-1)
-  Fp12 g3 = fp12_mul(fp12_sqr(g), g);
+  Fp12 g3 = fp12_mul(fp12_cyclotomic_sqr(g), g);
   return fp12_mul(c, g3);
 }
 

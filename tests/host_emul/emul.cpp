@@ -127,6 +127,19 @@ int emul_g2_decompress(uint8_t* out192, const uint8_t* in96) {
   fp_canon_to_be48(out192 + 144, fp_from_mont(q.y.c1));
   return 1;
 }
+// cyclotomic squaring == generic squaring on the cyclotomic subgroup (after the easy part)
+int emul_cyclotomic_sqr_check(const uint8_t* a1, const uint8_t* q1) {
+  G1Affine P = load_aff(a1);
+  G2Affine Q;
+  Q.x.c0 = fp_from_be48(q1); Q.x.c1 = fp_from_be48(q1 + 48);
+  Q.y.c0 = fp_from_be48(q1 + 96); Q.y.c1 = fp_from_be48(q1 + 144);
+  G2Prepared prep;
+  g2_prepare(prep, Q);
+  Fp12 f = miller_loop(&P, &prep, 1);
+  Fp12 g = fp12_mul(fp12_conj(f), fp12_inv(f));
+  g = fp12_mul(fp12_frobenius(fp12_frobenius(g)), g);
+  return fp12_eq(fp12_cyclotomic_sqr(g), fp12_sqr(g)) && !fp12_eq(fp12_cyclotomic_sqr(f), fp12_sqr(f)) ? 1 : 0;
+}
 // raw Fp12 pairing output for debugging / cross-checking with oracle/py/pairing.py
 void emul_pairing_gt(uint8_t* out576, const uint8_t* a1, const uint8_t* q1) {
   G1Affine P = load_aff(a1);

@@ -282,3 +282,8 @@ def test_pairing_check(lib, py_setup):
     assert lib.emul_pairing_check(aff_bytes(None), _g2_bytes(g2_0), aff_bytes(None), _g2_bytes(g2_1)) == 1
     assert lib.emul_pairing_check(aff_bytes(bls.G1), _g2_bytes(g2_0), aff_bytes(None), _g2_bytes(g2_1)) == 0
 
+
+
+def test_cyclotomic_squaring(lib, py_setup):
+    p = bls.g1_mul(bls.G1, 424242)
+    assert lib.emul_cyclotomic_sqr_check(aff_bytes(p), _g2_bytes(py_setup.g2[1])) == 1
