@@ -198,6 +198,13 @@ double lwkzg_imad_peak(int variant);
  * average milliseconds per launch (< 0 on error).  blocks_per_blob 0 = auto. */
 double lwkzg_bench_msm_kernel(const void *d_blobs, size_t n, int blocks_per_blob, int iters,
                               const KZGSettings *s);
+/* Measurement hook for the variable-base MSM sweep (BASELINE config 5): n
+ * synthetic points (pseudo-random entries of the fixed-base table, entry number
+ * (t * 2654435761) mod (W * 4096 * 2^(c-1)) for point t) times n synthetic
+ * scalars (the blob-word generator with blob id `seed`), generated on the
+ * device; returns the average milliseconds per MSM (< 0 on error) and writes
+ * the compressed result. */
+double lwkzg_bench_var_msm(Bytes48 *out, size_t n, int iters, uint64_t seed, const KZGSettings *s);
 /* fixed-base window actually in use for these settings (may be smaller than
  * the "window_bits" option if HBM was short), -1 on error */
 int lwkzg_window_bits(const KZGSettings *s);

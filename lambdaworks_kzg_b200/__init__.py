@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     C_KZG_OK,
     KzgError,
     bench_msm_kernel,
+    bench_var_msm,
     window_bits,
     Settings,
     blob_to_kzg_commitment,

@@ -83,6 +83,8 @@ def load_library() -> ctypes.CDLL:
     lib.lwkzg_imad_peak.restype = ctypes.c_double
     lib.lwkzg_bench_msm_kernel.argtypes = [vp, sz, ctypes.c_int, ctypes.c_int, sp]
     lib.lwkzg_bench_msm_kernel.restype = ctypes.c_double
+    lib.lwkzg_bench_var_msm.argtypes = [vp, sz, ctypes.c_int, ctypes.c_uint64, sp]
+    lib.lwkzg_bench_var_msm.restype = ctypes.c_double
     lib.lwkzg_window_bits.argtypes = [sp]
     lib.lwkzg_window_bits.restype = ctypes.c_int
     lib.lwkzg_kernel_launches.argtypes = []
@@ -296,6 +298,15 @@ def bench_msm_kernel(d_blobs: int, n: int, s, blocks_per_blob: int = 0, iters: i
     if ms < 0:
         raise KzgError(C_KZG_ERROR, "lwkzg_bench_msm_kernel", last_error())
     return ms
+
+
+def bench_var_msm(n: int, s, iters: int = 3, seed: int = 0):
+    """(ms per MSM, compressed result) for the synthetic variable-base MSM of size n."""
+    out = ctypes.create_string_buffer(48)
+    ms = float(load_library().lwkzg_bench_var_msm(out, n, iters, seed, _sp(s)))
+    if ms < 0:
+        raise KzgError(C_KZG_ERROR, "lwkzg_bench_var_msm", last_error())
+    return ms, out.raw
 
 
 def window_bits(s) -> int:

@@ -82,5 +82,9 @@ void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const
 // ---- generic (variable-base) MSM for lwkzg_g1_lincomb (varmsm.cu)
 void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st);
 size_t var_msm_scratch_bytes(size_t n);
+size_t var_msm_bad_flag_offset(size_t n);
+int var_msm_window_bits(size_t n);
+void launch_var_msm_synth(void* d_pts_be, void* d_sc_be, const void* d_table, unsigned long long n_entries, unsigned long long seed, size_t n,
+                          cudaStream_t st);  // int flag inside the scratch: 1 = some point was not on the curve
 
 }  // namespace lw

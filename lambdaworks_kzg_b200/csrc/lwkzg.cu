@@ -1005,6 +1005,45 @@ int lwkzg_window_bits(const KZGSettings* s) {
   return c ? c->c : -1;
 }
 
+// ---- measurement hook for BASELINE config 5 (variable-base MSM size sweep):
+// n synthetic points (pseudo-randomly chosen fixed-base table entries, so their
+// discrete logs are known to the tests) x n synthetic scalars, all generated and
+// kept on the device; the MSM pipeline alone is timed with CUDA events.
+double lwkzg_bench_var_msm(Bytes48* out, size_t n, int iters, uint64_t seed, const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  if (!c || !c->srs_valid || !out || n == 0 || iters <= 0) return -1.0;
+  CtxLock L(c);
+  cudaStream_t st = c->slot[0].st;
+  void *d_pts = nullptr, *d_sc = nullptr, *d_scratch = nullptr, *d_out = nullptr;
+  double ms_per = -1.0;
+  bool good = [&]() -> bool {
+    CU_TRY(cudaMalloc(&d_pts, n * 96));
+    CU_TRY(cudaMalloc(&d_sc, n * 32));
+    CU_TRY(cudaMalloc(&d_scratch, var_msm_scratch_bytes(n)));
+    CU_TRY(cudaMalloc(&d_out, 48));
+    unsigned long long entries = (unsigned long long)c->nwin * N_POINTS << (c->c - 1);
+    launch_var_msm_synth(d_pts, d_sc, c->d_table, entries, seed, n, st);
+    launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, st);  // warm-up
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    CU_TRY(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; i++) launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, st);
+    CU_TRY(cudaEventRecord(e1, st));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, d_out, 48, cudaMemcpyDeviceToHost));
+    ms_per = (double)ms / iters;
+    return true;
+  }();
+  cudaFree(d_pts); cudaFree(d_sc); cudaFree(d_scratch); cudaFree(d_out);
+  return good ? ms_per : -1.0;
+}
+
 // ---- generic linear combination (g1_lincomb, lib.rs:241-243)
 C_KZG_RET lwkzg_g1_lincomb(Bytes48* out, const uint8_t* points_xy_be, const uint8_t* scalars_be, size_t n) {
   if (!out) return C_KZG_ERROR;
@@ -1024,8 +1063,7 @@ C_KZG_RET lwkzg_g1_lincomb(Bytes48* out, const uint8_t* points_xy_be, const uint
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpy(out, d_out, 48, cudaMemcpyDeviceToHost));
-    size_t blocks = std::max<size_t>((n + 63) / 64, 1);
-    CU_TRY(cudaMemcpy(&bad, (uint8_t*)d_scratch + blocks * XYZZ_BYTES, sizeof(int), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&bad, (uint8_t*)d_scratch + var_msm_bad_flag_offset(nn), sizeof(int), cudaMemcpyDeviceToHost));
     return true;
   }();
   cudaFree(d_pts); cudaFree(d_sc); cudaFree(d_scratch); cudaFree(d_out);

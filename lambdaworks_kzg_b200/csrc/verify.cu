@@ -319,34 +319,6 @@ __global__ void __launch_bounds__(32) batch_final_kernel(int* __restrict__ ok_ou
   if (lane == 0) *ok_out = ok ? 1 : 0;
 }
 
-// ---- generic G1 linear combination (g1_lincomb): thread per point
-// double-and-add, block tree, serial finish.  Correct for any inputs; a sorted
-// bucket MSM for the 2^12..2^22 sweep is the planned replacement.
-constexpr int VM_THREADS = 64;
-__global__ void __launch_bounds__(VM_THREADS) var_msm_kernel(G1Xyzz* __restrict__ scratch, int* __restrict__ bad, const uint8_t* __restrict__ pts_be,
-                                                              const uint8_t* __restrict__ sc_be, unsigned long long n) {
-  __shared__ uint32_t red[48 * (VM_THREADS / 2)];
-  unsigned long long i = (unsigned long long)blockIdx.x * VM_THREADS + threadIdx.x;
-  G1Xyzz acc = xyzz_inf();
-  if (i < n) {
-    G1Affine p = affine_from_be96(pts_be + i * 96);
-    if (!g1a_is_inf(p) && !g1a_on_curve(p)) atomicExch(bad, 1);
-    Fr k = fr_canon_from_be32(sc_be + i * 32);
-    acc = g1_mul_scalar(p, k.l, 8);
-  }
-  block_reduce_xyzz<VM_THREADS>(acc, red);
-  if (threadIdx.x == 0) scratch[blockIdx.x] = acc;
-}
-__global__ void var_msm_finish_kernel(uint8_t* __restrict__ out48, const G1Xyzz* __restrict__ scratch, int blocks) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  G1Xyzz acc = xyzz_inf();
-  for (int b = 0; b < blocks; b++) {
-    G1Xyzz o = scratch[b];
-    xyzz_add_ni(acc, o);
-  }
-  g1_compress(out48, xyzz_to_affine(acc));
-}
-
 // ------------------------------------------------------------------ launchers
 void launch_g2_prepare(void* d_prepared, int* d_bad, const void* d_canon_in, cudaStream_t st) {
   g2_prepare_kernel<<<1, 32, 0, st>>>((G2Prepared*)d_prepared, d_bad, (const uint32_t*)d_canon_in);
@@ -390,16 +362,4 @@ void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const
   batch_final_kernel<<<1, 32, 0, st>>>(d_ok, (const uint8_t*)d_partials288, n_ranks, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
   count_launch();
 }
-size_t var_msm_scratch_bytes(size_t n) { return ((n + VM_THREADS - 1) / VM_THREADS + 1) * sizeof(G1Xyzz) + 16; }
-void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st) {
-  int blocks = (int)((n + VM_THREADS - 1) / VM_THREADS);
-  if (blocks < 1) blocks = 1;
-  G1Xyzz* sc = (G1Xyzz*)d_scratch;
-  int* bad = (int*)((uint8_t*)d_scratch + (size_t)blocks * sizeof(G1Xyzz));
-  cudaMemsetAsync(bad, 0, sizeof(int), st);
-  var_msm_kernel<<<blocks, VM_THREADS, 0, st>>>(sc, bad, (const uint8_t*)d_points_xy_be, (const uint8_t*)d_scalars_be, (unsigned long long)n);
-  var_msm_finish_kernel<<<1, 32, 0, st>>>((uint8_t*)d_out48, sc, blocks);
-  count_launch(2);
-}
-
 }  // namespace lw

@@ -424,3 +424,54 @@ def test_device_api_and_large_batch_properties(lw, settings13, ref):
     summed = blob_from_coeffs([t % R for t in total])
     want = bls.g1_compress(bls.g1_sum(bls.g1_decompress(cl[k]) for k in range(8)))
     assert lw.blob_to_kzg_commitment(summed, settings13) == want
+
+
+# ------------------------------------------------------------------ variable-base MSM (g1_lincomb, BASELINE config 5)
+def _synth_scalar(seed, t):
+    M = (1 << 64) - 1
+    st = 0xB2004844 ^ ((seed * 4096 + t) & M)
+    w = b""
+    for _ in range(4):
+        st = (st + 0x9E3779B97F4A7C15) & M
+        z = st
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        w += (z ^ (z >> 31)).to_bytes(8, "big")
+    return int.from_bytes(bytes([w[0] & 0x3F]) + w[1:], "big")
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 4096, 1 << 14, 1 << 16])
+def test_var_msm_synthetic_sizes(lw, settings8, py_setup, n):
+    """Points = pseudo-random entries d * 2^(c j) * P_i of the fixed-base table (tau known => known discrete logs)."""
+    c = lw.window_bits(settings8)
+    nwin = 255 // c + 1
+    entries = nwin * 4096 << (c - 1)
+    ms, got = lw.bench_var_msm(n, settings8, iters=1, seed=5)
+    tau = py_setup.tau
+    acc = 0
+    for t in range(n):
+        e = (t * 2654435761) % entries
+        d = (e & ((1 << (c - 1)) - 1)) + 1
+        i = (e >> (c - 1)) & 4095
+        j = e >> (c - 1 + 12)
+        acc = (acc + _synth_scalar(5, t) * d * pow(2, c * j, R) * pow(tau, i, R)) % R
+    assert got == bls.g1_compress(bls.g1_mul(bls.G1, acc)), n
+
+
+def test_g1_lincomb_edge_cases(lw, py_setup):
+    rnd = random.Random(77)
+    P0, P1 = py_setup.g1[5], py_setup.g1[9]
+    enc = lambda p: bytes(96) if p is None else p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")  # noqa: E731
+    cases = [
+        ([P0, P0, P0], [1, 1, 1]),                       # same point, same bucket -> doubling inside a bucket
+        ([P0, bls.g1_neg(P0)], [7, 7]),                  # cancellation
+        ([P0, P1, None, P0], [R - 1, R, R + 5, 0]),      # scalars >= r are reduced; infinity point; zero scalar
+        ([P0] * 300, [rnd.randrange(1 << 256) for _ in range(300)]),
+        ([py_setup.g1[rnd.randrange(4096)] for _ in range(700)], [3] * 700),  # every point in one bucket per window
+    ]
+    for pts, sc in cases:
+        want = bls.g1_compress(bls.g1_sum(bls.g1_mul(p, s % R) for p, s in zip(pts, sc)))
+        got = lw.g1_lincomb(b"".join(enc(p) for p in pts), b"".join(s.to_bytes(32, "big") for s in sc), len(pts))
+        assert got == want
+    with pytest.raises(lw.KzgError):
+        lw.g1_lincomb((1).to_bytes(48, "big") + (1).to_bytes(48, "big"), (1).to_bytes(32, "big"), 1)  # (1,1) is not on the curve
