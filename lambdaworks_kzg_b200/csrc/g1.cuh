@@ -270,4 +270,26 @@ LW_COLD bool g1_decompress(G1Affine& out, const uint8_t* in48) {
   return g1_in_subgroup(out);
 }
 
+// Strict (ZCash / blst, as c-kzg-4844 requires) variant for MODE_CKZG_LE:
+// infinity must be encoded exactly as c0 00..00 and x must be canonical (< p).
+LW_COLD bool g1_decompress_strict(G1Affine& out, const uint8_t* in48) {
+  uint8_t b0 = in48[0];
+  if (!(b0 & 0x80)) return false;
+  if (b0 & 0x40) {
+    if (b0 != 0xC0) return false;
+    for (int i = 1; i < 48; i++) if (in48[i]) return false;
+    out = g1a_inf();
+    return true;
+  }
+  // canonical x: big-endian compare with p
+  Fp xc;
+  for (int i = 0; i < 12; i++) {
+    const uint8_t* q = in48 + 44 - 4 * i;
+    xc.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+  }
+  xc.l[11] &= 0x1FFFFFFFu;
+  if (!limbs_lt<12>(xc.l, k::FP_MOD)) return false;
+  return g1_decompress(out, in48);
+}
+
 }  // namespace lw

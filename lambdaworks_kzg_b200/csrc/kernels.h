@@ -40,7 +40,7 @@ int msm_threads_per_block();
 // SHA-256 midstate over domain || le64(4096) || le64(0) || blob[0 .. 131040)
 void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st);
 // finish with blob tail + 48 commitment bytes -> z canonical (8 u32 LE per blob)
-void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st);
+void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st, bool le_digest = false);
 // z from caller bytes (big-endian, reduced)
 void launch_fr_from_be(void* d_z, const void* d_z_be32, int n, cudaStream_t st);
 // y = p(z), q = (p - y)/(X - z): warp per blob.  d_q (n x 4096 x 8 u32 canonical,
@@ -50,7 +50,7 @@ void launch_poly_eval_quot(void* d_q, void* d_y, void* d_y_be32, const void* d_b
 // ---- point codecs (codec.cu)
 // status[i] = 0 ok / 2 (C_KZG_ERROR) rejected.  d_aff (Montgomery, may be NULL),
 // d_recompressed48 (canonical re-encoding, may be NULL)
-void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st);
+void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st, bool strict = false);
 void launch_status_or(int* d_status, const int* d_other, int n, cudaStream_t st);
 
 // ---- synthetic data + probes (misc.cu)
@@ -69,15 +69,24 @@ void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st)
 void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
                           const void* d_g1_0_aff, const void* d_prep0, const void* d_prep1, cudaStream_t st);
 // tuples: compress(C)||z||y||compress(pi) (160 B each)
-void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st);
+void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le = false);
 // r = H(domain || le64(4096) || le64(n_total) || tuples) -> canonical r (8 u32)
-void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st);
+void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, bool le = false);
 // partial sums over [first, first+n_local): 3 XYZZ blocks-partials then reduced to 3 affine (canonical BE 96 B each)
 void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
                            size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st);
 size_t batch_partials_scratch_bytes(int n_local);
 // sum n_ranks partial triples, then e(rhs, g2_0) * e(-proof_lincomb, g2_1) == 1
 void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const void* d_prep0, const void* d_prep1, cudaStream_t st);
+
+// ---- MODE_CKZG_LE (le.cu)
+void launch_write_generator(void* d_out, cudaStream_t st);                 // the G1 generator, affine Montgomery
+void launch_le_roots(void* d_roots, cudaStream_t st);                      // 4096 Fr (Montgomery), bit-reversed order
+void launch_le_idft_rows(void* d_rows, cudaStream_t st);                   // 4096 x 4096 canonical scalars (512 MiB)
+void launch_affine_to_canon(void* d_out24, const void* d_aff, int n, cudaStream_t st);
+void launch_le_blob_check(int* d_status, const void* d_blobs, int n, cudaStream_t st);   // status 1 if a word >= r
+void launch_le_fr_parse(void* d_out, int* d_status, const void* d_in32, int n, cudaStream_t st);
+void launch_le_eval_quot(void* d_q, void* d_y, void* d_y_le32, const void* d_blobs, const void* d_z, const void* d_roots, int n, cudaStream_t st);
 
 // ---- generic (variable-base) MSM for lwkzg_g1_lincomb (varmsm.cu)
 void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st);

@@ -44,7 +44,9 @@ struct Options {
   long window_bits = 13;
   long msm_blocks_per_blob = 0;
   long chunk_blobs = 512;
+  long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode)
   Options() {
+    if (const char* e = getenv("LWKZG_MODE")) mode = atol(e);
     if (const char* e = getenv("LWKZG_WINDOW_BITS")) window_bits = atol(e);
     if (const char* e = getenv("LWKZG_CHUNK_BLOBS")) chunk_blobs = atol(e);
     if (const char* e = getenv("LWKZG_MSM_BLOCKS_PER_BLOB")) msm_blocks_per_blob = atol(e);
@@ -92,6 +94,9 @@ struct Ctx {
   bool srs_valid;     // every g1 value on the curve (else every call errors, like the reference's re-hydration)
   bool srs_in_g1;     // every g1 value in the r-torsion
   bool g2_valid;      // g2[0], g2[1] on the twist
+  int mode;           // semantic mode captured when the context was built
+  void* d_roots;      // MODE_CKZG_LE: bit-reversed 4096th roots of unity (Montgomery)
+  void* d_gen;        // MODE_CKZG_LE: the G1 generator (c-kzg verifies against G, not against g1_values[0] = L_0)
   void* d_srs;        // 4096 affine Montgomery
   void* d_table;      // fixed-base digit table
   void* d_prep0;      // prepared g2[0] / g2[1] line coefficients
@@ -150,11 +155,13 @@ void destroy_ctx(Ctx* c) {
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_prep0) cudaFree(c->d_prep0);
   if (c->d_prep1) cudaFree(c->d_prep1);
+  if (c->d_roots) cudaFree(c->d_roots);
+  if (c->d_gen) cudaFree(c->d_gen);
   c->magic = 0;
   delete c;
 }
 
-bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2) {
+bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long window_override) {
   CU_TRY(cudaGetDevice(&c->device));
   int lo = 0, hi = 0;
   CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -232,7 +239,14 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2) {
   long want_c;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    want_c = opts().window_bits;
+    want_c = window_override > 0 ? window_override : opts().window_bits;
+  }
+  c->mode = mode;
+  if (mode == 1) {
+    CU_TRY(cudaMalloc(&c->d_roots, (size_t)N_POINTS * 32));
+    launch_le_roots(c->d_roots, st);
+    CU_TRY(cudaMalloc(&c->d_gen, AFFINE_BYTES));
+    launch_write_generator(c->d_gen, st);
   }
   if (want_c < 4) want_c = 4;
   if (want_c > 15) want_c = 15;
@@ -258,14 +272,21 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2) {
   return true;
 }
 
-Ctx* build_ctx(const g1_t* g1, const g2_t* g2) {
+long current_mode() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return opts().mode;
+}
+
+Ctx* build_ctx(const g1_t* g1, const g2_t* g2, int mode = -1, long window_override = 0) {
+  if (mode < 0) mode = (int)current_mode();
   Ctx* c = new Ctx();
   memset(&c->fs_prefix, 0, sizeof(c->fs_prefix));
   c->magic = CTX_MAGIC;
-  c->d_srs = c->d_table = c->d_prep0 = c->d_prep1 = nullptr;
+  c->d_srs = c->d_table = c->d_prep0 = c->d_prep1 = c->d_roots = c->d_gen = nullptr;
+  c->mode = mode;
   c->c = c->nwin = 0;
   c->srs_valid = c->srs_in_g1 = c->g2_valid = false;
-  if (!build_ctx_inner(c, g1, g2)) {
+  if (!build_ctx_inner(c, g1, g2, mode, window_override)) {
     std::string e = tl_err;
     destroy_ctx(c);
     set_err(e);
@@ -361,6 +382,47 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
                    const void* d_commit_in48, const void* d_z_in_be) {
   const int bpb = auto_bpb(n);
   cudaStream_t st = s.st;
+  const bool le = c->mode == 1;
+  if (le) {
+    // MODE_CKZG_LE: canonical little-endian scalars = the limbs as they lie in memory,
+    // Lagrange table, barycentric evaluation, evaluation-form quotient, BADARGS for invalid input
+    int* stt = d_status ? d_status : (int*)s.status.p;
+    CU_TRY(cudaMemsetAsync(stt, 0, (size_t)n * sizeof(int), st));
+    launch_le_blob_check(stt, d_blobs, n, st);
+    if (mode == Mode::Commit) {
+      launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, false, n, bpb, st);
+      launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
+      return true;
+    }
+    const void* commit_for_hash = nullptr;
+    if (mode == Mode::CommitProve || mode == Mode::BlobProof) {
+      CU_TRY(cudaEventRecord(s.ev_fork, st));
+      CU_TRY(cudaStreamWaitEvent(s.aux, s.ev_fork, 0));
+      launch_challenge_midstate(s.states.p, d_blobs, n, s.aux);
+      CU_TRY(cudaEventRecord(s.ev_aux, s.aux));
+    }
+    if (mode == Mode::CommitProve) {
+      launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, false, n, bpb, st);
+      launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
+      commit_for_hash = d_c48;
+    } else if (mode == Mode::BlobProof) {
+      launch_g1_decompress(nullptr, nullptr, (int*)s.status2.p, d_commit_in48, n, st, true);
+      launch_status_or(stt, (const int*)s.status2.p, n, st);
+      commit_for_hash = d_commit_in48;  // c-kzg hashes the commitment bytes as given
+    }
+    if (mode == Mode::PointProof) {
+      CU_TRY(cudaMemsetAsync(s.status2.p, 0, (size_t)n * sizeof(int), st));
+      launch_le_fr_parse(s.z.p, (int*)s.status2.p, d_z_in_be, n, st);
+      launch_status_or(stt, (const int*)s.status2.p, n, st);
+    } else {
+      CU_TRY(cudaStreamWaitEvent(st, s.ev_aux, 0));
+      launch_challenge_finish(s.z.p, s.states.p, d_blobs, commit_for_hash, n, st, true);
+    }
+    launch_le_eval_quot(s.q.p, nullptr, d_ybe, d_blobs, s.z.p, c->d_roots, n, st);
+    launch_msm_gather(s.partials.p, c->d_table, c->c, s.q.p, false, n, bpb, st);
+    launch_msm_finalize(d_p48, nullptr, s.partials.p, bpb, n, st);
+    return true;
+  }
   if (mode == Mode::Commit) {
     launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, true, n, bpb, st);
     launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
@@ -608,7 +670,40 @@ C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, si
     canon_to_blst_fp(&g2[i].y.fp[1], &c2[i * 48 + 36]);
     if (st[n1 + i] == 0) g2[i].z.fp[0].l[5] = 1;  // affine z = 1 + 0u ; infinity keeps z = 0
   }
-  Ctx* c = build_ctx(g1, g2);
+  const int mode = (int)current_mode();
+  if (mode == 1 && n1 == N_POINTS) {
+    // c-kzg's load_trusted_setup stores the SRS in Lagrange form, bit-reversed
+    // (the step the reference left as a TODO, lib.rs:760-770): L_i = sum_j (1/n) w_i^-j [tau^j]G,
+    // computed as 4096 fixed-base MSMs over a temporary 8-bit table of the monomial points.
+    Ctx* tmp = build_ctx(g1, g2, 0, 8);
+    if (!tmp || !tmp->srs_valid) { if (tmp) destroy_ctx(tmp); free(g1); free(g2); set_err("Lagrange conversion failed"); return C_KZG_ERROR; }
+    std::vector<uint32_t> lag((size_t)N_POINTS * 24);
+    bool good = [&]() -> bool {
+      void *d_rows = nullptr, *d_aff = nullptr, *d_canon = nullptr;
+      Slot& sl = tmp->slot[0];
+      const int bpb = 1;
+      if (!slot_reserve(sl, N_POINTS, bpb, false)) return false;
+      CU_TRY(cudaMalloc(&d_rows, (size_t)N_POINTS * BLOB_BYTES));
+      CU_TRY(cudaMalloc(&d_aff, (size_t)N_POINTS * AFFINE_BYTES));
+      CU_TRY(cudaMalloc(&d_canon, (size_t)N_POINTS * 96));
+      launch_le_idft_rows(d_rows, sl.st);
+      launch_msm_gather(sl.partials.p, tmp->d_table, tmp->c, d_rows, false, N_POINTS, bpb, sl.st);
+      launch_msm_finalize(nullptr, d_aff, sl.partials.p, bpb, N_POINTS, sl.st);
+      launch_affine_to_canon(d_canon, d_aff, N_POINTS, sl.st);
+      CU_TRY(cudaMemcpyAsync(lag.data(), d_canon, (size_t)N_POINTS * 96, cudaMemcpyDeviceToHost, sl.st));
+      CU_TRY(cudaStreamSynchronize(sl.st));
+      CU_TRY(cudaGetLastError());
+      cudaFree(d_rows); cudaFree(d_aff); cudaFree(d_canon);
+      return true;
+    }();
+    destroy_ctx(tmp);
+    if (!good) { free(g1); free(g2); return C_KZG_ERROR; }
+    for (size_t i = 0; i < (size_t)N_POINTS; i++) {
+      canon_to_blst_fp(&g1[i].x, &lag[i * 24]);
+      canon_to_blst_fp(&g1[i].y, &lag[i * 24 + 12]);
+    }
+  }
+  Ctx* c = build_ctx(g1, g2, mode);
   if (!c) { free(g1); free(g2); return C_KZG_ERROR; }
   out->fs = reinterpret_cast<FFTSettings*>(c);
   out->g1_values = g1;
@@ -639,9 +734,10 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   cudaStream_t s0 = c->slot[0].st;
   CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitments, n * 48, cudaMemcpyHostToDevice, s0));
   CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proofs, n * 48, cudaMemcpyHostToDevice, s0));
-  launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0);
+  const bool le = c->mode == 1;
+  launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0, le);
   // proofs: decode status into the (still unused) tuples buffer, then merge
-  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, s0);
+  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, s0, le);
   launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, (int)n, s0);
   CU_TRY(cudaStreamSynchronize(s0));
   size_t k = 0;
@@ -656,33 +752,45 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     launch_challenge_midstate(sl.states.p, sl.blobs.p, m, sl.aux);
     CU_TRY(cudaEventRecord(sl.ev_aux, sl.aux));
     CU_TRY(cudaStreamWaitEvent(sl.st, sl.ev_aux, 0));
-    launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, sl.states.p, sl.blobs.p, (const uint8_t*)c->vb_c48r.p + off * 48, m, sl.st);
-    launch_poly_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, sl.blobs.p, (const uint8_t*)c->vb_z.p + off * 32, m, sl.st);
+    if (le) {
+      CU_TRY(cudaMemsetAsync(sl.status2.p, 0, (size_t)m * sizeof(int), sl.st));
+      launch_le_blob_check((int*)sl.status2.p, sl.blobs.p, m, sl.st);
+      launch_status_or((int*)c->vb_status.p + off, (const int*)sl.status2.p, m, sl.st);
+      launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, sl.states.p, sl.blobs.p, (const uint8_t*)c->vb_cin.p + off * 48, m, sl.st, true);
+      launch_le_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, sl.blobs.p, (const uint8_t*)c->vb_z.p + off * 32, c->d_roots, m, sl.st);
+    } else {
+      launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, sl.states.p, sl.blobs.p, (const uint8_t*)c->vb_c48r.p + off * 48, m, sl.st);
+      launch_poly_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, sl.blobs.p, (const uint8_t*)c->vb_z.p + off * 32, m, sl.st);
+    }
   }
   for (auto& sl : c->slot) {
     CU_TRY(cudaStreamSynchronize(sl.st));
     CU_TRY(cudaStreamSynchronize(sl.aux));
   }
-  launch_make_tuples(c->vb_tuples.p, c->vb_c48r.p, c->vb_z.p, c->vb_y.p, c->vb_p48r.p, (int)n, s0);
+  launch_make_tuples(c->vb_tuples.p, c->vb_c48r.p, c->vb_z.p, c->vb_y.p, c->vb_p48r.p, (int)n, s0, le);
   CU_TRY(cudaStreamSynchronize(s0));
   CU_TRY(cudaGetLastError());
   c->vb_n = n;
   return true;
 }
 
+int g_bad_code = 0;  // set by any_bad_status: first non-zero per-item code (guarded by the context lock)
 bool any_bad_status(Ctx* c, size_t n, bool& bad) {
   std::vector<int> st(n);
   CU_TRY(cudaMemcpy(st.data(), c->vb_status.p, n * sizeof(int), cudaMemcpyDeviceToHost));
   bad = false;
+  g_bad_code = 0;
   for (int v : st)
-    if (v) bad = true;
+    if (v && !bad) { bad = true; g_bad_code = v; }
   return true;
 }
+C_KZG_RET bad_code() { return g_bad_code == 1 ? C_KZG_BADARGS : C_KZG_ERROR; }
 
 // single-proof verification with everything already decoded in the workspace (item 0)
 bool verify_single_from_workspace(Ctx* c, bool& ok) {
   cudaStream_t s0 = c->slot[0].st;
-  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->d_srs, c->d_prep0, c->d_prep1, s0);
+  // reference: KZG::verify subtracts y * srs[0] (= G for a monomial setup); c-kzg uses the generator itself
+  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->mode == 1 ? c->d_gen : c->d_srs, c->d_prep0, c->d_prep1, s0);
   int okv = 0;
   CU_TRY(cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
   CU_TRY(cudaStreamSynchronize(s0));
@@ -713,6 +821,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "window_bits") { if (value < 4 || value > 15) return 1; opts().window_bits = value; return 0; }
   if (n == "msm_blocks_per_blob") { if (value < 0 || value > 128 || (value & (value - 1))) return 1; opts().msm_blocks_per_blob = value; return 0; }
   if (n == "chunk_blobs") { if (value < 1) return 1; opts().chunk_blobs = value; return 0; }
+  if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
   return 1;
 }
 long lwkzg_get_option(const char* name) {
@@ -721,6 +830,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "window_bits") return opts().window_bits;
   if (n == "msm_blocks_per_blob") return opts().msm_blocks_per_blob;
   if (n == "chunk_blobs") return opts().chunk_blobs;
+  if (n == "mode") return opts().mode;
   return -1;
 }
 
@@ -845,18 +955,27 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
     CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitment_bytes, 48, cudaMemcpyHostToDevice, s0));
     CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proof_bytes, 48, cudaMemcpyHostToDevice, s0));
     CU_TRY(cudaMemcpyAsync(c->vb_zy_in.p, zy, 64, cudaMemcpyHostToDevice, s0));
-    launch_g1_decompress(c->vb_caff.p, nullptr, (int*)c->vb_status.p, c->vb_cin.p, 1, s0);
-    launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, s0);
+    const bool le = c->mode == 1;
+    launch_g1_decompress(c->vb_caff.p, nullptr, (int*)c->vb_status.p, c->vb_cin.p, 1, s0, le);
+    launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, s0, le);
     launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, 1, s0);
-    launch_fr_from_be(c->vb_z.p, c->vb_zy_in.p, 1, s0);
-    launch_fr_from_be(c->vb_y.p, (const uint8_t*)c->vb_zy_in.p + 32, 1, s0);
+    if (le) {
+      CU_TRY(cudaMemsetAsync(c->vb_tuples.p, 0, 2 * sizeof(int), s0));
+      launch_le_fr_parse(c->vb_z.p, (int*)c->vb_tuples.p, c->vb_zy_in.p, 1, s0);
+      launch_le_fr_parse(c->vb_y.p, (int*)c->vb_tuples.p + 1, (const uint8_t*)c->vb_zy_in.p + 32, 1, s0);
+      launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, 1, s0);
+      launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p + 1, 1, s0);
+    } else {
+      launch_fr_from_be(c->vb_z.p, c->vb_zy_in.p, 1, s0);
+      launch_fr_from_be(c->vb_y.p, (const uint8_t*)c->vb_zy_in.p + 32, 1, s0);
+    }
     CU_TRY(cudaStreamSynchronize(s0));
     return true;
   }();
   if (!good) return C_KZG_ERROR;
   bool bad = false;
   if (!any_bad_status(c, 1, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   bool res = false;
   if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
@@ -873,7 +992,7 @@ C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commi
   if (!verify_prepare(c, blob, commitment_bytes, proof_bytes, 1)) return C_KZG_ERROR;
   bool bad = false;
   if (!any_bad_status(c, 1, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   bool res = false;
   if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
@@ -885,7 +1004,12 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
                                       const KZGSettings* s) {
   if (!ok) return C_KZG_ERROR;
   *ok = false;  // lib.rs:533-535
-  if (n == 0) return C_KZG_OK;  // lib.rs:538-543: *ok stays false
+  if (n == 0) {
+    // lib.rs:538-543: the reference rejects an empty batch; c-kzg (MODE_CKZG_LE) accepts it
+    Ctx* c0 = ctx_of(s);
+    if (c0 && c0->mode == 1) *ok = true;
+    return C_KZG_OK;
+  }
   if (n == 1) return verify_blob_kzg_proof(ok, blobs, commitments_bytes, proofs_bytes, s);  // lib.rs:544
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
@@ -893,10 +1017,10 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
   if (!verify_prepare(c, blobs, commitments_bytes, proofs_bytes, n)) return C_KZG_ERROR;
   bool bad = false;
   if (!any_bad_status(c, n, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   cudaStream_t s0 = c->slot[0].st;
-  launch_batch_challenge(c->vb_r.p, c->vb_tuples.p, n, s0);
+  launch_batch_challenge(c->vb_r.p, c->vb_tuples.p, n, s0, c->mode == 1);
   launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, 0, (int)n, c->vb_scratch.p, s0);
   launch_batch_final((int*)c->vb_ok.p, c->vb_partial.p, 1, c->d_prep0, c->d_prep1, s0);
   int okv = 0;
@@ -920,7 +1044,7 @@ C_KZG_RET lwkzg_verify_batch_phase1(uint8_t* tuples160, const Blob* blobs, const
   if (!verify_prepare(c, blobs, commitments, proofs, n_local)) return C_KZG_ERROR;
   bool bad = false;
   if (!any_bad_status(c, n_local, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment or proof bytes"); return C_KZG_ERROR; }
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   if (cudaMemcpy(tuples160, c->vb_tuples.p, n_local * 160, cudaMemcpyDeviceToHost) != cudaSuccess) { set_err("D2H failed"); return C_KZG_ERROR; }
   return C_KZG_OK;
@@ -938,7 +1062,7 @@ C_KZG_RET lwkzg_verify_batch_phase2(uint8_t* partial288, const uint8_t* all_tupl
   bool good = [&]() -> bool {
     CU_TRY(cudaMemcpyAsync(d_all, all_tuples160, n_total * 160, cudaMemcpyHostToDevice, s0));
     if (!c->vb_r.ensure(32) || !c->vb_partial.ensure(288) || !c->vb_scratch.ensure(batch_partials_scratch_bytes((int)std::max<size_t>(n_local, 1)))) return false;
-    launch_batch_challenge(c->vb_r.p, d_all, n_total, s0);
+    launch_batch_challenge(c->vb_r.p, d_all, n_total, s0, c->mode == 1);
     launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, first, (int)n_local, c->vb_scratch.p, s0);
     CU_TRY(cudaMemcpyAsync(partial288, c->vb_partial.p, 288, cudaMemcpyDeviceToHost, s0));
     CU_TRY(cudaStreamSynchronize(s0));

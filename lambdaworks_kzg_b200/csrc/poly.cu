@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(32) challenge_midstate_kernel(Sha256State* __r
 
 // blocks 2048 (blob tail 32 B + commitment[0..32)) and 2049 (commitment[32..48) + padding)
 __global__ void __launch_bounds__(32) challenge_finish_kernel(uint32_t* __restrict__ z_out, const Sha256State* __restrict__ states,
-                                                               const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commit48, int n) {
+                                                               const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commit48, int n,
+                                                               int le_digest) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   Sha256State s = states[b];
@@ -71,8 +72,9 @@ __global__ void __launch_bounds__(32) challenge_finish_kernel(uint32_t* __restri
   w[15] = 131152u * 8u;
   sha256_compress(s, w);
   // digest read big-endian, reduced mod r (hash_field_unsafe, utils.rs:148-154)
+  // (MODE_CKZG_LE reads the digest little-endian: SURVEY App. B)
   Fr z;
-  for (int i = 0; i < 8; i++) z.l[i] = s.h[7 - i];
+  for (int i = 0; i < 8; i++) z.l[i] = le_digest ? bswap32(s.h[i]) : s.h[7 - i];
   mod_reduce_small<FrCfg, 2>(z.l);
   for (int i = 0; i < 8; i++) z_out[b * 8 + i] = z.l[i];
 }
@@ -153,9 +155,10 @@ void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaS
   challenge_midstate_kernel<<<(n + 31) / 32, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n);
   count_launch();
 }
-void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st) {
+void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st, bool le_digest) {
   if (n <= 0) return;
-  challenge_finish_kernel<<<(n + 31) / 32, 32, 0, st>>>((uint32_t*)d_z, (const Sha256State*)d_states, (const uint8_t*)d_blobs, (const uint8_t*)d_commit48, n);
+  challenge_finish_kernel<<<(n + 31) / 32, 32, 0, st>>>((uint32_t*)d_z, (const Sha256State*)d_states, (const uint8_t*)d_blobs, (const uint8_t*)d_commit48, n,
+                                                       le_digest ? 1 : 0);
   count_launch();
 }
 void launch_fr_from_be(void* d_z, const void* d_z_be32, int n, cudaStream_t st) {

@@ -103,21 +103,26 @@ __global__ void __launch_bounds__(32) verify_single_kernel(int* __restrict__ ok_
 
 // tuple_i = compress(C_i) || be32(z_i) || be32(y_i) || compress(pi_i)  (utils.rs:183-201)
 __global__ void make_tuples_kernel(uint8_t* __restrict__ tuples, const uint8_t* __restrict__ c48, const uint32_t* __restrict__ z,
-                                   const uint32_t* __restrict__ y, const uint8_t* __restrict__ pi48, int n) {
+                                   const uint32_t* __restrict__ y, const uint8_t* __restrict__ pi48, int n, int le) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint8_t* t = tuples + (size_t)i * 160;
   for (int k = 0; k < 48; k++) t[k] = c48[(size_t)i * 48 + k];
   Fr zz, yy;
   for (int k = 0; k < 8; k++) { zz.l[k] = z[i * 8 + k]; yy.l[k] = y[i * 8 + k]; }
-  fr_canon_to_be32(t + 48, zz);
-  fr_canon_to_be32(t + 80, yy);
+  if (le) {  // MODE_CKZG_LE: field elements are hashed little-endian
+    for (int k = 0; k < 8; k++)
+      for (int b = 0; b < 4; b++) { t[48 + 4 * k + b] = (uint8_t)(zz.l[k] >> (8 * b)); t[80 + 4 * k + b] = (uint8_t)(yy.l[k] >> (8 * b)); }
+  } else {
+    fr_canon_to_be32(t + 48, zz);
+    fr_canon_to_be32(t + 80, yy);
+  }
   for (int k = 0; k < 48; k++) t[112 + k] = pi48[(size_t)i * 48 + k];
 }
 
 // r = H("RCKZGBATCH___V1_" || le64(4096) || le64(n) || tuples), read big-endian, mod r.
 // Sequential by nature (one SHA-256 stream): single thread.
-__global__ void batch_challenge_kernel(uint32_t* __restrict__ r_out, const uint8_t* __restrict__ tuples, unsigned long long n_total) {
+__global__ void batch_challenge_kernel(uint32_t* __restrict__ r_out, const uint8_t* __restrict__ tuples, unsigned long long n_total, int le) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   Sha256State s;
   sha256_init(s);
@@ -152,7 +157,7 @@ __global__ void batch_challenge_kernel(uint32_t* __restrict__ r_out, const uint8
     sha256_compress(s, w);
   }
   Fr r;
-  for (int i = 0; i < 8; i++) r.l[i] = s.h[7 - i];
+  for (int i = 0; i < 8; i++) r.l[i] = le ? bswap32(s.h[i]) : s.h[7 - i];
   mod_reduce_small<FrCfg, 2>(r.l);
   for (int i = 0; i < 8; i++) r_out[i] = r.l[i];
 }
@@ -334,13 +339,14 @@ void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, 
                                          (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
   count_launch();
 }
-void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st) {
+void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le) {
   if (n <= 0) return;
-  make_tuples_kernel<<<(n + 63) / 64, 64, 0, st>>>((uint8_t*)d_tuples160, (const uint8_t*)d_c48, (const uint32_t*)d_z, (const uint32_t*)d_y, (const uint8_t*)d_pi48, n);
+  make_tuples_kernel<<<(n + 63) / 64, 64, 0, st>>>((uint8_t*)d_tuples160, (const uint8_t*)d_c48, (const uint32_t*)d_z, (const uint32_t*)d_y, (const uint8_t*)d_pi48, n,
+                                                  le ? 1 : 0);
   count_launch();
 }
-void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st) {
-  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (const uint8_t*)d_tuples160, (unsigned long long)n_total);
+void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, bool le) {
+  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (const uint8_t*)d_tuples160, (unsigned long long)n_total, le ? 1 : 0);
   count_launch();
 }
 size_t batch_partials_scratch_bytes(int n_local) {
