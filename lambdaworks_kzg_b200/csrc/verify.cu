@@ -10,7 +10,7 @@
 // so that both G2 arguments are the FIXED setup points whose Miller-loop lines
 // were precomputed at load time (pairing.cuh): no G2 arithmetic at verify time.
 #include "kernels.h"
-#include "pairing.cuh"
+#include "pairing_warp.cuh"
 #include "sha256.cuh"
 
 namespace lw {
@@ -54,21 +54,14 @@ __global__ void g2_check_kernel(int* __restrict__ bad, const uint32_t* __restric
   bad[i] = g2a_on_curve(q) ? 0 : 1;
 }
 
-// ---- two-pairing check: lanes 0 and 1 run one Miller loop each, lane 0 merges.
-__device__ __forceinline__ bool two_pairing_check(const G1Affine& a, const G1Affine& b, const G2Prepared* prep0, const G2Prepared* prep1, Fp12* sh /* shared, 1 elem */) {
-  const int lane = threadIdx.x;
-  Fp12 f;
-  if (lane == 0) f = miller_loop(&a, prep0, 1);
-  if (lane == 1) {
-    f = miller_loop(&b, prep1, 1);
-    *sh = f;
-  }
-  __syncthreads();
+// ---- two-pairing check, warp-cooperative (pairing_warp.cuh): every Fp12 product is
+// spread over 18 lanes.  `pts` (2 points) and `m` live in shared memory; all 32
+// lanes of the block's single warp must call this.
+__device__ __forceinline__ bool two_pairing_check(const G1Affine* pts, const G2Prepared* prep0, const G2Prepared* prep1, WarpPairingMem& m) {
+  const G2Prepared* qs[2] = {prep0, prep1};
+  warp_pairing_product(m, pts, qs, 2);
   bool ok = false;
-  if (lane == 0) {
-    f = fp12_mul(f, *sh);
-    ok = fp12_is_one(final_exponentiation(f));
-  }
+  if (threadIdx.x == 0) ok = warp_fp12_is_one(m.f);
   return ok;
 }
 
@@ -78,8 +71,8 @@ __global__ void __launch_bounds__(32) verify_single_kernel(int* __restrict__ ok_
                                                             const G1Affine* __restrict__ g1_0, const G2Prepared* __restrict__ prep0,
                                                             const G2Prepared* __restrict__ prep1) {
   __shared__ G1Xyzz sh_pt[2];
-  __shared__ Fp12 sh_f;
-  __shared__ G1Affine sh_lhs;
+  __shared__ WarpPairingMem sh_m;
+  __shared__ G1Affine sh_pair[2];
   const int lane = threadIdx.x;
   G1Affine C = *c_aff, PI = *pi_aff;
   if (lane < 2) {
@@ -93,11 +86,11 @@ __global__ void __launch_bounds__(32) verify_single_kernel(int* __restrict__ ok_
     G1Xyzz acc = xyzz_from_affine(C);
     xyzz_add_ni(acc, xyzz_neg(sh_pt[0]));
     xyzz_add_ni(acc, sh_pt[1]);
-    sh_lhs = xyzz_to_affine(acc);
+    sh_pair[0] = xyzz_to_affine(acc);
+    sh_pair[1] = g1a_neg(PI);
   }
   __syncthreads();
-  G1Affine lhs = sh_lhs;
-  bool ok = two_pairing_check(lhs, g1a_neg(PI), prep0, prep1, &sh_f);
+  bool ok = two_pairing_check(sh_pair, prep0, prep1, sh_m);
   if (lane == 0) *ok_out = ok ? 1 : 0;
 }
 
@@ -301,7 +294,7 @@ __device__ __forceinline__ G1Affine affine_from_be96(const uint8_t* b) {
 // ok = [ e(c_minus_y + proof_z, g2_0) == e(proof_lincomb, g2_1) ]   (lib.rs:679-691)
 __global__ void __launch_bounds__(32) batch_final_kernel(int* __restrict__ ok_out, const uint8_t* __restrict__ partials, int n_ranks,
                                                           const G2Prepared* __restrict__ prep0, const G2Prepared* __restrict__ prep1) {
-  __shared__ Fp12 sh_f;
+  __shared__ WarpPairingMem sh_m;
   __shared__ G1Affine sh_pts[2];
   const int lane = threadIdx.x;
   if (lane < 2) {
@@ -319,8 +312,7 @@ __global__ void __launch_bounds__(32) batch_final_kernel(int* __restrict__ ok_ou
     sh_pts[lane] = lane == 0 ? a : g1a_neg(a);
   }
   __syncthreads();
-  G1Affine rhs = sh_pts[0], npl = sh_pts[1];
-  bool ok = two_pairing_check(rhs, npl, prep0, prep1, &sh_f);
+  bool ok = two_pairing_check(sh_pts, prep0, prep1, sh_m);
   if (lane == 0) *ok_out = ok ? 1 : 0;
 }
 

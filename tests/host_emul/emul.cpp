@@ -13,6 +13,7 @@
 #include "../../lambdaworks_kzg_b200/csrc/recode.cuh"
 #ifdef LWKZG_EMUL_PAIRING
 #include "../../lambdaworks_kzg_b200/csrc/pairing.cuh"
+#include "../../lambdaworks_kzg_b200/csrc/pairing_warp.cuh"
 #endif
 
 using namespace lw;
@@ -139,6 +140,42 @@ int emul_cyclotomic_sqr_check(const uint8_t* a1, const uint8_t* q1) {
   Fp12 g = fp12_mul(fp12_conj(f), fp12_inv(f));
   g = fp12_mul(fp12_frobenius(fp12_frobenius(g)), g);
   return fp12_eq(fp12_cyclotomic_sqr(g), fp12_sqr(g)) && !fp12_eq(fp12_cyclotomic_sqr(f), fp12_sqr(f)) ? 1 : 0;
+}
+// warp-cooperative pairing (pairing_warp.cuh), lanes emulated sequentially:
+// returns 1 iff (a) a random-ish Fp12 product matches the single-thread product and
+// (b) the two-pair warp pairing result is bit-identical to the single-thread one
+int emul_warp_pairing_check(const uint8_t* a1, const uint8_t* q1, const uint8_t* a2, const uint8_t* q2, int* is_one) {
+  G1Affine P[2] = {load_aff(a1), load_aff(a2)};
+  G2Affine Q[2];
+  const uint8_t* qs[2] = {q1, q2};
+  for (int i = 0; i < 2; i++) {
+    Q[i].x.c0 = fp_from_be48(qs[i]); Q[i].x.c1 = fp_from_be48(qs[i] + 48);
+    Q[i].y.c0 = fp_from_be48(qs[i] + 96); Q[i].y.c1 = fp_from_be48(qs[i] + 144);
+  }
+  static G2Prepared prep[2];
+  g2_prepare(prep[0], Q[0]);
+  g2_prepare(prep[1], Q[1]);
+  Fp12 f1 = miller_loop(&P[0], &prep[0], 1), f2 = miller_loop(&P[1], &prep[1], 1);
+  // (a) multiplication
+  static WarpPairingMem m;
+  m.a = *reinterpret_cast<WarpFp12*>(&f1);
+  m.b = *reinterpret_cast<WarpFp12*>(&f2);
+  wfp12_mul(m.c, m.a, m.b, m.sc);
+  Fp12 want = fp12_mul(f1, f2);
+  if (!fp12_eq(*reinterpret_cast<Fp12*>(&m.c), want)) return 0;
+  wfp12_mul(m.a, m.a, m.a, m.sc);  // aliasing
+  Fp12 sq = fp12_sqr(f1);
+  if (!fp12_eq(*reinterpret_cast<Fp12*>(&m.a), sq)) return 0;
+  wfp12_frobenius(m.t, m.c);
+  Fp12 fr = fp12_frobenius(want);
+  if (!fp12_eq(*reinterpret_cast<Fp12*>(&m.t), fr)) return 0;
+  // (b) full pairing product
+  const G2Prepared* pq[2] = {&prep[0], &prep[1]};
+  warp_pairing_product(m, P, pq, 2);
+  Fp12 ref = final_exponentiation(miller_loop(P, prep, 2));
+  if (!fp12_eq(*reinterpret_cast<Fp12*>(&m.f), ref)) return 0;
+  *is_one = warp_fp12_is_one(m.f) ? 1 : 0;
+  return 1;
 }
 // raw Fp12 pairing output for debugging / cross-checking with oracle/py/pairing.py
 void emul_pairing_gt(uint8_t* out576, const uint8_t* a1, const uint8_t* q1) {

@@ -287,3 +287,18 @@ def test_pairing_check(lib, py_setup):
 def test_cyclotomic_squaring(lib, py_setup):
     p = bls.g1_mul(bls.G1, 424242)
     assert lib.emul_cyclotomic_sqr_check(aff_bytes(p), _g2_bytes(py_setup.g2[1])) == 1
+
+
+def test_warp_cooperative_pairing(lib, py_setup):
+    """pairing_warp.cuh (lanes emulated one after the other) == single-thread pairing, bit for bit."""
+    g2_0, g2_1 = py_setup.g2[0], py_setup.g2[1]
+    tau = py_setup.tau
+    A = bls.g1_mul(bls.G1, 987654321)
+    tA = bls.g1_mul(A, tau)
+    one = ctypes.c_int(-1)
+    assert lib.emul_warp_pairing_check(aff_bytes(tA), _g2_bytes(g2_0), aff_bytes(bls.g1_neg(A)), _g2_bytes(g2_1), ctypes.byref(one)) == 1
+    assert one.value == 1
+    assert lib.emul_warp_pairing_check(aff_bytes(tA), _g2_bytes(g2_0), aff_bytes(A), _g2_bytes(g2_1), ctypes.byref(one)) == 1
+    assert one.value == 0
+    assert lib.emul_warp_pairing_check(aff_bytes(None), _g2_bytes(g2_0), aff_bytes(bls.g1_neg(A)), _g2_bytes(g2_1), ctypes.byref(one)) == 1
+    assert one.value == 0
