@@ -105,6 +105,10 @@ struct Ctx {
   // batched-verification workspace (sized for the largest batch seen)
   DevBuf vb_cin, vb_pin, vb_caff, vb_piaff, vb_c48r, vb_p48r, vb_z, vb_y, vb_tuples, vb_status, vb_r, vb_partial, vb_scratch, vb_ok, vb_zy_in;
   size_t vb_n = 0;  // items currently held by the workspace (phase1 -> phase2)
+  // pinned host staging for batch results: a D2H copy into pageable memory would block the host
+  // until the chunk's kernels finish and serialise the two pipeline slots
+  void* h_stage = nullptr;
+  size_t h_stage_cap = 0;
   std::mutex mu;
 };
 
@@ -157,6 +161,7 @@ void destroy_ctx(Ctx* c) {
   if (c->d_prep1) cudaFree(c->d_prep1);
   if (c->d_roots) cudaFree(c->d_roots);
   if (c->d_gen) cudaFree(c->d_gen);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   c->magic = 0;
   delete c;
 }
@@ -490,10 +495,21 @@ C_KZG_RET host_batch(Mode mode, const KZGSettings* s, size_t n, const Blob* blob
     std::lock_guard<std::mutex> lk2(g_mu);
     chunk = std::max(1L, opts().chunk_blobs);
   }
-  std::vector<int> st_host(n, 0);
-  // outputs land in temporaries so that failed items leave caller memory untouched (lib.rs:275-281, 334-341)
-  std::vector<Bytes48> c_tmp(c_out ? n : 0), p_tmp(p_out ? n : 0);
-  std::vector<Bytes32> y_tmp(y_out ? n : 0);
+  // outputs land in (pinned) temporaries so that failed items leave caller memory untouched
+  // (lib.rs:275-281, 334-341) and the D2H copies stay asynchronous
+  const size_t stage_bytes = n * (48 + 48 + 32 + sizeof(int));
+  if (stage_bytes > c->h_stage_cap) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->h_stage_cap = 0;
+    if (cudaMallocHost(&c->h_stage, stage_bytes) != cudaSuccess) { set_err("cudaMallocHost failed"); return C_KZG_MALLOC; }
+    c->h_stage_cap = stage_bytes;
+  }
+  Bytes48* c_tmp = (Bytes48*)c->h_stage;
+  Bytes48* p_tmp = c_tmp + n;
+  Bytes32* y_tmp = (Bytes32*)(p_tmp + n);
+  int* st_host = (int*)(y_tmp + n);
+  memset(st_host, 0, n * sizeof(int));
   auto fail = [&]() {
     for (auto& sl : c->slot) { cudaStreamSynchronize(sl.st); cudaStreamSynchronize(sl.aux); }
     return C_KZG_ERROR;
@@ -529,9 +545,8 @@ C_KZG_RET host_batch(Mode mode, const KZGSettings* s, size_t n, const Blob* blob
     if (status) status[i] = st_host[i];
   }
   if (!status) {
-    C_KZG_RET r = first_bad(st_host);
-    if (r != C_KZG_OK) set_err("invalid input item");
-    return r;
+    for (size_t i = 0; i < n; i++)
+      if (st_host[i]) { set_err("invalid input item"); return (C_KZG_RET)st_host[i]; }
   }
   return C_KZG_OK;
 }
