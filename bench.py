@@ -147,6 +147,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
