@@ -46,6 +46,7 @@ from .api import (  # noqa: F401
     verify_batch_phase3,
     verify_blob_kzg_proof,
     verify_blob_kzg_proof_batch,
+    verify_blob_kzg_proof_batch_ptr,
     verify_kzg_proof,
 )
 from .sharding import shard_range, verify_blob_kzg_proof_batch_distributed  # noqa: F401

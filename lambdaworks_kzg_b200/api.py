@@ -235,6 +235,13 @@ def verify_blob_kzg_proof_batch(blobs: Sequence[bytes], commitments: Sequence[by
     return bool(ok.value)
 
 
+def verify_blob_kzg_proof_batch_ptr(blobs_ptr: int, commitments_ptr: int, proofs_ptr: int, n: int, s) -> bool:
+    """Same C call with raw host addresses (e.g. pinned torch tensors): no Python-side copies."""
+    ok = ctypes.c_bool(False)
+    _check(load_library().verify_blob_kzg_proof_batch(ctypes.byref(ok), blobs_ptr, commitments_ptr, proofs_ptr, n, _sp(s)), "verify_blob_kzg_proof_batch")
+    return bool(ok.value)
+
+
 # ------------------------------------------------------------------ batch extensions (host buffers)
 def _status_list(n):
     return (ctypes.c_int * max(n, 1))()

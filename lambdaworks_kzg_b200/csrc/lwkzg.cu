@@ -834,7 +834,7 @@ int lwkzg_set_option(const char* name, long value) {
   std::lock_guard<std::mutex> lk(g_mu);
   std::string n(name ? name : "");
   if (n == "window_bits") { if (value < 4 || value > 15) return 1; opts().window_bits = value; return 0; }
-  if (n == "msm_blocks_per_blob") { if (value < 0 || value > 128 || (value & (value - 1))) return 1; opts().msm_blocks_per_blob = value; return 0; }
+  if (n == "msm_blocks_per_blob") { if (value < 0 || value > 128 || (value > 32 && (value & (value - 1)))) return 1; opts().msm_blocks_per_blob = value; return 0; }
   if (n == "chunk_blobs") { if (value < 1) return 1; opts().chunk_blobs = value; return 0; }
   if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
   return 1;

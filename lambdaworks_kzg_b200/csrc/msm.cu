@@ -177,9 +177,40 @@ void launch_msm_gather(void* d_partials, const void* d_table, int c, const void*
   count_launch();
 }
 
+// Warp-per-blob variant for many partials (single-blob / tiny-batch calls use up to
+// 128 blocks per blob): lanes sum strided partials, then a 5-level tree in shared memory.
+__global__ void __launch_bounds__(32) msm_finalize_warp_kernel(uint8_t* __restrict__ out48, G1Affine* __restrict__ aff_out,
+                                                                const G1Xyzz* __restrict__ partials, int parts, int n) {
+  __shared__ uint32_t red[48 * 16];
+  const int blob = blockIdx.x, lane = threadIdx.x;
+  const G1Xyzz* p = partials + (size_t)blob * parts;
+  G1Xyzz acc = xyzz_inf();
+  for (int i = lane; i < parts; i += 32) {
+    G1Xyzz o = p[i];
+    xyzz_add_ni(acc, o);
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    if (lane >= s && lane < 2 * s) xyzz_to_smem(red, 16, lane - s, acc);
+    __syncwarp();
+    if (lane < s) {
+      G1Xyzz o = xyzz_from_smem(red, 16, lane);
+      xyzz_add_ni(acc, o);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    G1Affine a = xyzz_to_affine(acc);
+    if (aff_out) aff_out[blob] = a;
+    if (out48) g1_compress(out48 + (size_t)blob * 48, a);
+  }
+}
+
 void launch_msm_finalize(void* d_out48, void* d_aff_out, const void* d_partials, int parts_per_blob, int n_blobs, cudaStream_t st) {
   if (n_blobs <= 0) return;
-  msm_finalize_kernel<<<(n_blobs + 31) / 32, 32, 0, st>>>((uint8_t*)d_out48, (G1Affine*)d_aff_out, (const G1Xyzz*)d_partials, parts_per_blob, n_blobs);
+  if (parts_per_blob >= 8)
+    msm_finalize_warp_kernel<<<n_blobs, 32, 0, st>>>((uint8_t*)d_out48, (G1Affine*)d_aff_out, (const G1Xyzz*)d_partials, parts_per_blob, n_blobs);
+  else
+    msm_finalize_kernel<<<(n_blobs + 31) / 32, 32, 0, st>>>((uint8_t*)d_out48, (G1Affine*)d_aff_out, (const G1Xyzz*)d_partials, parts_per_blob, n_blobs);
   count_launch();
 }
 

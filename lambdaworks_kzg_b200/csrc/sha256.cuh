@@ -56,6 +56,61 @@ LW_INL void sha256_compress(Sha256State& s, uint32_t* w) {
   s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
 
+// Rounds only, with W[i] + K[i] precomputed (warp-cooperative path below).
+// wk is laid out [64][32]: word i of the block prepared by lane b at wk[i * 32 + b].
+LW_INL void sha256_rounds_wk(Sha256State& s, const uint32_t* wk, int b) {
+  uint32_t a = s.h[0], bb = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#pragma unroll
+  for (int i = 0; i < 64; i++) {
+    uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+    uint32_t ch = (e & f) ^ (~e & g);
+    uint32_t t1 = h + S1 + ch + wk[i * 32 + b];
+    uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+    uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
+    uint32_t t2 = S0 + mj;
+    h = g; g = f; f = e; e = d + t1; d = c; c = bb; bb = a; a = t1 + t2;
+  }
+  s.h[0] += a; s.h[1] += bb; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+// Message-schedule expansion of one block into wk (adds the round constants).
+LW_INL void sha256_expand_wk(uint32_t* wk, int b, uint32_t* w /* 16 words in, 64 used */) {
+#pragma unroll
+  for (int i = 0; i < 64; i++) {
+    if (i >= 16) {
+      uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+      uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+      uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+      w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+    }
+    wk[i * 32 + b] = w[i & 15] + SHA_K[i];
+  }
+}
+#if !defined(LWKZG_HOST_EMUL)
+// Warp-cooperative hashing of `nblocks` consecutive full blocks: SHA-256 is
+// sequential in the state but the message schedule (60 % of the work) is not, so
+// the 32 lanes expand 32 blocks in parallel and lane 0 then only runs the rounds.
+// load(blk, w16) must fill the 16 big-endian words of block blk.  The state is
+// lane 0's; wk is 64*32 words of shared memory owned by this warp.
+template <class Load>
+__device__ __forceinline__ void sha256_warp_blocks(Sha256State& s, int nblocks, Load load, uint32_t* wk) {
+  const int lane = threadIdx.x & 31;
+  for (int base = 0; base < nblocks; base += 32) {
+    const int blk = base + lane;
+    if (blk < nblocks) {
+      uint32_t w[16];
+      load(blk, w);
+      sha256_expand_wk(wk, lane, w);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int cnt = (nblocks - base < 32) ? (nblocks - base) : 32;
+      for (int b = 0; b < cnt; b++) sha256_rounds_wk(s, wk, b);
+    }
+    __syncwarp();
+  }
+}
+#endif
+
 LW_INL void sha256_digest_bytes(uint8_t* out32, const Sha256State& s) {
   for (int i = 0; i < 8; i++) {
     out32[4 * i] = (uint8_t)(s.h[i] >> 24); out32[4 * i + 1] = (uint8_t)(s.h[i] >> 16);

@@ -114,28 +114,37 @@ __global__ void make_tuples_kernel(uint8_t* __restrict__ tuples, const uint8_t* 
 }
 
 // r = H("RCKZGBATCH___V1_" || le64(4096) || le64(n) || tuples), read big-endian, mod r.
-// Sequential by nature (one SHA-256 stream): single thread.
-__global__ void batch_challenge_kernel(uint32_t* __restrict__ r_out, const uint8_t* __restrict__ tuples, unsigned long long n_total, int le) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// One SHA-256 stream: the warp expands message schedules in parallel, lane 0 runs the rounds.
+__global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restrict__ r_out, const uint8_t* __restrict__ tuples, unsigned long long n_total, int le) {
+  __shared__ uint32_t wk[64 * 32];
+  __shared__ uint8_t head[32];
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    const char dom[17] = "RCKZGBATCH___V1_";
+    for (int i = 0; i < 16; i++) head[i] = (uint8_t)dom[i];
+    for (int i = 0; i < 8; i++) head[16 + i] = 0;
+    head[17] = 0x10;  // le64(4096)
+    for (int i = 0; i < 8; i++) head[24 + i] = (uint8_t)(n_total >> (8 * i));
+  }
+  __syncwarp();
+  const unsigned long long total = 32ull + 160ull * n_total;
+  const int nfull = (int)(total / 64);
+  auto byte_at = [&](unsigned long long off) -> uint8_t { return off < 32 ? head[off] : tuples[off - 32]; };
   Sha256State s;
   sha256_init(s);
-  uint32_t w[16];
-  // header: 32 bytes; then 160 n bytes.  Stream bytes through a 64-byte window.
-  uint8_t head[32] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_', 0, 0x10, 0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 8; i++) head[24 + i] = (uint8_t)(n_total >> (8 * i));
-  const unsigned long long total = 32ull + 160ull * n_total;
-  auto byte_at = [&](unsigned long long off) -> uint8_t { return off < 32 ? head[off] : tuples[off - 32]; };
-  unsigned long long off = 0;
-  for (; off + 64 <= total; off += 64) {
-    if (off >= 32 && ((off - 32) & 3) == 0) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(tuples + (off - 32));
+  sha256_warp_blocks(s, nfull, [&](int blk, uint32_t* w) {
+    unsigned long long off = 64ull * blk;
+    if (blk >= 1) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(tuples + (off - 32));  // 32-byte aligned
       for (int i = 0; i < 16; i++) w[i] = bswap32(src[i]);
     } else {
       for (int i = 0; i < 16; i++)
         w[i] = ((uint32_t)byte_at(off + 4 * i) << 24) | ((uint32_t)byte_at(off + 4 * i + 1) << 16) | ((uint32_t)byte_at(off + 4 * i + 2) << 8) | byte_at(off + 4 * i + 3);
     }
-    sha256_compress(s, w);
-  }
+  }, wk);
+  if (lane != 0) return;
+  uint32_t w[16];
+  unsigned long long off = 64ull * nfull;
   uint8_t tail[128];
   int rem = (int)(total - off);
   for (int i = 0; i < rem; i++) tail[i] = byte_at(off + i);
