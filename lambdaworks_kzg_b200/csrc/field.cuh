@@ -50,8 +50,13 @@ inline Fp fp_mul_nv(Fp a, Fp b) { return fp_mul(a, b); }
 #else
 static __device__ __noinline__ Fp fp_mul_nv(Fp a, Fp b) { Fp r; mont_mul<FpCfg>(r.l, a.l, b.l); return r; }
 #endif
+#if defined(LWKZG_HOST_EMUL)
+inline Fp fp_sqr_nv(Fp a) { return fp_sqr(a); }
+#else
+static __device__ __noinline__ Fp fp_sqr_nv(Fp a) { Fp r; mont_sqr<FpCfg>(r.l, a.l); return r; }
+#endif
 LW_INL void fp_mul_ni(Fp& r, const Fp& a, const Fp& b) { r = fp_mul_nv(a, b); }
-LW_INL void fp_sqr_ni(Fp& r, const Fp& a) { r = fp_mul_nv(a, a); }
+LW_INL void fp_sqr_ni(Fp& r, const Fp& a) { r = fp_sqr_nv(a); }
 
 LW_COLD Fp fp_pow_const(const Fp& a, const uint32_t* e, int ne) {
   Fp acc = fp_one();

@@ -158,10 +158,10 @@ LW_INL void xyzz_madd_hot(G1Xyzz& acc, const G1Affine& p) {
     xyzz_madd_rare(acc, p);
     return;
   }
-  Fp PP = fp_mul_nv(Pd, Pd);
+  Fp PP = fp_sqr_nv(Pd);
   Fp PPP = fp_mul_nv(Pd, PP);
   Fp Q = fp_mul_nv(acc.x, PP);
-  Fp X3 = fp_sub(fp_sub(fp_mul_nv(Rd, Rd), PPP), fp_dbl(Q));
+  Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
   Fp Y3 = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(acc.y, PPP));
   acc.zz = fp_mul_nv(acc.zz, PP);
   acc.zzz = fp_mul_nv(acc.zzz, PPP);

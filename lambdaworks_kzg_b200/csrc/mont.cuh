@@ -188,9 +188,123 @@ LW_INL void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   for (int i = 0; i < N; i++) r[i] = borrow ? T[i] : t[i];
 }
 
+// Montgomery square: r = a^2 / 2^(32N) mod m.
+//
+// Product phase with the symmetric half only: the off-diagonal products a_i a_j
+// (i < j) are accumulated once -- j - i odd lands on odd limb positions and goes
+// to the accumulator PO (pairs (1,2)(3,4)...), j - i even to PE (pairs (0,1)(2,3)
+// ...), so every row is again two aligned carry chains of wide MACs -- then
+// doubled with funnel shifts and completed by the N diagonal squares (one more
+// aligned chain): N(N+1)/2 wide MACs instead of N^2.  Rows are processed in
+// ascending i, so the limb that receives a chain's carry-out holds at most
+// earlier carries.  The 2N-limb product is then reduced with the same even/odd
+// reduction rounds as mont_mul, injecting one high product limb per round.
 template <class C>
 LW_INL void mont_sqr(uint32_t* r, const uint32_t* a) {
-  mont_mul<C>(r, a, a);
+  constexpr int N = C::N;
+  const uint32_t* m = C::mod();
+  uint32_t PE[2 * N], PO[2 * N];  // PE[k] = limb k, PO[k] = limb k + 1
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) { PE[k] = 0; PO[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) {
+    // odd offsets j = i+1, i+3, ... -> PO indices (i+j-1, i+j)
+    {
+      const int j0 = i + 1;
+      PO[i + j0 - 1] = ptx::mad_lo_cc(a[i], a[j0], PO[i + j0 - 1]);
+      PO[i + j0] = ptx::madc_hi_cc(a[i], a[j0], PO[i + j0]);
+      int last = j0;
+#pragma unroll
+      for (int j = i + 3; j < N; j += 2) {
+        PO[i + j - 1] = ptx::madc_lo_cc(a[i], a[j], PO[i + j - 1]);
+        PO[i + j] = ptx::madc_hi_cc(a[i], a[j], PO[i + j]);
+        last = j;
+      }
+      PO[i + last + 1] = ptx::addc(PO[i + last + 1], 0);
+    }
+    // even offsets j = i+2, i+4, ... -> PE indices (i+j, i+j+1)
+    if (i + 2 < N) {
+      const int j0 = i + 2;
+      PE[i + j0] = ptx::mad_lo_cc(a[i], a[j0], PE[i + j0]);
+      PE[i + j0 + 1] = ptx::madc_hi_cc(a[i], a[j0], PE[i + j0 + 1]);
+      int last = j0;
+#pragma unroll
+      for (int j = i + 4; j < N; j += 2) {
+        PE[i + j] = ptx::madc_lo_cc(a[i], a[j], PE[i + j]);
+        PE[i + j + 1] = ptx::madc_hi_cc(a[i], a[j], PE[i + j + 1]);
+        last = j;
+      }
+      PE[i + last + 2] = ptx::addc(PE[i + last + 2], 0);
+    }
+  }
+  // S = PE + (PO << 32), T = 2 S + sum a_i^2 2^(64 i)
+  uint32_t T[2 * N];
+  T[0] = PE[0];
+  T[1] = ptx::add_cc(PE[1], PO[0]);
+#pragma unroll
+  for (int k = 2; k < 2 * N; k++) T[k] = ptx::addc_cc(PE[k], PO[k - 1]);
+#pragma unroll
+  for (int k = 2 * N - 1; k > 0; k--) T[k] = (T[k] << 1) | (T[k - 1] >> 31);
+  T[0] <<= 1;
+  T[0] = ptx::mad_lo_cc(a[0], a[0], T[0]);
+  T[1] = ptx::madc_hi_cc(a[0], a[0], T[1]);
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    T[2 * i] = ptx::madc_lo_cc(a[i], a[i], T[2 * i]);
+    T[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], T[2 * i + 1]);
+  }
+  // ---- Montgomery reduction of T: running window R = E + O 2^32
+  uint32_t E[N], O[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) { E[k] = T[k]; O[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (i > 0) {
+      // R >>= 32: O becomes the new E; E shifted down one pair becomes the new O,
+      // with product limb N+i-1 entering at window position N-1
+      const uint32_t orphan = E[1];
+      uint32_t nO[N];
+#pragma unroll
+      for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
+      nO[N - 2] = T[N + i - 1];
+      nO[N - 1] = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) E[j] = O[j];
+#pragma unroll
+      for (int j = 0; j < N; j++) O[j] = nO[j];
+      E[0] = ptx::add_cc(E[0], orphan);  // carry flows into the O chain below (mul.lo leaves CC alone)
+    }
+    const uint32_t mi = ptx::mul_lo(E[0], C::INV);
+    if (i > 0) {
+      O[0] = ptx::madc_lo_cc(m[1], mi, O[0]);
+    } else {
+      O[0] = ptx::mad_lo_cc(m[1], mi, O[0]);
+    }
+    O[1] = ptx::madc_hi_cc(m[1], mi, O[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      O[j] = ptx::madc_lo_cc(m[j + 1], mi, O[j]);
+      O[j + 1] = ptx::madc_hi_cc(m[j + 1], mi, O[j + 1]);
+    }
+    E[0] = ptx::mad_lo_cc(m[0], mi, E[0]);  // == 0
+    E[1] = ptx::madc_hi_cc(m[0], mi, E[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      E[j] = ptx::madc_lo_cc(m[j], mi, E[j]);
+      E[j + 1] = ptx::madc_hi_cc(m[j], mi, E[j + 1]);
+    }
+    O[N - 1] = ptx::addc(O[N - 1], 0);
+  }
+  // result limb k = O[k] + E[k+1], plus the last product limb at position N-1
+  uint32_t Rr[N];
+  Rr[0] = ptx::add_cc(O[0], E[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) Rr[k] = ptx::addc_cc(O[k], E[k + 1]);
+  Rr[N - 1] = ptx::addc(O[N - 1], T[2 * N - 1]);
+  uint32_t t[N];
+  uint32_t borrow = limbs_sub<N>(t, Rr, m);
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = borrow ? Rr[i] : t[i];
 }
 
 // Reduce an arbitrary N-limb integer (< 2^(32N)) into [0, m): at most

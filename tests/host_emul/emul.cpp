@@ -21,6 +21,8 @@ using namespace lw;
 extern "C" {
 
 void emul_fp_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul<FpCfg>(r, a, b); }
+void emul_fp_sqr(uint32_t* r, const uint32_t* a) { mont_sqr<FpCfg>(r, a); }
+void emul_fr_sqr(uint32_t* r, const uint32_t* a) { mont_sqr<FrCfg>(r, a); }
 void emul_fp_add(uint32_t* r, const uint32_t* a, const uint32_t* b) { mod_add<FpCfg>(r, a, b); }
 void emul_fp_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { mod_sub<FpCfg>(r, a, b); }
 void emul_fp_neg(uint32_t* r, const uint32_t* a) { mod_neg<FpCfg>(r, a); }

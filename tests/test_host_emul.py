@@ -302,3 +302,16 @@ def test_warp_cooperative_pairing(lib, py_setup):
     assert one.value == 0
     assert lib.emul_warp_pairing_check(aff_bytes(None), _g2_bytes(g2_0), aff_bytes(bls.g1_neg(A)), _g2_bytes(g2_1), ctypes.byref(one)) == 1
     assert one.value == 0
+
+
+def test_dedicated_squaring(lib):
+    """mont_sqr (symmetric product phase + injected reduction) == a*a/R for both fields."""
+    rnd = random.Random(99)
+    out = (ctypes.c_uint32 * 12)()
+    for a in EDGE_P + [rnd.randrange(P) for _ in range(400)]:
+        lib.emul_fp_sqr(out, u32(a, 12))
+        assert from_u32(out) == a * a * pow(RP, -1, P) % P, hex(a)
+    out8 = (ctypes.c_uint32 * 8)()
+    for a in EDGE_R + [rnd.randrange(R) for _ in range(400)]:
+        lib.emul_fr_sqr(out8, u32(a, 8))
+        assert from_u32(out8) == a * a * pow(RR, -1, R) % R, hex(a)
