@@ -188,6 +188,65 @@ LW_INL void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   for (int i = 0; i < N; i++) r[i] = borrow ? T[i] : t[i];
 }
 
+// Montgomery reduction of a 2N-limb product T (< m^2 ... < m 2^(32N)): r = T / 2^(32N) mod m.
+// Same even/odd aligned accumulators as mont_mul; one high limb of T is injected per round.
+template <class C>
+LW_INL void mont_redc_2n(uint32_t* r, const uint32_t* T) {
+  constexpr int N = C::N;
+  const uint32_t* m = C::mod();
+  uint32_t E[N], O[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) { E[k] = T[k]; O[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (i > 0) {
+      // R >>= 32: O becomes the new E; E shifted down one pair becomes the new O,
+      // with product limb N+i-1 entering at window position N-1
+      const uint32_t orphan = E[1];
+      uint32_t nO[N];
+#pragma unroll
+      for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
+      nO[N - 2] = T[N + i - 1];
+      nO[N - 1] = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) E[j] = O[j];
+#pragma unroll
+      for (int j = 0; j < N; j++) O[j] = nO[j];
+      E[0] = ptx::add_cc(E[0], orphan);  // carry flows into the O chain below (mul.lo leaves CC alone)
+    }
+    const uint32_t mi = ptx::mul_lo(E[0], C::INV);
+    if (i > 0) {
+      O[0] = ptx::madc_lo_cc(m[1], mi, O[0]);
+    } else {
+      O[0] = ptx::mad_lo_cc(m[1], mi, O[0]);
+    }
+    O[1] = ptx::madc_hi_cc(m[1], mi, O[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      O[j] = ptx::madc_lo_cc(m[j + 1], mi, O[j]);
+      O[j + 1] = ptx::madc_hi_cc(m[j + 1], mi, O[j + 1]);
+    }
+    E[0] = ptx::mad_lo_cc(m[0], mi, E[0]);  // == 0
+    E[1] = ptx::madc_hi_cc(m[0], mi, E[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      E[j] = ptx::madc_lo_cc(m[j], mi, E[j]);
+      E[j + 1] = ptx::madc_hi_cc(m[j], mi, E[j + 1]);
+    }
+    O[N - 1] = ptx::addc(O[N - 1], 0);
+  }
+  // result limb k = O[k] + E[k+1], plus the last product limb at position N-1
+  uint32_t Rr[N];
+  Rr[0] = ptx::add_cc(O[0], E[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) Rr[k] = ptx::addc_cc(O[k], E[k + 1]);
+  Rr[N - 1] = ptx::addc(O[N - 1], T[2 * N - 1]);
+  uint32_t t[N];
+  uint32_t borrow = limbs_sub<N>(t, Rr, m);
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = borrow ? Rr[i] : t[i];
+}
+
 // Montgomery square: r = a^2 / 2^(32N) mod m.
 //
 // Product phase with the symmetric half only: the off-diagonal products a_i a_j
@@ -253,58 +312,7 @@ LW_INL void mont_sqr(uint32_t* r, const uint32_t* a) {
     T[2 * i] = ptx::madc_lo_cc(a[i], a[i], T[2 * i]);
     T[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], T[2 * i + 1]);
   }
-  // ---- Montgomery reduction of T: running window R = E + O 2^32
-  uint32_t E[N], O[N];
-#pragma unroll
-  for (int k = 0; k < N; k++) { E[k] = T[k]; O[k] = 0; }
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-    if (i > 0) {
-      // R >>= 32: O becomes the new E; E shifted down one pair becomes the new O,
-      // with product limb N+i-1 entering at window position N-1
-      const uint32_t orphan = E[1];
-      uint32_t nO[N];
-#pragma unroll
-      for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
-      nO[N - 2] = T[N + i - 1];
-      nO[N - 1] = 0;
-#pragma unroll
-      for (int j = 0; j < N; j++) E[j] = O[j];
-#pragma unroll
-      for (int j = 0; j < N; j++) O[j] = nO[j];
-      E[0] = ptx::add_cc(E[0], orphan);  // carry flows into the O chain below (mul.lo leaves CC alone)
-    }
-    const uint32_t mi = ptx::mul_lo(E[0], C::INV);
-    if (i > 0) {
-      O[0] = ptx::madc_lo_cc(m[1], mi, O[0]);
-    } else {
-      O[0] = ptx::mad_lo_cc(m[1], mi, O[0]);
-    }
-    O[1] = ptx::madc_hi_cc(m[1], mi, O[1]);
-#pragma unroll
-    for (int j = 2; j < N; j += 2) {
-      O[j] = ptx::madc_lo_cc(m[j + 1], mi, O[j]);
-      O[j + 1] = ptx::madc_hi_cc(m[j + 1], mi, O[j + 1]);
-    }
-    E[0] = ptx::mad_lo_cc(m[0], mi, E[0]);  // == 0
-    E[1] = ptx::madc_hi_cc(m[0], mi, E[1]);
-#pragma unroll
-    for (int j = 2; j < N; j += 2) {
-      E[j] = ptx::madc_lo_cc(m[j], mi, E[j]);
-      E[j + 1] = ptx::madc_hi_cc(m[j], mi, E[j + 1]);
-    }
-    O[N - 1] = ptx::addc(O[N - 1], 0);
-  }
-  // result limb k = O[k] + E[k+1], plus the last product limb at position N-1
-  uint32_t Rr[N];
-  Rr[0] = ptx::add_cc(O[0], E[1]);
-#pragma unroll
-  for (int k = 1; k < N - 1; k++) Rr[k] = ptx::addc_cc(O[k], E[k + 1]);
-  Rr[N - 1] = ptx::addc(O[N - 1], T[2 * N - 1]);
-  uint32_t t[N];
-  uint32_t borrow = limbs_sub<N>(t, Rr, m);
-#pragma unroll
-  for (int i = 0; i < N; i++) r[i] = borrow ? Rr[i] : t[i];
+  mont_redc_2n<C>(r, T);
 }
 
 // Reduce an arbitrary N-limb integer (< 2^(32N)) into [0, m): at most

@@ -13,7 +13,8 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    EXP = os.path.join(os.path.dirname(HERE), "tools", "experiments")
+    deps = [SRC] + [os.path.join(d, f) for d in (CSRC, EXP) for f in os.listdir(d) if f.endswith(".cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

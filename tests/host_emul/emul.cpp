@@ -8,6 +8,8 @@
 // NOT a fallback: the shipped library has no host compute path.
 #include <cstring>
 #include "../../lambdaworks_kzg_b200/csrc/g1.cuh"
+#include "../../tools/experiments/fpdp.cuh"
+#include "../../tools/experiments/karatsuba.cuh"
 #include "../../lambdaworks_kzg_b200/csrc/sha256.cuh"
 #include "../../lambdaworks_kzg_b200/csrc/frpoly.cuh"
 #include "../../lambdaworks_kzg_b200/csrc/recode.cuh"
@@ -21,7 +23,11 @@ using namespace lw;
 extern "C" {
 
 void emul_fp_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul<FpCfg>(r, a, b); }
+void emul_fp_mul_k(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul_karatsuba<FpCfg>(r, a, b); }
+void emul_fr_mul_k(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul_karatsuba<FrCfg>(r, a, b); }
 void emul_fp_sqr(uint32_t* r, const uint32_t* a) { mont_sqr<FpCfg>(r, a); }
+void emul_fp_mul_dp(uint32_t* r, const uint32_t* a, const uint32_t* b) { dp::mont_mul(r, a, b); }
+void emul_fp_sqr_dp(uint32_t* r, const uint32_t* a) { dp::mont_sqr(r, a); }
 void emul_fr_sqr(uint32_t* r, const uint32_t* a) { mont_sqr<FrCfg>(r, a); }
 void emul_fp_add(uint32_t* r, const uint32_t* a, const uint32_t* b) { mod_add<FpCfg>(r, a, b); }
 void emul_fp_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { mod_sub<FpCfg>(r, a, b); }

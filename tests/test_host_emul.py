@@ -315,3 +315,39 @@ def test_dedicated_squaring(lib):
     for a in EDGE_R + [rnd.randrange(R) for _ in range(400)]:
         lib.emul_fr_sqr(out8, u32(a, 8))
         assert from_u32(out8) == a * a * pow(RR, -1, R) % R, hex(a)
+
+
+def test_karatsuba_multiplier(lib):
+    rnd = random.Random(101)
+    out = (ctypes.c_uint32 * 12)()
+    vals = EDGE_P + [(1 << 192) - 1, ((1 << 192) - 1) << 189 | ((1 << 189) - 1), P - (1 << 192)] + [rnd.randrange(P) for _ in range(400)]
+    vals = [v % P for v in vals]
+    for i, a in enumerate(vals):
+        b = vals[(i * 11 + 5) % len(vals)]
+        lib.emul_fp_mul_k(out, u32(a, 12), u32(b, 12))
+        assert from_u32(out) == a * b * pow(RP, -1, P) % P, (hex(a), hex(b))
+    out8 = (ctypes.c_uint32 * 8)()
+    rv = EDGE_R + [(1 << 128) - 1, R - (1 << 128)] + [rnd.randrange(R) for _ in range(300)]
+    for i, a in enumerate(rv):
+        b = rv[(i * 7 + 2) % len(rv)]
+        lib.emul_fr_mul_k(out8, u32(a, 8), u32(b, 8))
+        assert from_u32(out8) == a * b * pow(RR, -1, R) % R
+
+
+def test_fp64_pipe_multiplier(lib):
+    """csrc/fpdp.cuh (DFMA limb products, radix 2^48) == a b R^-1 mod p, same bits as the IMAD multiplier."""
+    rnd = random.Random(202)
+    out = (ctypes.c_uint32 * 12)()
+    ref = (ctypes.c_uint32 * 12)()
+    m48 = (1 << 48) - 1
+    special = [sum(m48 << (48 * i) for i in range(8)) % P, sum((1 << 47) << (48 * i) for i in range(8)) % P,
+               P - 1, P - 2, 1, 0, 2, (1 << 380), (1 << 381) - 1, m48, m48 << 48, P >> 1]
+    vals = [v % P for v in EDGE_P + special] + [rnd.randrange(P) for _ in range(1500)]
+    for i, a in enumerate(vals):
+        b = vals[(i * 13 + 7) % len(vals)]
+        lib.emul_fp_mul_dp(out, u32(a, 12), u32(b, 12))
+        assert from_u32(out) == a * b * pow(RP, -1, P) % P, (hex(a), hex(b))
+        lib.emul_fp_mul(ref, u32(a, 12), u32(b, 12))
+        assert list(out) == list(ref)
+        lib.emul_fp_sqr_dp(out, u32(a, 12))
+        assert from_u32(out) == a * a * pow(RP, -1, P) % P, hex(a)
