@@ -85,56 +85,68 @@ LW_INL G1Xyzz xyzz_dbl(const G1Xyzz& p) {
 }
 
 // acc += p   (p affine)
+// Single exit on purpose (also in xyzz_add below): these bodies end up inside out-of-line
+// functions, and ptxas 12.9 mis-allocates uniform registers around a divergent early
+// `return` (the struct-copy loop of one path reused the uniform register that held an
+// operand address of the other path -> illegal local reads; found with compute-sanitizer,
+// profiles/r01_sanitizer.md).  Structured if/else keeps the paths inside one
+// convergence region.
 LW_INL void xyzz_madd(G1Xyzz& acc, const G1Affine& p) {
-  if (g1a_is_inf(p)) return;
-  if (xyzz_is_inf(acc)) {
-    acc.x = p.x; acc.y = p.y; acc.zz = fp_one(); acc.zzz = fp_one();
-    return;
+  if (!g1a_is_inf(p)) {
+    if (xyzz_is_inf(acc)) {
+      acc.x = p.x; acc.y = p.y; acc.zz = fp_one(); acc.zzz = fp_one();
+    } else {
+      Fp U2 = fp_mul(p.x, acc.zz);
+      Fp S2 = fp_mul(p.y, acc.zzz);
+      Fp Pd = fp_sub(U2, acc.x);
+      Fp Rd = fp_sub(S2, acc.y);
+      if (fp_is_zero(Pd)) {
+        if (fp_is_zero(Rd)) acc = xyzz_dbl_affine(p);
+        else acc = xyzz_inf();
+      } else {
+        Fp PP = fp_sqr(Pd);
+        Fp PPP = fp_mul(Pd, PP);
+        Fp Q = fp_mul(acc.x, PP);
+        Fp X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
+        Fp Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(acc.y, PPP));
+        acc.zz = fp_mul(acc.zz, PP);
+        acc.zzz = fp_mul(acc.zzz, PPP);
+        acc.x = X3;
+        acc.y = Y3;
+      }
+    }
   }
-  Fp U2 = fp_mul(p.x, acc.zz);
-  Fp S2 = fp_mul(p.y, acc.zzz);
-  Fp Pd = fp_sub(U2, acc.x);
-  Fp Rd = fp_sub(S2, acc.y);
-  if (fp_is_zero(Pd)) {
-    if (fp_is_zero(Rd)) acc = xyzz_dbl_affine(p);
-    else acc = xyzz_inf();
-    return;
-  }
-  Fp PP = fp_sqr(Pd);
-  Fp PPP = fp_mul(Pd, PP);
-  Fp Q = fp_mul(acc.x, PP);
-  Fp X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
-  Fp Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(acc.y, PPP));
-  acc.zz = fp_mul(acc.zz, PP);
-  acc.zzz = fp_mul(acc.zzz, PPP);
-  acc.x = X3;
-  acc.y = Y3;
 }
 
 // a += b   (both XYZZ)
 LW_INL void xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
-  if (xyzz_is_inf(b)) return;
-  if (xyzz_is_inf(a)) { a = b; return; }
-  Fp U1 = fp_mul(a.x, b.zz);
-  Fp U2 = fp_mul(b.x, a.zz);
-  Fp S1 = fp_mul(a.y, b.zzz);
-  Fp S2 = fp_mul(b.y, a.zzz);
-  Fp Pd = fp_sub(U2, U1);
-  Fp Rd = fp_sub(S2, S1);
-  if (fp_is_zero(Pd)) {
-    if (fp_is_zero(Rd)) a = xyzz_dbl(a);
-    else a = xyzz_inf();
-    return;
+  if (!xyzz_is_inf(b)) {
+    if (xyzz_is_inf(a)) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) { a.x.l[i] = b.x.l[i]; a.y.l[i] = b.y.l[i]; a.zz.l[i] = b.zz.l[i]; a.zzz.l[i] = b.zzz.l[i]; }
+    } else {
+      Fp U1 = fp_mul(a.x, b.zz);
+      Fp U2 = fp_mul(b.x, a.zz);
+      Fp S1 = fp_mul(a.y, b.zzz);
+      Fp S2 = fp_mul(b.y, a.zzz);
+      Fp Pd = fp_sub(U2, U1);
+      Fp Rd = fp_sub(S2, S1);
+      if (fp_is_zero(Pd)) {
+        if (fp_is_zero(Rd)) a = xyzz_dbl(a);
+        else a = xyzz_inf();
+      } else {
+        Fp PP = fp_sqr(Pd);
+        Fp PPP = fp_mul(Pd, PP);
+        Fp Q = fp_mul(U1, PP);
+        Fp X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
+        Fp Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(S1, PPP));
+        a.zz = fp_mul(fp_mul(a.zz, b.zz), PP);
+        a.zzz = fp_mul(fp_mul(a.zzz, b.zzz), PPP);
+        a.x = X3;
+        a.y = Y3;
+      }
+    }
   }
-  Fp PP = fp_sqr(Pd);
-  Fp PPP = fp_mul(Pd, PP);
-  Fp Q = fp_mul(U1, PP);
-  Fp X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
-  Fp Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(S1, PPP));
-  a.zz = fp_mul(fp_mul(a.zz, b.zz), PP);
-  a.zzz = fp_mul(fp_mul(a.zzz, b.zzz), PPP);
-  a.x = X3;
-  a.y = Y3;
 }
 
 // Hot-loop variant of the mixed addition.  Identical arithmetic, but every field
@@ -145,28 +157,29 @@ LW_INL void xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
 // equal-x cases go through the out-of-line generic formulas.
 LW_COLD void xyzz_madd_rare(G1Xyzz& acc, const G1Affine& p) { xyzz_madd(acc, p); }
 LW_INL void xyzz_madd_hot(G1Xyzz& acc, const G1Affine& p) {
-  if (g1a_is_inf(p)) return;
-  if (xyzz_is_inf(acc)) {
-    acc.x = p.x; acc.y = p.y; acc.zz = fp_one(); acc.zzz = fp_one();
-    return;
+  if (!g1a_is_inf(p)) {
+    if (xyzz_is_inf(acc)) {
+      acc.x = p.x; acc.y = p.y; acc.zz = fp_one(); acc.zzz = fp_one();
+    } else {
+      Fp U2 = fp_mul_nv(p.x, acc.zz);
+      Fp S2 = fp_mul_nv(p.y, acc.zzz);
+      Fp Pd = fp_sub(U2, acc.x);
+      Fp Rd = fp_sub(S2, acc.y);
+      if (fp_is_zero(Pd)) {  // same x: doubling or cancellation
+        xyzz_madd_rare(acc, p);
+      } else {
+        Fp PP = fp_sqr_nv(Pd);
+        Fp PPP = fp_mul_nv(Pd, PP);
+        Fp Q = fp_mul_nv(acc.x, PP);
+        Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
+        Fp Y3 = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(acc.y, PPP));
+        acc.zz = fp_mul_nv(acc.zz, PP);
+        acc.zzz = fp_mul_nv(acc.zzz, PPP);
+        acc.x = X3;
+        acc.y = Y3;
+      }
+    }
   }
-  Fp U2 = fp_mul_nv(p.x, acc.zz);
-  Fp S2 = fp_mul_nv(p.y, acc.zzz);
-  Fp Pd = fp_sub(U2, acc.x);
-  Fp Rd = fp_sub(S2, acc.y);
-  if (fp_is_zero(Pd)) {  // same x: doubling or cancellation
-    xyzz_madd_rare(acc, p);
-    return;
-  }
-  Fp PP = fp_sqr_nv(Pd);
-  Fp PPP = fp_mul_nv(Pd, PP);
-  Fp Q = fp_mul_nv(acc.x, PP);
-  Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
-  Fp Y3 = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(acc.y, PPP));
-  acc.zz = fp_mul_nv(acc.zz, PP);
-  acc.zzz = fp_mul_nv(acc.zzz, PPP);
-  acc.x = X3;
-  acc.y = Y3;
 }
 
 // Out-of-line copies of the group law for cold callers (scalar-mul ladders,

@@ -44,12 +44,15 @@ struct Options {
   long window_bits = 13;
   long msm_blocks_per_blob = 0;
   long chunk_blobs = 512;
+  long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
+  long msm_ba_min_blobs = 64;
   long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode)
   Options() {
     if (const char* e = getenv("LWKZG_MODE")) mode = atol(e);
     if (const char* e = getenv("LWKZG_WINDOW_BITS")) window_bits = atol(e);
     if (const char* e = getenv("LWKZG_CHUNK_BLOBS")) chunk_blobs = atol(e);
     if (const char* e = getenv("LWKZG_MSM_BLOCKS_PER_BLOB")) msm_blocks_per_blob = atol(e);
+    if (const char* e = getenv("LWKZG_MSM_ALGO")) msm_algo = atol(e);
   }
 };
 Options& opts() {
@@ -83,6 +86,7 @@ constexpr int NSLOT = 2;
 struct Slot {
   cudaStream_t st = nullptr, aux = nullptr;
   cudaEvent_t ev_in = nullptr, ev_aux = nullptr, ev_done = nullptr, ev_fork = nullptr;
+  DevBuf ba_scratch;  // accumulators + prefix products of the batched-affine MSM kernel
   DevBuf blobs, q, partials, states, z, y, ybe, c48, cin48, p48, caff, status, status2, zbe;
 };
 
@@ -144,7 +148,7 @@ void destroy_ctx(Ctx* c) {
   for (auto& s : c->slot) {
     if (s.st) cudaStreamSynchronize(s.st);
     if (s.aux) cudaStreamSynchronize(s.aux);
-    for (DevBuf* b : {&s.blobs, &s.q, &s.partials, &s.states, &s.z, &s.y, &s.ybe, &s.c48, &s.cin48, &s.p48, &s.caff, &s.status, &s.status2, &s.zbe}) b->release();
+    for (DevBuf* b : {&s.ba_scratch, &s.blobs, &s.q, &s.partials, &s.states, &s.z, &s.y, &s.ybe, &s.c48, &s.cin48, &s.p48, &s.caff, &s.status, &s.status2, &s.zbe}) b->release();
     if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_aux) cudaEventDestroy(s.ev_aux);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -371,12 +375,34 @@ int auto_bpb(int n) {
   return std::min(b, 128);
 }
 
+// The fixed-base MSM of one chunk: batched-affine accumulation when the batch is large enough to
+// fill the GPU with one or two blocks per blob, XYZZ accumulation (window-split, many blocks per
+// blob) for latency-bound small calls.
+bool use_batch_affine(int n, int bpb) {
+  long algo, minb;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    algo = opts().msm_algo;
+    minb = opts().msm_ba_min_blobs;
+  }
+  return algo == 1 && n >= minb && msm_ba_supported(bpb);
+}
+void run_msm(Slot& s, const Ctx* c, const void* d_scalars, bool be_input, int n, int bpb, cudaStream_t st);
+
 bool slot_reserve(Slot& s, int n, int bpb, bool need_blobs) {
+  if (use_batch_affine(n, bpb) && !s.ba_scratch.ensure(msm_ba_scratch_bytes(n, bpb))) return false;
   if (need_blobs && !s.blobs.ensure((size_t)n * BLOB_BYTES)) return false;
   return s.q.ensure((size_t)n * BLOB_BYTES) && s.partials.ensure((size_t)n * bpb * XYZZ_BYTES) && s.states.ensure((size_t)n * 32) &&
          s.z.ensure((size_t)n * 32) && s.y.ensure((size_t)n * 32) && s.ybe.ensure((size_t)n * 32) && s.c48.ensure((size_t)n * 48) &&
          s.cin48.ensure((size_t)n * 48) && s.p48.ensure((size_t)n * 48) && s.caff.ensure((size_t)n * AFFINE_BYTES) &&
          s.status.ensure((size_t)n * sizeof(int)) && s.status2.ensure((size_t)n * sizeof(int)) && s.zbe.ensure((size_t)n * 32);
+}
+
+void run_msm(Slot& s, const Ctx* c, const void* d_scalars, bool be_input, int n, int bpb, cudaStream_t st) {
+  if (use_batch_affine(n, bpb) && s.ba_scratch.cap >= msm_ba_scratch_bytes(n, bpb))
+    launch_msm_gather_ba(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, bpb, s.ba_scratch.p, st);
+  else
+    launch_msm_gather(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, bpb, st);
 }
 
 // Enqueue one chunk on slot.st (+ slot.aux for the SHA midstate).  All pointers
@@ -395,7 +421,7 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
     CU_TRY(cudaMemsetAsync(stt, 0, (size_t)n * sizeof(int), st));
     launch_le_blob_check(stt, d_blobs, n, st);
     if (mode == Mode::Commit) {
-      launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, false, n, bpb, st);
+      run_msm(s, c, d_blobs, false, n, bpb, st);
       launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
       return true;
     }
@@ -407,7 +433,7 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
       CU_TRY(cudaEventRecord(s.ev_aux, s.aux));
     }
     if (mode == Mode::CommitProve) {
-      launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, false, n, bpb, st);
+      run_msm(s, c, d_blobs, false, n, bpb, st);
       launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
       commit_for_hash = d_c48;
     } else if (mode == Mode::BlobProof) {
@@ -424,12 +450,12 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
       launch_challenge_finish(s.z.p, s.states.p, d_blobs, commit_for_hash, n, st, true);
     }
     launch_le_eval_quot(s.q.p, nullptr, d_ybe, d_blobs, s.z.p, c->d_roots, n, st);
-    launch_msm_gather(s.partials.p, c->d_table, c->c, s.q.p, false, n, bpb, st);
+    run_msm(s, c, s.q.p, false, n, bpb, st);
     launch_msm_finalize(d_p48, nullptr, s.partials.p, bpb, n, st);
     return true;
   }
   if (mode == Mode::Commit) {
-    launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, true, n, bpb, st);
+    run_msm(s, c, d_blobs, true, n, bpb, st);
     launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
     if (d_status) CU_TRY(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int), st));
     return true;
@@ -443,7 +469,7 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
     CU_TRY(cudaEventRecord(s.ev_aux, s.aux));
   }
   if (mode == Mode::CommitProve) {
-    launch_msm_gather(s.partials.p, c->d_table, c->c, d_blobs, true, n, bpb, st);
+    run_msm(s, c, d_blobs, true, n, bpb, st);
     launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
     commit_for_hash = d_c48;
     if (d_status) CU_TRY(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int), st));
@@ -465,7 +491,7 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
     launch_challenge_finish(s.z.p, s.states.p, d_blobs, commit_for_hash, n, st);
   }
   launch_poly_eval_quot(s.q.p, nullptr, d_ybe, d_blobs, s.z.p, n, st);
-  launch_msm_gather(s.partials.p, c->d_table, c->c, s.q.p, false, n, bpb, st);
+  run_msm(s, c, s.q.p, false, n, bpb, st);
   launch_msm_finalize(d_p48, nullptr, s.partials.p, bpb, n, st);
   return true;
 }
@@ -702,7 +728,7 @@ C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, si
       CU_TRY(cudaMalloc(&d_aff, (size_t)N_POINTS * AFFINE_BYTES));
       CU_TRY(cudaMalloc(&d_canon, (size_t)N_POINTS * 96));
       launch_le_idft_rows(d_rows, sl.st);
-      launch_msm_gather(sl.partials.p, tmp->d_table, tmp->c, d_rows, false, N_POINTS, bpb, sl.st);
+      run_msm(sl, tmp, d_rows, false, N_POINTS, bpb, sl.st);
       launch_msm_finalize(nullptr, d_aff, sl.partials.p, bpb, N_POINTS, sl.st);
       launch_affine_to_canon(d_canon, d_aff, N_POINTS, sl.st);
       CU_TRY(cudaMemcpyAsync(lag.data(), d_canon, (size_t)N_POINTS * 96, cudaMemcpyDeviceToHost, sl.st));
@@ -837,6 +863,8 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "msm_blocks_per_blob") { if (value < 0 || value > 128 || (value > 32 && (value & (value - 1)))) return 1; opts().msm_blocks_per_blob = value; return 0; }
   if (n == "chunk_blobs") { if (value < 1) return 1; opts().chunk_blobs = value; return 0; }
   if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
+  if (n == "msm_algo") { if (value != 0 && value != 1) return 1; opts().msm_algo = value; return 0; }
+  if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
   return 1;
 }
 long lwkzg_get_option(const char* name) {
@@ -846,6 +874,8 @@ long lwkzg_get_option(const char* name) {
   if (n == "msm_blocks_per_blob") return opts().msm_blocks_per_blob;
   if (n == "chunk_blobs") return opts().chunk_blobs;
   if (n == "mode") return opts().mode;
+  if (n == "msm_algo") return opts().msm_algo;
+  if (n == "msm_ba_min_blobs") return opts().msm_ba_min_blobs;
   return -1;
 }
 
@@ -1127,9 +1157,9 @@ double lwkzg_bench_msm_kernel(const void* d_blobs, size_t n, int blocks_per_blob
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  launch_msm_gather(sl.partials.p, c->d_table, c->c, d_blobs, true, (int)n, bpb, sl.st);  // warm-up
+  run_msm(sl, c, d_blobs, true, (int)n, bpb, sl.st);  // warm-up
   cudaEventRecord(e0, sl.st);
-  for (int i = 0; i < iters; i++) launch_msm_gather(sl.partials.p, c->d_table, c->c, d_blobs, true, (int)n, bpb, sl.st);
+  for (int i = 0; i < iters; i++) run_msm(sl, c, d_blobs, true, (int)n, bpb, sl.st);
   cudaEventRecord(e1, sl.st);
   cudaEventSynchronize(e1);
   float ms = 0;

@@ -18,6 +18,7 @@
 // combine the per-thread sums.  The kernel is bound by the integer (IMAD)
 // pipe: ~10 Fp multiplications per gathered entry against 96 B of traffic.
 #include "g1.cuh"
+#include "fpinv.cuh"
 #include "kernels.h"
 #include "recode.cuh"
 
@@ -28,6 +29,9 @@ namespace lw {
 #endif
 #ifndef LWKZG_MSM_MIN_BLOCKS
 #define LWKZG_MSM_MIN_BLOCKS 3
+#endif
+#ifndef LWKZG_MSM_BA_K
+#define LWKZG_MSM_BA_K 16
 #endif
 constexpr int MSM_THREADS = LWKZG_MSM_THREADS;
 
@@ -144,6 +148,197 @@ msm_gather_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table
 
   block_reduce_xyzz<MSM_THREADS>(acc, red);
   if (tid == 0) partials[(size_t)blob * gridDim.x + blockIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// Batched-affine variant of the gather kernel (large batches).
+//
+// The XYZZ mixed addition above costs 8 M + 2 S on the integer-multiply pipe, and
+// that pipe is the bound (profiles/r01_ncu_msm_summary.md, r01_multiplier_experiments.md).
+// An AFFINE addition costs 2 M + 1 S plus one inversion of (x2 - x1); with
+// Montgomery's trick K independent additions share one inversion for 3 M each:
+// 5 M + 1 S per accumulated table entry.  Each thread therefore keeps K affine
+// accumulators (in an L2-resident scratch area, interleaved so that a warp's
+// 128-bit accesses are contiguous) and consumes its table entries K at a time:
+//   pass 1: d_k = T_k.x - A_k.x, exclusive prefix products (stored)
+//   one inversion of the total product (fpinv.cuh: binary GCD, mostly ALU work)
+//   pass 2 (k descending): 1/d_k from the running inverse and the stored prefix,
+//           A_k <- A_k + T_k
+// Rare cases (accumulator at infinity, equal x) are flagged per slot and never
+// enter the product.  At the end the K accumulators are folded into one XYZZ
+// sum and the block reduces as before, so partials / finalize are unchanged.
+LW_COLD Fp fp_inv_gcd_ni(Fp y) { return fp_inv_gcd(y); }
+LW_COLD G1Affine g1a_dbl_ni(G1Affine p) { return xyzz_to_affine(xyzz_dbl_affine(p)); }
+
+constexpr uint32_t BA_NONE = 0xffffffffu;
+
+__device__ __forceinline__ Fp load_fp_scratch(const uint4* p /* 3 words, stride MSM_THREADS */) {
+  uint4 v0 = __ldcg(p), v1 = __ldcg(p + MSM_THREADS), v2 = __ldcg(p + 2 * MSM_THREADS);
+  Fp e;
+  e.l[0] = v0.x; e.l[1] = v0.y; e.l[2] = v0.z; e.l[3] = v0.w;
+  e.l[4] = v1.x; e.l[5] = v1.y; e.l[6] = v1.z; e.l[7] = v1.w;
+  e.l[8] = v2.x; e.l[9] = v2.y; e.l[10] = v2.z; e.l[11] = v2.w;
+  return e;
+}
+__device__ __forceinline__ void store_fp_scratch(uint4* p, const Fp& e) {
+  __stcg(p, make_uint4(e.l[0], e.l[1], e.l[2], e.l[3]));
+  __stcg(p + MSM_THREADS, make_uint4(e.l[4], e.l[5], e.l[6], e.l[7]));
+  __stcg(p + 2 * MSM_THREADS, make_uint4(e.l[8], e.l[9], e.l[10], e.l[11]));
+}
+__device__ __forceinline__ Fp load_entry_x(const uint4* __restrict__ table, size_t idx) {
+  const uint4* p = table + idx * 6;
+  uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+  Fp e;
+  e.l[0] = v0.x; e.l[1] = v0.y; e.l[2] = v0.z; e.l[3] = v0.w;
+  e.l[4] = v1.x; e.l[5] = v1.y; e.l[6] = v1.z; e.l[7] = v1.w;
+  e.l[8] = v2.x; e.l[9] = v2.y; e.l[10] = v2.z; e.l[11] = v2.w;
+  return e;
+}
+
+template <bool BE, int K>
+__global__ void __launch_bounds__(MSM_THREADS, LWKZG_MSM_MIN_BLOCKS)
+msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
+                     uint4* __restrict__ scratch, int c, int pt_threads) {
+  __shared__ uint32_t sk[8][MSM_THREADS];
+  __shared__ uint32_t sidx[K][MSM_THREADS];   // entry index | sign << 31, or BA_NONE
+  __shared__ uint32_t red[48 * (MSM_THREADS / 2)];
+
+  const int W = 255 / c + 1;
+  const int tid = threadIdx.x;
+  const int blob = blockIdx.y;
+  const int pl = blockIdx.x * MSM_THREADS + tid;   // point lane, < pt_threads <= N_POINTS
+  const uint8_t* sc = scalars + (size_t)blob * BLOB_BYTES;
+  // slot k: words 0-2 = A.x, 3-5 = A.y, 6-8 = exclusive prefix product
+  uint4* my = scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (K * 9 * MSM_THREADS) + tid;
+
+  int pi = pl, j = W, carry = 0;        // j == W: the next scalar has to be fetched
+  size_t pbase = 0;
+  bool ended = pi >= N_POINTS;
+  uint32_t infmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);   // accumulators at infinity
+
+  while (!ended) {
+    // ------------------------------------------------------------ pass 1
+    Fp prod = fp_one();
+    uint32_t specmask = 0;   // slots with T.x == A.x
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+      // next non-zero digit of this thread's (point, window) stream
+      uint32_t e = BA_NONE;
+      while (!ended) {
+        if (j == W) {
+          const uint4* sp = reinterpret_cast<const uint4*>(sc + (size_t)pi * 32);
+          uint4 a = __ldg(sp), b = __ldg(sp + 1);
+          Fr kk;
+          if (BE) {
+            uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            kk = fr_canon_from_be_words(w);
+          } else {
+            kk.l[0] = a.x; kk.l[1] = a.y; kk.l[2] = a.z; kk.l[3] = a.w;
+            kk.l[4] = b.x; kk.l[5] = b.y; kk.l[6] = b.z; kk.l[7] = b.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) sk[i][tid] = kk.l[i];
+          j = 0; carry = 0;
+          pbase = (size_t)pi << (c - 1);
+        }
+        const int d = smem_digit(sk, tid, c, j, carry);
+        const size_t wbase = ((size_t)j * N_POINTS) << (c - 1);
+        j++;
+        if (j == W) { pi += pt_threads; if (pi >= N_POINTS) ended = true; }
+        if (d != 0) {
+          e = (uint32_t)(wbase + pbase + (size_t)((d < 0 ? -d : d) - 1)) | (d < 0 ? 0x80000000u : 0u);
+          break;
+        }
+      }
+      if (e != BA_NONE) {
+        const Fp tx = load_entry_x(table, e & 0x7fffffffu);
+        if (fp_is_zero(tx)) {
+          // (0, 0) encodes infinity in the table (hand-built setups); x == 0 with y != 0 is a curve point
+          const G1Affine t = load_entry(table, e & 0x7fffffffu);
+          if (fp_is_zero(t.y)) e = BA_NONE;
+        }
+        if (e != BA_NONE && !((infmask >> k) & 1u)) {
+          const Fp ax = load_fp_scratch(my + (k * 9) * MSM_THREADS);
+          const Fp d = fp_sub(tx, ax);
+          if (fp_is_zero(d)) {
+            specmask |= 1u << k;
+          } else {
+            store_fp_scratch(my + (k * 9 + 6) * MSM_THREADS, prod);
+            prod = fp_mul_nv(prod, d);
+          }
+        }
+      }
+      sidx[k][tid] = e;
+    }
+    // ------------------------------------------------------------ shared inversion
+    Fp inv = fp_inv_gcd_ni(prod);
+    // ------------------------------------------------------------ pass 2
+#pragma unroll 1
+    for (int k = K - 1; k >= 0; k--) {
+      const uint32_t e = sidx[k][tid];
+      if (e == BA_NONE) continue;
+      G1Affine t = load_entry(table, e & 0x7fffffffu);
+      t.y = fp_cneg(t.y, (e >> 31) != 0);
+      uint4* slot = my + (k * 9) * MSM_THREADS;
+      if ((infmask >> k) & 1u) {
+        store_fp_scratch(slot, t.x);
+        store_fp_scratch(slot + 3 * MSM_THREADS, t.y);
+        infmask &= ~(1u << k);
+        continue;
+      }
+      const Fp ax = load_fp_scratch(slot), ay = load_fp_scratch(slot + 3 * MSM_THREADS);
+      if ((specmask >> k) & 1u) {
+        if (fp_eq(t.y, ay)) {
+          const G1Affine dd = g1a_dbl_ni(t);
+          store_fp_scratch(slot, dd.x);
+          store_fp_scratch(slot + 3 * MSM_THREADS, dd.y);
+        } else {
+          infmask |= 1u << k;   // T == -A
+        }
+        continue;
+      }
+      const Fp ex = load_fp_scratch(slot + 6 * MSM_THREADS);
+      const Fp d = fp_sub(t.x, ax);
+      const Fp dinv = fp_mul_nv(inv, ex);
+      inv = fp_mul_nv(inv, d);
+      const Fp lam = fp_mul_nv(fp_sub(t.y, ay), dinv);
+      const Fp x3 = fp_sub(fp_sub(fp_sqr_nv(lam), ax), t.x);
+      const Fp y3 = fp_sub(fp_mul_nv(lam, fp_sub(ax, x3)), ay);
+      store_fp_scratch(slot, x3);
+      store_fp_scratch(slot + 3 * MSM_THREADS, y3);
+    }
+  }
+
+  // fold the K accumulators, then the block
+  G1Xyzz acc = xyzz_inf();
+#pragma unroll 1
+  for (int k = 0; k < K; k++) {
+    if ((infmask >> k) & 1u) continue;
+    G1Affine a;
+    a.x = load_fp_scratch(my + (k * 9) * MSM_THREADS);
+    a.y = load_fp_scratch(my + (k * 9 + 3) * MSM_THREADS);
+    xyzz_madd_hot(acc, a);
+  }
+  block_reduce_xyzz<MSM_THREADS>(acc, red);
+  if (tid == 0) partials[(size_t)blob * gridDim.x + blockIdx.x] = acc;
+}
+
+constexpr int BA_K = LWKZG_MSM_BA_K;
+size_t msm_ba_scratch_bytes(int n_blobs, int blocks_per_blob) {
+  return (size_t)n_blobs * blocks_per_blob * BA_K * 9 * MSM_THREADS * sizeof(uint4);
+}
+bool msm_ba_supported(int blocks_per_blob) { return blocks_per_blob * MSM_THREADS <= N_POINTS; }
+
+void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
+                          int blocks_per_blob, void* d_scratch, cudaStream_t st) {
+  if (n_blobs <= 0) return;
+  dim3 grid(blocks_per_blob, n_blobs);
+  const int pt = blocks_per_blob * MSM_THREADS;
+  if (be_input)
+    msm_gather_ba_kernel<true, BA_K><<<grid, MSM_THREADS, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, pt);
+  else
+    msm_gather_ba_kernel<false, BA_K><<<grid, MSM_THREADS, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, pt);
+  count_launch();
 }
 
 // Sum the per-block partials of one blob, normalise (one inversion), compress.

@@ -351,3 +351,19 @@ def test_fp64_pipe_multiplier(lib):
         assert list(out) == list(ref)
         lib.emul_fp_sqr_dp(out, u32(a, 12))
         assert from_u32(out) == a * a * pow(RP, -1, P) % P, hex(a)
+
+
+def test_gcd_inversion(lib):
+    """csrc/fpinv.cuh: approximate binary GCD inversion == Fermat inversion == pow(x, -1, p) (Montgomery in/out)."""
+    rnd = random.Random(303)
+    out = (ctypes.c_uint32 * 12)()
+    vals = [0, 1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 380, (1 << 381) - 1, (1 << 64) - 1, 1 << 32,
+            (1 << 62) - 1, 1 << 61, 1 << 62, 1 << 63, (1 << 381) - (1 << 190), RP % P, pow(RP, 2, P)]
+    vals += [rnd.randrange(1, P) for _ in range(3000)]
+    vals += [rnd.randrange(1, 1 << rnd.randrange(1, 381)) for _ in range(1500)]
+    vals += [P - rnd.randrange(1, 1 << rnd.randrange(1, 380)) for _ in range(1500)]
+    for a in vals:
+        a %= P
+        lib.emul_fp_inv_gcd(out, u32(a, 12))   # a is taken as the Montgomery representation of a / R
+        want = 0 if a == 0 else pow(a * pow(RP, -1, P) % P, -1, P) * RP % P
+        assert from_u32(out) == want, hex(a)
