@@ -48,6 +48,24 @@ def workload_name(n, wb):
             "tests/golden/trusted_setup.txt (monomial, tau=1337), fixed-base window %d bits" % (n, wb))
 
 
+def entries_per_point(lw, c, sample_blobs=2):
+    """Average number of non-zero signed base-2^c digits of the synthetic blob words (= table entries accumulated
+    per SRS point), counted on a small host-side sample with the kernel's own recoding rule (csrc/recode.cuh)."""
+    W = 255 // c + 1
+    nz = tot = 0
+    for k in range(sample_blobs):
+        blob = lw.synth_blob_host(k)
+        for i in range(0, len(blob), 32 * 16):  # every 16th word
+            v = int.from_bytes(blob[i:i + 32], "big")
+            carry = 0
+            for j in range(W):
+                d = ((v >> (c * j)) & ((1 << c) - 1)) + carry
+                carry = 1 if d > (1 << (c - 1)) else 0
+                nz += 1 if (d != 0 and d != (1 << c)) else 0
+            tot += 1
+    return nz / tot
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -225,21 +243,40 @@ def main():
         peak = max(lw.imad_peak(1), lw.imad_peak(0))
         achieved = n * MAC32_PER_MSM / (k_ms * 1e-3)
         nwin = 255 // wb + 1
-        alg_bytes = n * (BLOB_BYTES + 4096 * nwin * 96)  # scalars streamed once + one 96 B table entry per (point, window)
+        epp = entries_per_point(lw, wb)  # table entries really accumulated per point (non-zero signed digits)
+        alg_bytes = n * (BLOB_BYTES + 4096 * epp * 96)  # scalars streamed once + one 96 B table entry per non-zero digit
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        roofline = {"bound": "int32-imad", "kernel": "msm_gather_kernel<BE>", "achieved": achieved / 1e12, "peak": peak / 1e12,
+        # what the kernel really executes, in wide multiply-accumulates (Fp product 300, Fp square 234)
+        M, S = 300.0, 234.0
+        batch_affine = lw.get_option("msm_algo") == 1 and n >= lw.get_option("msm_ba_min_blobs")
+        if batch_affine:
+            T, K = lw.get_option("msm_ba_threads"), lw.get_option("msm_ba_slots")
+            per_thread = 4096 * epp / T
+            rounds = -(-per_thread // K)
+            executed = n * (4096 * epp * (5 * M + S)            # affine addition with shared inversion
+                            + T * (K - 1) * (8 * M + 2 * S)     # folding the K accumulators of a thread (XYZZ)
+                            + T * rounds * (20 * 120 + M)       # binary-GCD inversions: ~20 rounds x 120 wide MACs
+                            + (T - 1) * 14 * M)                 # block tree
+            kernel = "msm_gather_ba_kernel<BE, K=%d, threads=%d> (batched-affine accumulation)" % (K, T)
+        else:
+            executed = n * 4096 * epp * (8 * M + 2 * S)
+            kernel = "msm_gather_kernel<BE> (XYZZ accumulation)"
+        roofline = {"bound": "int32-imad", "kernel": kernel, "achieved": achieved / 1e12, "peak": peak / 1e12,
                     "unit": "TMAC32/s", "frac": achieved / peak,
                     "peak_source": "lwkzg_imad_peak(): memory-free IMAD.WIDE probe with distinct operand registers, run in this process "
                                    "(burst; best of carry-chain and carry-less variants; see profiles/r01_pipe_probe.md)",
+                    "note": "achieved = SURVEY 8(d)'s ALGORITHMIC work (2.80e8 MAC32 per MSM-4096: bucket method, c = 13, XYZZ) / kernel time; "
+                            "the kernel needs fewer multiplications than that model (full digit table, batched-affine additions), so frac may "
+                            "exceed 1 -- frac_executed is the pipe-utilisation figure",
                     "alg_mac32_per_launch": n * MAC32_PER_MSM, "kernel_ms": k_ms,
-                    # what the kernel really executes: one 10-multiplication mixed addition per (point, window), 300 MAC32 each
-                    "executed_mac32_per_launch": n * 4096 * nwin * 10 * 300.0,
-                    "frac_executed": n * 4096 * nwin * 10 * 300.0 / (k_ms * 1e-3) / peak,
+                    "executed_mac32_per_launch": executed,
+                    "frac_executed": executed / (k_ms * 1e-3) / peak,
+                    "table_entries_per_point": epp,
                     "kernel_share_of_step": 2 * k_ms / ms_per_step,
                     # second half of BASELINE's metric: G1 MSM points/s (fixed-base MSM over the 4096-point SRS, this kernel)
                     "g1_msm_points_per_s": n * 4096 / (k_ms * 1e-3),

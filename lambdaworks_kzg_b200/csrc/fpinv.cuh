@@ -50,8 +50,9 @@ LW_INL void mul_word(uint32_t* X, const uint32_t* a, uint32_t w) {
 }
 
 // r = |a f + b g| / 2^30 (the division is exact), returns all-ones when a f + b g < 0.
-// 0 <= a, b < 2^382; |f|, |g| <= 2^30.
-LW_INL uint32_t lincomb_shr(uint32_t* r, const uint32_t* a, uint32_t f, const uint32_t* b, uint32_t g) {
+// 0 <= a, b < 2^382; |f|, |g| <= 2^30.  Out of line (called twice per round): the inversion runs
+// concurrently with other warps' multiplication code and must not evict it from the instruction cache.
+LW_INL uint32_t lincomb_shr_inl(uint32_t* r, const uint32_t* a, uint32_t f, const uint32_t* b, uint32_t g) {
   const uint32_t mf = (uint32_t)((int32_t)f >> 31), mg = (uint32_t)((int32_t)g >> 31);
   const uint32_t af = (f ^ mf) - mf, ag = (g ^ mg) - mg;
   uint32_t X[13], Y[13];
@@ -78,7 +79,7 @@ LW_INL uint32_t lincomb_shr(uint32_t* r, const uint32_t* a, uint32_t f, const ui
 }
 
 // r = (u f + v g) / 2^32 mod p, in [0, p).  0 <= u, v <= p; |f|, |g| <= 2^30.
-LW_INL void cofactor_update(uint32_t* r, const uint32_t* u, uint32_t f, const uint32_t* v, uint32_t g) {
+LW_INL void cofactor_update_inl(uint32_t* r, const uint32_t* u, uint32_t f, const uint32_t* v, uint32_t g) {
   const uint32_t mf = (uint32_t)((int32_t)f >> 31), mg = (uint32_t)((int32_t)g >> 31);
   const uint32_t af = (f ^ mf) - mf, ag = (g ^ mg) - mg;
   const uint32_t* mod = k::FP_MOD;
@@ -107,15 +108,30 @@ LW_INL void cofactor_update(uint32_t* r, const uint32_t* u, uint32_t f, const ui
   for (int i = 0; i < 12; i++) r[i] = borrow ? X[i + 1] : t[i];
 }
 
+// by-value wrappers: operands and results travel in registers (pointer arguments would force the
+// caller's arrays into local memory)
+struct FpSigned { Fp v; uint32_t neg; };
+LW_COLD FpSigned lincomb_shr(Fp a, uint32_t f, Fp b, uint32_t g) {
+  FpSigned r;
+  r.neg = lincomb_shr_inl(r.v.l, a.l, f, b.l, g);
+  return r;
+}
+LW_COLD Fp cofactor_update(Fp u, uint32_t f, Fp v, uint32_t g) {
+  Fp r;
+  cofactor_update_inl(r.l, u.l, f, v.l, g);
+  return r;
+}
+
 }  // namespace gcdinv
 
 // Montgomery form in, Montgomery form out; 0 -> 0.
 LW_INL Fp fp_inv_gcd(const Fp& y) {
   using namespace gcdinv;
-  uint32_t a[12], b[12], u[12], v[12];
+  Fp A = y, B, U = fp_zero(), V = fp_zero();
 #pragma unroll
-  for (int i = 0; i < 12; i++) { a[i] = y.l[i]; b[i] = k::FP_MOD[i]; u[i] = 0; v[i] = 0; }
-  u[0] = 1;
+  for (int i = 0; i < 12; i++) B.l[i] = k::FP_MOD[i];
+  U.l[0] = 1;
+  uint32_t *a = A.l, *b = B.l;
   int rounds = 0;
 #pragma unroll 1
   for (; rounds < MAX_ROUNDS; rounds++) {
@@ -141,7 +157,7 @@ LW_INL Fp fp_inv_gcd(const Fp& y) {
     uint64_t bbar = exact ? (((uint64_t)b[1] << 32) | b[0]) : (((uint64_t)tb << 30) | (b[0] & 0x3fffffffu));
     // ---- 30 divsteps on the approximations
     uint32_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
-#pragma unroll 6
+#pragma unroll 2
     for (int j = 0; j < STEPS; j++) {
       const uint64_t odd = 0ull - (abar & 1ull);
       const uint64_t sw = odd & (abar < bbar ? ~0ull : 0ull);
@@ -158,21 +174,20 @@ LW_INL Fp fp_inv_gcd(const Fp& y) {
       g1 <<= 1;
     }
     // ---- apply the transition matrix
-    uint32_t na[12], nb[12], nu[12], nv[12];
-    const uint32_t sa = lincomb_shr(na, a, f0, b, g0);
-    const uint32_t sb = lincomb_shr(nb, a, f1, b, g1);
+    const FpSigned na = lincomb_shr(A, f0, B, g0);
+    const FpSigned nb = lincomb_shr(A, f1, B, g1);
+    const uint32_t sa = na.neg, sb = nb.neg;
     f0 = (f0 ^ sa) - sa; g0 = (g0 ^ sa) - sa;  // a < 0: (a, f0, g0) <- (-a, -f0, -g0)
     f1 = (f1 ^ sb) - sb; g1 = (g1 ^ sb) - sb;
-    cofactor_update(nu, u, f0, v, g0);
-    cofactor_update(nv, u, f1, v, g1);
-#pragma unroll
-    for (int i = 0; i < 12; i++) { a[i] = na[i]; b[i] = nb[i]; u[i] = nu[i]; v[i] = nv[i]; }
+    const Fp nu = cofactor_update(U, f0, V, g0);
+    const Fp nv = cofactor_update(U, f1, V, g1);
+    A = na.v; B = nb.v; U = nu; V = nv;
   }
   // y^-1 = 4^rounds v as integers; Montgomery form of the inverse = y^-1 R^2 = mont_mul(v, 4^rounds R^3)
-  Fp vv, kk;
+  Fp kk;
 #pragma unroll
-  for (int i = 0; i < 12; i++) { vv.l[i] = v[i]; kk.l[i] = k::FP_GCDINV_SCALE[rounds][i]; }
-  return fp_mul(vv, kk);
+  for (int i = 0; i < 12; i++) kk.l[i] = k::FP_GCDINV_SCALE[rounds][i];
+  return fp_mul_nv(V, kk);
 }
 
 }  // namespace lw

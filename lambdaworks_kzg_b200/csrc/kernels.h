@@ -32,11 +32,14 @@ void launch_table_fill(void* d_table, const void* d_bases, int c, int nwin, int 
 // partials: n * blocks_per_blob XYZZ accumulators.
 void launch_msm_gather(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input,
                        int n_blobs, int blocks_per_blob, cudaStream_t st);
-// batched-affine variant for large batches (same partials); needs blocks_per_blob * threads <= 4096 and a scratch area
+// batched-affine variant for large batches: one block per blob, one XYZZ partial per blob, plus a scratch area
+// for the per-thread affine accumulators
 void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input,
-                          int n_blobs, int blocks_per_blob, void* d_scratch, cudaStream_t st);
-size_t msm_ba_scratch_bytes(int n_blobs, int blocks_per_blob);
-bool msm_ba_supported(int blocks_per_blob);
+                          int n_blobs, void* d_scratch, cudaStream_t st);
+size_t msm_ba_scratch_bytes(int n_blobs);
+int msm_ba_threads();
+int msm_ba_slots();
+void msm_ba_set_variant(int v);   // tuning: index into BA_VARIANTS (accumulators per thread x threads per blob), msm.cu
 // sum partials, normalise, compress.  d_aff_out (may be NULL): Montgomery affine.
 void launch_msm_finalize(void* d_out48, void* d_aff_out, const void* d_partials, int parts_per_blob, int n_blobs, cudaStream_t st);
 int msm_threads_per_block();

@@ -45,7 +45,7 @@ struct Options {
   long msm_blocks_per_blob = 0;
   long chunk_blobs = 512;
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
-  long msm_ba_min_blobs = 64;
+  long msm_ba_min_blobs = 512;
   long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode)
   Options() {
     if (const char* e = getenv("LWKZG_MODE")) mode = atol(e);
@@ -362,7 +362,16 @@ Ctx* ctx_of(const KZGSettings* s) {
 // ------------------------------------------------------------------ pipeline
 enum class Mode { Commit, CommitProve, BlobProof, PointProof };
 
+// The fixed-base MSM of one chunk: batched-affine accumulation (one block per blob) when the batch is
+// large enough to fill the GPU that way, XYZZ accumulation (window-split, many blocks per blob) for
+// latency-bound small calls.
+bool use_batch_affine(int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return opts().msm_algo == 1 && n >= opts().msm_ba_min_blobs;
+}
+
 int auto_bpb(int n) {
+  if (use_batch_affine(n)) return 1;
   long o;
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -375,22 +384,10 @@ int auto_bpb(int n) {
   return std::min(b, 128);
 }
 
-// The fixed-base MSM of one chunk: batched-affine accumulation when the batch is large enough to
-// fill the GPU with one or two blocks per blob, XYZZ accumulation (window-split, many blocks per
-// blob) for latency-bound small calls.
-bool use_batch_affine(int n, int bpb) {
-  long algo, minb;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    algo = opts().msm_algo;
-    minb = opts().msm_ba_min_blobs;
-  }
-  return algo == 1 && n >= minb && msm_ba_supported(bpb);
-}
 void run_msm(Slot& s, const Ctx* c, const void* d_scalars, bool be_input, int n, int bpb, cudaStream_t st);
 
 bool slot_reserve(Slot& s, int n, int bpb, bool need_blobs) {
-  if (use_batch_affine(n, bpb) && !s.ba_scratch.ensure(msm_ba_scratch_bytes(n, bpb))) return false;
+  if (use_batch_affine(n) && !s.ba_scratch.ensure(msm_ba_scratch_bytes(n))) return false;
   if (need_blobs && !s.blobs.ensure((size_t)n * BLOB_BYTES)) return false;
   return s.q.ensure((size_t)n * BLOB_BYTES) && s.partials.ensure((size_t)n * bpb * XYZZ_BYTES) && s.states.ensure((size_t)n * 32) &&
          s.z.ensure((size_t)n * 32) && s.y.ensure((size_t)n * 32) && s.ybe.ensure((size_t)n * 32) && s.c48.ensure((size_t)n * 48) &&
@@ -399,8 +396,8 @@ bool slot_reserve(Slot& s, int n, int bpb, bool need_blobs) {
 }
 
 void run_msm(Slot& s, const Ctx* c, const void* d_scalars, bool be_input, int n, int bpb, cudaStream_t st) {
-  if (use_batch_affine(n, bpb) && s.ba_scratch.cap >= msm_ba_scratch_bytes(n, bpb))
-    launch_msm_gather_ba(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, bpb, s.ba_scratch.p, st);
+  if (bpb == 1 && use_batch_affine(n) && s.ba_scratch.cap >= msm_ba_scratch_bytes(n))
+    launch_msm_gather_ba(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, s.ba_scratch.p, st);
   else
     launch_msm_gather(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, bpb, st);
 }
@@ -865,6 +862,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
   if (n == "msm_algo") { if (value != 0 && value != 1) return 1; opts().msm_algo = value; return 0; }
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
+  if (n == "msm_ba_variant") { if (value < 0 || value > 5) return 1; msm_ba_set_variant((int)value); return 0; }
   return 1;
 }
 long lwkzg_get_option(const char* name) {
@@ -876,6 +874,8 @@ long lwkzg_get_option(const char* name) {
   if (n == "mode") return opts().mode;
   if (n == "msm_algo") return opts().msm_algo;
   if (n == "msm_ba_min_blobs") return opts().msm_ba_min_blobs;
+  if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel
+  if (n == "msm_ba_slots") return msm_ba_slots();       // read-only: affine accumulators per thread
   return -1;
 }
 

@@ -93,6 +93,18 @@ __device__ __forceinline__ int smem_digit(const uint32_t (*sk)[MSM_THREADS], int
   return d;
 }
 
+template <int TH>
+__device__ __forceinline__ int smem_digit_t(const uint32_t (*sk)[TH], int tid, int c, int j, int& carry) {
+  const int bit = j * c;
+  const int w = bit >> 5, s = bit & 31;
+  const uint32_t lo = sk[w][tid];
+  const uint32_t hi = (w + 1 < 8) ? sk[w + 1][tid] : 0u;
+  uint32_t raw = __funnelshift_r(lo, hi, s) & ((1u << c) - 1u);
+  int d = (int)raw + carry;
+  if (d > (1 << (c - 1))) { d -= (1 << c); carry = 1; } else { carry = 0; }
+  return d;
+}
+
 template <bool BE>
 __global__ void __launch_bounds__(MSM_THREADS, LWKZG_MSM_MIN_BLOCKS)
 msm_gather_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
@@ -172,18 +184,20 @@ LW_COLD G1Affine g1a_dbl_ni(G1Affine p) { return xyzz_to_affine(xyzz_dbl_affine(
 
 constexpr uint32_t BA_NONE = 0xffffffffu;
 
-__device__ __forceinline__ Fp load_fp_scratch(const uint4* p /* 3 words, stride MSM_THREADS */) {
-  uint4 v0 = __ldcg(p), v1 = __ldcg(p + MSM_THREADS), v2 = __ldcg(p + 2 * MSM_THREADS);
+template <int TH>
+__device__ __forceinline__ Fp load_fp_scratch(const uint4* p /* 3 words, stride TH */) {
+  uint4 v0 = __ldcg(p), v1 = __ldcg(p + TH), v2 = __ldcg(p + 2 * TH);
   Fp e;
   e.l[0] = v0.x; e.l[1] = v0.y; e.l[2] = v0.z; e.l[3] = v0.w;
   e.l[4] = v1.x; e.l[5] = v1.y; e.l[6] = v1.z; e.l[7] = v1.w;
   e.l[8] = v2.x; e.l[9] = v2.y; e.l[10] = v2.z; e.l[11] = v2.w;
   return e;
 }
+template <int TH>
 __device__ __forceinline__ void store_fp_scratch(uint4* p, const Fp& e) {
   __stcg(p, make_uint4(e.l[0], e.l[1], e.l[2], e.l[3]));
-  __stcg(p + MSM_THREADS, make_uint4(e.l[4], e.l[5], e.l[6], e.l[7]));
-  __stcg(p + 2 * MSM_THREADS, make_uint4(e.l[8], e.l[9], e.l[10], e.l[11]));
+  __stcg(p + TH, make_uint4(e.l[4], e.l[5], e.l[6], e.l[7]));
+  __stcg(p + 2 * TH, make_uint4(e.l[8], e.l[9], e.l[10], e.l[11]));
 }
 __device__ __forceinline__ Fp load_entry_x(const uint4* __restrict__ table, size_t idx) {
   const uint4* p = table + idx * 6;
@@ -195,34 +209,49 @@ __device__ __forceinline__ Fp load_entry_x(const uint4* __restrict__ table, size
   return e;
 }
 
-template <bool BE, int K>
-__global__ void __launch_bounds__(MSM_THREADS, LWKZG_MSM_MIN_BLOCKS)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_entry_l2(const uint4* table, size_t idx) {
+  const uint4* p = table + idx * 6;
+  prefetch_l2(p);
+  prefetch_l2(p + 4);
+}
+template <int TH>
+__device__ __forceinline__ void prefetch_fp_scratch(const uint4* p) {
+  prefetch_l2(p); prefetch_l2(p + TH); prefetch_l2(p + 2 * TH);
+}
+template <int TH>
+__device__ __forceinline__ void prefetch_slot_l2(const uint4* p) {
+#pragma unroll
+  for (int w = 0; w < 9; w++) prefetch_l2(p + w * TH);
+}
+
+template <bool BE, int K, int MINB, int TH>
+__global__ void __launch_bounds__(TH, MINB)
 msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
                      uint4* __restrict__ scratch, int c, int pt_threads) {
-  __shared__ uint32_t sk[8][MSM_THREADS];
-  __shared__ uint32_t sidx[K][MSM_THREADS];   // entry index | sign << 31, or BA_NONE
-  __shared__ uint32_t red[48 * (MSM_THREADS / 2)];
+  __shared__ uint32_t sk[8][TH];
+  __shared__ uint32_t sidx[K][TH];   // entry index | sign << 31, or BA_NONE
+  __shared__ uint32_t red[48 * (TH / 2)];
 
   const int W = 255 / c + 1;
   const int tid = threadIdx.x;
   const int blob = blockIdx.y;
-  const int pl = blockIdx.x * MSM_THREADS + tid;   // point lane, < pt_threads <= N_POINTS
+  const int pl = blockIdx.x * TH + tid;   // point lane, < pt_threads <= N_POINTS
   const uint8_t* sc = scalars + (size_t)blob * BLOB_BYTES;
   // slot k: words 0-2 = A.x, 3-5 = A.y, 6-8 = exclusive prefix product
-  uint4* my = scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (K * 9 * MSM_THREADS) + tid;
+  uint4* my = scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (K * 9 * TH) + tid;
 
   int pi = pl, j = W, carry = 0;        // j == W: the next scalar has to be fetched
   size_t pbase = 0;
   bool ended = pi >= N_POINTS;
-  uint32_t infmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);   // accumulators at infinity
+  uint64_t infmask = K >= 64 ? ~0ull : ((1ull << K) - 1ull);   // accumulators at infinity
 
   while (!ended) {
-    // ------------------------------------------------------------ pass 1
-    Fp prod = fp_one();
-    uint32_t specmask = 0;   // slots with T.x == A.x
+    // ------------------------------------------------------------ pass 1a: the next K non-zero digits
+    // of this thread's (point, window) stream -> entry indices; their table lines and the accumulator
+    // rows are requested into L2 so that pass 1b finds them there
 #pragma unroll 1
     for (int k = 0; k < K; k++) {
-      // next non-zero digit of this thread's (point, window) stream
       uint32_t e = BA_NONE;
       while (!ended) {
         if (j == W) {
@@ -241,7 +270,7 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
           j = 0; carry = 0;
           pbase = (size_t)pi << (c - 1);
         }
-        const int d = smem_digit(sk, tid, c, j, carry);
+        const int d = smem_digit_t<TH>(sk, tid, c, j, carry);
         const size_t wbase = ((size_t)j * N_POINTS) << (c - 1);
         j++;
         if (j == W) { pi += pt_threads; if (pi >= N_POINTS) ended = true; }
@@ -250,62 +279,91 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
           break;
         }
       }
+      sidx[k][tid] = e;
       if (e != BA_NONE) {
-        const Fp tx = load_entry_x(table, e & 0x7fffffffu);
-        if (fp_is_zero(tx)) {
-          // (0, 0) encodes infinity in the table (hand-built setups); x == 0 with y != 0 is a curve point
-          const G1Affine t = load_entry(table, e & 0x7fffffffu);
-          if (fp_is_zero(t.y)) e = BA_NONE;
-        }
-        if (e != BA_NONE && !((infmask >> k) & 1u)) {
-          const Fp ax = load_fp_scratch(my + (k * 9) * MSM_THREADS);
-          const Fp d = fp_sub(tx, ax);
-          if (fp_is_zero(d)) {
-            specmask |= 1u << k;
-          } else {
-            store_fp_scratch(my + (k * 9 + 6) * MSM_THREADS, prod);
-            prod = fp_mul_nv(prod, d);
-          }
+        prefetch_l2(table + (size_t)(e & 0x7fffffffu) * 6);
+        if (!((infmask >> k) & 1ull)) prefetch_fp_scratch<TH>(my + (k * 9) * TH);
+      }
+    }
+    // ------------------------------------------------------------ pass 1b: differences and prefix products
+    Fp prod = fp_one();
+    uint64_t specmask = 0;   // slots with T.x == A.x
+    uint32_t e_next = sidx[0][tid];
+    Fp tx_next = fp_zero(), ax_next = fp_zero();
+    if (e_next != BA_NONE) {
+      tx_next = load_entry_x(table, e_next & 0x7fffffffu);
+      if (!(infmask & 1ull)) ax_next = load_fp_scratch<TH>(my);
+    }
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+      uint32_t e = e_next;
+      const Fp tx = tx_next, ax = ax_next;
+      if (k + 1 < K) {   // operands of the next slot are in flight while this one multiplies
+        e_next = sidx[k + 1][tid];
+        if (e_next != BA_NONE) {
+          tx_next = load_entry_x(table, e_next & 0x7fffffffu);
+          if (!((infmask >> (k + 1)) & 1ull)) ax_next = load_fp_scratch<TH>(my + ((k + 1) * 9) * TH);
         }
       }
-      sidx[k][tid] = e;
+      if (e == BA_NONE) continue;
+      if (fp_is_zero(tx)) {
+        // (0, 0) encodes infinity in the table (hand-built setups); x == 0 with y != 0 is a curve point
+        const G1Affine t = load_entry(table, e & 0x7fffffffu);
+        if (fp_is_zero(t.y)) { sidx[k][tid] = BA_NONE; continue; }
+      }
+      if ((infmask >> k) & 1ull) continue;
+      const Fp d = fp_sub(tx, ax);
+      if (fp_is_zero(d)) {
+        specmask |= 1ull << k;
+      } else {
+        store_fp_scratch<TH>(my + (k * 9 + 6) * TH, prod);
+        prod = fp_mul_nv(prod, d);
+      }
     }
     // ------------------------------------------------------------ shared inversion
     Fp inv = fp_inv_gcd_ni(prod);
     // ------------------------------------------------------------ pass 2
+    for (int k = K - 1; k >= K - 2 && k >= 0; k--) {
+      const uint32_t e = sidx[k][tid];
+      if (e != BA_NONE) { prefetch_entry_l2(table, e & 0x7fffffffu); prefetch_slot_l2<TH>(my + (k * 9) * TH); }
+    }
 #pragma unroll 1
     for (int k = K - 1; k >= 0; k--) {
+      if (k >= 2) {
+        const uint32_t e2 = sidx[k - 2][tid];
+        if (e2 != BA_NONE) { prefetch_entry_l2(table, e2 & 0x7fffffffu); prefetch_slot_l2<TH>(my + ((k - 2) * 9) * TH); }
+      }
       const uint32_t e = sidx[k][tid];
       if (e == BA_NONE) continue;
       G1Affine t = load_entry(table, e & 0x7fffffffu);
       t.y = fp_cneg(t.y, (e >> 31) != 0);
-      uint4* slot = my + (k * 9) * MSM_THREADS;
-      if ((infmask >> k) & 1u) {
-        store_fp_scratch(slot, t.x);
-        store_fp_scratch(slot + 3 * MSM_THREADS, t.y);
-        infmask &= ~(1u << k);
+      uint4* slot = my + (k * 9) * TH;
+      if ((infmask >> k) & 1ull) {
+        store_fp_scratch<TH>(slot, t.x);
+        store_fp_scratch<TH>(slot + 3 * TH, t.y);
+        infmask &= ~(1ull << k);
         continue;
       }
-      const Fp ax = load_fp_scratch(slot), ay = load_fp_scratch(slot + 3 * MSM_THREADS);
-      if ((specmask >> k) & 1u) {
+      const Fp ax = load_fp_scratch<TH>(slot), ay = load_fp_scratch<TH>(slot + 3 * TH);
+      if ((specmask >> k) & 1ull) {
         if (fp_eq(t.y, ay)) {
           const G1Affine dd = g1a_dbl_ni(t);
-          store_fp_scratch(slot, dd.x);
-          store_fp_scratch(slot + 3 * MSM_THREADS, dd.y);
+          store_fp_scratch<TH>(slot, dd.x);
+          store_fp_scratch<TH>(slot + 3 * TH, dd.y);
         } else {
-          infmask |= 1u << k;   // T == -A
+          infmask |= 1ull << k;   // T == -A
         }
         continue;
       }
-      const Fp ex = load_fp_scratch(slot + 6 * MSM_THREADS);
+      const Fp ex = load_fp_scratch<TH>(slot + 6 * TH);
       const Fp d = fp_sub(t.x, ax);
       const Fp dinv = fp_mul_nv(inv, ex);
       inv = fp_mul_nv(inv, d);
       const Fp lam = fp_mul_nv(fp_sub(t.y, ay), dinv);
       const Fp x3 = fp_sub(fp_sub(fp_sqr_nv(lam), ax), t.x);
       const Fp y3 = fp_sub(fp_mul_nv(lam, fp_sub(ax, x3)), ay);
-      store_fp_scratch(slot, x3);
-      store_fp_scratch(slot + 3 * MSM_THREADS, y3);
+      store_fp_scratch<TH>(slot, x3);
+      store_fp_scratch<TH>(slot + 3 * TH, y3);
     }
   }
 
@@ -313,31 +371,49 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
   G1Xyzz acc = xyzz_inf();
 #pragma unroll 1
   for (int k = 0; k < K; k++) {
-    if ((infmask >> k) & 1u) continue;
+    if ((infmask >> k) & 1ull) continue;
     G1Affine a;
-    a.x = load_fp_scratch(my + (k * 9) * MSM_THREADS);
-    a.y = load_fp_scratch(my + (k * 9 + 3) * MSM_THREADS);
+    a.x = load_fp_scratch<TH>(my + (k * 9) * TH);
+    a.y = load_fp_scratch<TH>(my + (k * 9 + 3) * TH);
     xyzz_madd_hot(acc, a);
   }
-  block_reduce_xyzz<MSM_THREADS>(acc, red);
+  block_reduce_xyzz<TH>(acc, red);
   if (tid == 0) partials[(size_t)blob * gridDim.x + blockIdx.x] = acc;
 }
 
-constexpr int BA_K = LWKZG_MSM_BA_K;
-size_t msm_ba_scratch_bytes(int n_blobs, int blocks_per_blob) {
-  return (size_t)n_blobs * blocks_per_blob * BA_K * 9 * MSM_THREADS * sizeof(uint4);
+// variant = accumulators per thread (K), threads per blob (= block size) and register budget
+struct BaVariant { int k, threads; };
+static const BaVariant BA_VARIANTS[] = {{64, 128}, {32, 128}, {64, 64}, {32, 64}, {64, 32}, {16, 128}};
+static int g_ba_variant = 0;
+void msm_ba_set_variant(int v) { if (v >= 0 && v < (int)(sizeof(BA_VARIANTS) / sizeof(BA_VARIANTS[0]))) g_ba_variant = v; }
+int msm_ba_threads() { return BA_VARIANTS[g_ba_variant].threads; }
+int msm_ba_slots() { return BA_VARIANTS[g_ba_variant].k; }
+size_t msm_ba_scratch_bytes(int n_blobs) {   // sized for the largest variant: 64 slots x 9 words x 128 threads
+  return (size_t)n_blobs * 64 * 9 * 128 * sizeof(uint4);
 }
-bool msm_ba_supported(int blocks_per_blob) { return blocks_per_blob * MSM_THREADS <= N_POINTS; }
 
-void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
-                          int blocks_per_blob, void* d_scratch, cudaStream_t st) {
-  if (n_blobs <= 0) return;
-  dim3 grid(blocks_per_blob, n_blobs);
-  const int pt = blocks_per_blob * MSM_THREADS;
+template <int K, int MINB, int TH>
+static void launch_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
+                      void* d_scratch, cudaStream_t st) {
+  dim3 grid(1, n_blobs);
   if (be_input)
-    msm_gather_ba_kernel<true, BA_K><<<grid, MSM_THREADS, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, pt);
+    msm_gather_ba_kernel<true, K, MINB, TH><<<grid, TH, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, TH);
   else
-    msm_gather_ba_kernel<false, BA_K><<<grid, MSM_THREADS, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, pt);
+    msm_gather_ba_kernel<false, K, MINB, TH><<<grid, TH, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, TH);
+}
+
+// one block per blob; partials: one XYZZ per blob
+void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
+                          void* d_scratch, cudaStream_t st) {
+  if (n_blobs <= 0) return;
+  switch (g_ba_variant) {
+    case 1: launch_ba<32, 3, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    case 2: launch_ba<64, 6, 64>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    case 3: launch_ba<32, 6, 64>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    case 4: launch_ba<64, 12, 32>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    case 5: launch_ba<16, 3, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    default: launch_ba<64, 3, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+  }
   count_launch();
 }
 

@@ -383,6 +383,105 @@ def test_hand_built_settings(lw, settings8, py_setup):
     assert e.value.code == lw.C_KZG_ERROR
 
 
+# ------------------------------------------------------------------ batched-affine MSM kernel (large-batch path)
+@pytest.fixture
+def force_batch_affine(lw):
+    """Route even tiny batches through msm_gather_ba_kernel (normally used from 512 blobs up)."""
+    old = lw.get_option("msm_ba_min_blobs")
+    lw.set_option("msm_algo", 1)
+    lw.set_option("msm_ba_min_blobs", 1)
+    yield
+    lw.set_option("msm_ba_min_blobs", old)
+    lw.set_option("msm_ba_variant", 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_batch_affine_edge_blobs_vs_oracle(lw, ref, settings8, force_batch_affine, variant):
+    lw.set_option("msm_ba_variant", variant)
+    blobs = edge_blobs()
+    names = list(blobs)
+    coms, proofs, st = lw.commit_and_prove_batch(b"".join(blobs[n] for n in names), len(names), settings8)
+    assert st == [0] * len(names)
+    for n, c, p in zip(names, coms, proofs):
+        want_c = ref.blob_to_kzg_commitment(blobs[n])
+        assert c == want_c, n
+        assert p == ref.compute_blob_kzg_proof(blobs[n], want_c), n
+
+
+def test_batch_affine_synthetic_vs_oracle(lw, ref, settings13, force_batch_affine):
+    n = 12
+    blobs = [lw.synth_blob_host(k) for k in range(n)]
+    coms, proofs, st = lw.commit_and_prove_batch(b"".join(blobs), n, settings13)
+    assert st == [0] * n
+    for k in range(n):
+        c = ref.blob_to_kzg_commitment(blobs[k])
+        assert coms[k] == c, k
+        assert proofs[k] == ref.compute_blob_kzg_proof(blobs[k], c), k
+
+
+def test_batch_affine_repeated_srs_points(lw, py_setup, force_batch_affine):
+    """Equal table entries meet in one accumulator slot (T == A: doubling; T == -A: cancellation): a hand-built
+    SRS whose 4096 points are all the same point, blobs with few distinct words."""
+    from lambdaworks_kzg_b200.api import CKZGSettings
+
+    lw.set_option("window_bits", 8)
+    tmp = lw.load_trusted_setup_file(os.path.join(GOLDEN, "trusted_setup.txt"))
+    raw = bytearray(tmp.g1_values_bytes())
+    g2raw = tmp.g2_values_bytes()
+    tmp.free()
+    for i in range(4096):
+        if i != 1:
+            raw[144 * i: 144 * i + 144] = raw[144:288]      # every point = g1[1]
+    g1 = ctypes.create_string_buffer(bytes(raw), 4096 * 144)
+    g2 = ctypes.create_string_buffer(g2raw, 65 * 288)
+    s = CKZGSettings(None, ctypes.cast(g1, ctypes.c_void_p), ctypes.cast(g2, ctypes.c_void_p))
+    rnd = random.Random(77)
+    w = [rnd.randrange(R) for _ in range(3)]
+    cases = [
+        [w[0]] * 4096,
+        [w[0], R - w[0]] * 2048,                               # sums to zero: commitment = infinity
+        [w[rnd.randrange(3)] for _ in range(4096)],
+        [1] * 4096,
+        [(1 << 7)] * 4096,                                     # digit 2^(c-1) in the lowest window
+        [w[0]] * 64 + [0] * 4032,
+    ]
+    blobs = [blob_from_coeffs(c) for c in cases]
+    coms, st = lw.blob_to_kzg_commitment_batch(b"".join(blobs), len(blobs), s)
+    assert st == [0] * len(blobs)
+    P1 = py_setup.g1[1]
+    for c, got in zip(cases, coms):
+        want = bls.g1_compress(bls.g1_mul(P1, sum(c) % R) if sum(c) % R else None)
+        assert got == want
+    lw.set_option("msm_algo", 0)
+    coms0, _ = lw.blob_to_kzg_commitment_batch(b"".join(blobs), len(blobs), s)
+    lw.set_option("msm_algo", 1)
+    assert coms0 == coms
+
+
+def test_large_batch_with_degenerate_blobs_both_kernels(lw, ref, settings13):
+    """512 blobs, a handful of them degenerate: both MSM kernels, identical bytes, oracle on the odd ones.  (This
+    shape crashed msm_finalize_kernel before the single-exit rewrite of the group law -- profiles/r01_sanitizer.md.)"""
+    n = 512
+    blobs = [lw.synth_blob_host(k) for k in range(n)]
+    special = {1: bytes(kzg.BYTES_PER_BLOB), 2: blob_from_coeffs([123456789] * 4096), 3: blob_from_coeffs([0] * 4095 + [1]),
+               4: blob_from_coeffs([R - 1] * 4096), 5: blob_from_coeffs([1] * 4096), 6: blob_from_coeffs([R + 5] * 4096), 300: blob_from_coeffs([7])}
+    for k, b in special.items():
+        blobs[k] = b
+    cat = b"".join(blobs)
+    out = {}
+    for algo in (0, 1):
+        lw.set_option("msm_algo", algo)
+        coms, proofs, st = lw.commit_and_prove_batch(cat, n, settings13)
+        assert st == [0] * n
+        out[algo] = (coms, proofs)
+    lw.set_option("msm_algo", 1)
+    assert out[0] == out[1]
+    for k in list(special) + [0, 511]:
+        c = ref.blob_to_kzg_commitment(blobs[k])
+        assert out[1][0][k] == c, k
+        assert out[1][1][k] == ref.compute_blob_kzg_proof(blobs[k], c), k
+
+
 # ------------------------------------------------------------------ device API + full-size properties
 def test_device_api_and_large_batch_properties(lw, settings13, ref):
     import torch

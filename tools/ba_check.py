@@ -29,23 +29,40 @@ if os.environ.get("DEGEN", "1") == "1":
     v[5][:] = torch.tensor(list((1).to_bytes(32, "big")), dtype=torch.uint8, device=dev)
     v[6][:] = torch.tensor(list((R + 5).to_bytes(32, "big")), dtype=torch.uint8, device=dev)
 res = {}
-for algo in [int(x) for x in os.environ.get("ALGOS", "0,1").split(",")]:
-    lw.set_option("msm_algo", algo)
+def run_cp(tag):
     coms = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
     proofs = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+    best = 1e9
     for it in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         lw.commit_and_prove_batch_device(coms.data_ptr(), proofs.data_ptr(), blobs.data_ptr(), n, s, st, 0)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        print("algo=%d commit+prove n=%d: %.2f ms -> %.1f blobs/s" % (algo, n, ms, n / ms * 1e3), flush=True)
-    res[algo] = (coms.cpu(), proofs.cpu())
-    for nb in sorted({min(512, n), n}):
-        for bpb in (1, 2, 4):
-            ms = lw.bench_msm_kernel(blobs.data_ptr(), nb, s, bpb, 3)
-            print("algo=%d msm kernel n=%d bpb=%d: %.3f ms -> %.1f MSM/s" % (algo, nb, bpb, ms, nb / ms * 1e3), flush=True)
+        best = min(best, e0.elapsed_time(e1))
+    print("%s commit+prove n=%d: %.2f ms -> %.1f blobs/s" % (tag, n, best, n / best * 1e3), flush=True)
+    return coms.cpu(), proofs.cpu()
+
+for algo in [int(x) for x in os.environ.get("ALGOS", "0,1").split(",")]:
+    lw.set_option("msm_algo", algo)
+    if algo == 0:
+        res[0] = run_cp("algo=0")
+        for nb in sorted({min(512, n), n}):
+            ms = lw.bench_msm_kernel(blobs.data_ptr(), nb, s, 2, 3)
+            print("algo=0 msm kernel n=%d bpb=2: %.3f ms -> %.1f MSM/s" % (nb, ms, nb / ms * 1e3), flush=True)
+        continue
+    for variant in [int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4,5").split(",")]:
+        lw.set_option("msm_ba_variant", variant)
+        for nb in sorted({min(512, n), min(1024, n), n}):
+            ms = lw.bench_msm_kernel(blobs.data_ptr(), nb, s, 0, 3)
+            print("algo=1 variant=%d msm kernel n=%d: %.3f ms -> %.1f MSM/s" % (variant, nb, ms, nb / ms * 1e3), flush=True)
+        for chunk in (512, 1024):
+            lw.set_option("chunk_blobs", chunk)
+            r = run_cp("algo=1 variant=%d chunk=%d" % (variant, chunk))
+            if 1 in res and not (torch.equal(r[0], res[1][0]) and torch.equal(r[1], res[1][1])):
+                print("VARIANT MISMATCH", variant, chunk); sys.exit(1)
+            res[1] = r
+        lw.set_option("chunk_blobs", 512)
 if len(res) < 2:
     sys.exit(0)
 same_c = torch.equal(res[0][0], res[1][0]); same_p = torch.equal(res[0][1], res[1][1])
