@@ -225,16 +225,6 @@ __device__ __forceinline__ void prefetch_slot_l2(const uint4* p) {
   for (int w = 0; w < 9; w++) prefetch_l2(p + w * TH);
 }
 
-__device__ __forceinline__ Fp load_entry_y(const uint4* __restrict__ table, size_t idx) {
-  const uint4* p = table + idx * 6 + 3;
-  uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-  Fp e;
-  e.l[0] = v0.x; e.l[1] = v0.y; e.l[2] = v0.z; e.l[3] = v0.w;
-  e.l[4] = v1.x; e.l[5] = v1.y; e.l[6] = v1.z; e.l[7] = v1.w;
-  e.l[8] = v2.x; e.l[9] = v2.y; e.l[10] = v2.z; e.l[11] = v2.w;
-  return e;
-}
-
 template <bool BE, int K, int MINB, int TH>
 __global__ void __launch_bounds__(TH, MINB)
 msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
@@ -292,35 +282,27 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
       sidx[k][tid] = e;
       if (e != BA_NONE) {
         prefetch_l2(table + (size_t)(e & 0x7fffffffu) * 6);
-        prefetch_l2(table + (size_t)(e & 0x7fffffffu) * 6 + 2);   // x spans two 64-byte granules for odd entries
         if (!((infmask >> k) & 1ull)) prefetch_fp_scratch<TH>(my + (k * 9) * TH);
       }
     }
     // ------------------------------------------------------------ pass 1b: differences and prefix products
     Fp prod = fp_one();
     uint64_t specmask = 0;   // slots with T.x == A.x
-    // operands of the next two slots are in flight while the current one multiplies
-    uint32_t e1 = sidx[0][tid], e2 = K > 1 ? sidx[1][tid] : BA_NONE;
-    Fp tx1 = fp_zero(), ax1 = fp_zero(), tx2 = fp_zero(), ax2 = fp_zero();
-    if (e1 != BA_NONE) {
-      tx1 = load_entry_x(table, e1 & 0x7fffffffu);
-      if (!(infmask & 1ull)) ax1 = load_fp_scratch<TH>(my);
-    }
-    if (e2 != BA_NONE) {
-      tx2 = load_entry_x(table, e2 & 0x7fffffffu);
-      if (!((infmask >> 1) & 1ull)) ax2 = load_fp_scratch<TH>(my + 9 * TH);
+    uint32_t e_next = sidx[0][tid];
+    Fp tx_next = fp_zero(), ax_next = fp_zero();
+    if (e_next != BA_NONE) {
+      tx_next = load_entry_x(table, e_next & 0x7fffffffu);
+      if (!(infmask & 1ull)) ax_next = load_fp_scratch<TH>(my);
     }
 #pragma unroll 1
     for (int k = 0; k < K; k++) {
-      const uint32_t e = e1;
-      const Fp tx = tx1, ax = ax1;
-      e1 = e2; tx1 = tx2; ax1 = ax2;
-      e2 = BA_NONE;
-      if (k + 2 < K) {
-        e2 = sidx[k + 2][tid];
-        if (e2 != BA_NONE) {
-          tx2 = load_entry_x(table, e2 & 0x7fffffffu);
-          if (!((infmask >> (k + 2)) & 1ull)) ax2 = load_fp_scratch<TH>(my + ((k + 2) * 9) * TH);
+      uint32_t e = e_next;
+      const Fp tx = tx_next, ax = ax_next;
+      if (k + 1 < K) {   // operands of the next slot are in flight while this one multiplies
+        e_next = sidx[k + 1][tid];
+        if (e_next != BA_NONE) {
+          tx_next = load_entry_x(table, e_next & 0x7fffffffu);
+          if (!((infmask >> (k + 1)) & 1ull)) ax_next = load_fp_scratch<TH>(my + ((k + 1) * 9) * TH);
         }
       }
       if (e == BA_NONE) continue;
@@ -341,76 +323,46 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
     // ------------------------------------------------------------ shared inversion
     Fp inv = fp_inv_gcd_ni(prod);
     // ------------------------------------------------------------ pass 2
-    for (int k = K - 1; k >= K - 3 && k >= 0; k--) {
+    for (int k = K - 1; k >= K - 2 && k >= 0; k--) {
       const uint32_t e = sidx[k][tid];
       if (e != BA_NONE) { prefetch_entry_l2(table, e & 0x7fffffffu); prefetch_slot_l2<TH>(my + (k * 9) * TH); }
     }
-    // software pipeline: (T.x, A.x, prefix) of the next slot are loaded while the current slot finishes
-    uint32_t en = sidx[K - 1][tid];
-    Fp txn = fp_zero(), axn = fp_zero(), exn = fp_zero();
-    if (en != BA_NONE) {
-      txn = load_entry_x(table, en & 0x7fffffffu);
-      axn = load_fp_scratch<TH>(my + ((K - 1) * 9) * TH);
-      exn = load_fp_scratch<TH>(my + ((K - 1) * 9 + 6) * TH);
-    }
 #pragma unroll 1
     for (int k = K - 1; k >= 0; k--) {
-      if (k >= 3) {
-        const uint32_t e3 = sidx[k - 3][tid];
-        if (e3 != BA_NONE) { prefetch_entry_l2(table, e3 & 0x7fffffffu); prefetch_slot_l2<TH>(my + ((k - 3) * 9) * TH); }
+      if (k >= 2) {
+        const uint32_t e2 = sidx[k - 2][tid];
+        if (e2 != BA_NONE) { prefetch_entry_l2(table, e2 & 0x7fffffffu); prefetch_slot_l2<TH>(my + ((k - 2) * 9) * TH); }
       }
-      const uint32_t e = en;
-      const Fp tx = txn, ax = axn, ex = exn;
-      const uint32_t e_nx = k > 0 ? sidx[k - 1][tid] : BA_NONE;
+      const uint32_t e = sidx[k][tid];
+      if (e == BA_NONE) continue;
+      G1Affine t = load_entry(table, e & 0x7fffffffu);
+      t.y = fp_cneg(t.y, (e >> 31) != 0);
       uint4* slot = my + (k * 9) * TH;
-      const size_t idx = e & 0x7fffffffu;
-      const bool neg = (e >> 31) != 0;
-      const bool rare = e == BA_NONE || (((infmask | specmask) >> k) & 1ull);
-      if (rare) {
-        // no entry, empty accumulator (first round, or after a cancellation) or equal x
-        if (e != BA_NONE) {
-          G1Affine t = load_entry(table, idx);
-          t.y = fp_cneg(t.y, neg);
-          if ((infmask >> k) & 1ull) {
-            store_fp_scratch<TH>(slot, t.x);
-            store_fp_scratch<TH>(slot + 3 * TH, t.y);
-            infmask &= ~(1ull << k);
-          } else {
-            const Fp ay = load_fp_scratch<TH>(slot + 3 * TH);
-            if (fp_eq(t.y, ay)) {
-              const G1Affine dd = g1a_dbl_ni(t);
-              store_fp_scratch<TH>(slot, dd.x);
-              store_fp_scratch<TH>(slot + 3 * TH, dd.y);
-            } else {
-              infmask |= 1ull << k;   // T == -A
-            }
-          }
-        }
-        en = e_nx;
-        if (en != BA_NONE) {
-          txn = load_entry_x(table, en & 0x7fffffffu);
-          axn = load_fp_scratch<TH>(my + ((k - 1) * 9) * TH);
-          exn = load_fp_scratch<TH>(my + ((k - 1) * 9 + 6) * TH);
+      if ((infmask >> k) & 1ull) {
+        store_fp_scratch<TH>(slot, t.x);
+        store_fp_scratch<TH>(slot + 3 * TH, t.y);
+        infmask &= ~(1ull << k);
+        continue;
+      }
+      const Fp ax = load_fp_scratch<TH>(slot), ay = load_fp_scratch<TH>(slot + 3 * TH);
+      if ((specmask >> k) & 1ull) {
+        if (fp_eq(t.y, ay)) {
+          const G1Affine dd = g1a_dbl_ni(t);
+          store_fp_scratch<TH>(slot, dd.x);
+          store_fp_scratch<TH>(slot + 3 * TH, dd.y);
+        } else {
+          infmask |= 1ull << k;   // T == -A
         }
         continue;
       }
+      const Fp ex = load_fp_scratch<TH>(slot + 6 * TH);
+      const Fp d = fp_sub(t.x, ax);
       const Fp dinv = fp_mul_nv(inv, ex);
-      // the y coordinates travel while the running inverse is updated
-      const Fp ay = load_fp_scratch<TH>(slot + 3 * TH);
-      const Fp ty = fp_cneg(load_entry_y(table, idx), neg);
-      asm volatile("" ::: "memory");
-      inv = fp_mul_nv(inv, fp_sub(tx, ax));
-      const Fp lam = fp_mul_nv(fp_sub(ty, ay), dinv);
-      const Fp x3 = fp_sub(fp_sub(fp_sqr_nv(lam), ax), tx);
-      store_fp_scratch<TH>(slot, x3);
-      en = e_nx;
-      if (en != BA_NONE) {
-        txn = load_entry_x(table, en & 0x7fffffffu);
-        axn = load_fp_scratch<TH>(my + ((k - 1) * 9) * TH);
-        exn = load_fp_scratch<TH>(my + ((k - 1) * 9 + 6) * TH);
-      }
-      asm volatile("" ::: "memory");
+      inv = fp_mul_nv(inv, d);
+      const Fp lam = fp_mul_nv(fp_sub(t.y, ay), dinv);
+      const Fp x3 = fp_sub(fp_sub(fp_sqr_nv(lam), ax), t.x);
       const Fp y3 = fp_sub(fp_mul_nv(lam, fp_sub(ax, x3)), ay);
+      store_fp_scratch<TH>(slot, x3);
       store_fp_scratch<TH>(slot + 3 * TH, y3);
     }
   }
@@ -431,7 +383,7 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
 
 // variant = accumulators per thread (K), threads per blob (= block size) and register budget
 struct BaVariant { int k, threads; };
-static const BaVariant BA_VARIANTS[] = {{64, 128}, {32, 128}, {64, 64}, {32, 64}, {64, 32}, {16, 128}, {64, 128}, {32, 128}};
+static const BaVariant BA_VARIANTS[] = {{64, 128}, {32, 128}, {64, 64}, {32, 64}, {64, 32}, {16, 128}};
 static int g_ba_variant = 0;
 void msm_ba_set_variant(int v) { if (v >= 0 && v < (int)(sizeof(BA_VARIANTS) / sizeof(BA_VARIANTS[0]))) g_ba_variant = v; }
 int msm_ba_threads() { return BA_VARIANTS[g_ba_variant].threads; }
@@ -460,8 +412,6 @@ void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const vo
     case 3: launch_ba<32, 6, 64>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
     case 4: launch_ba<64, 12, 32>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
     case 5: launch_ba<16, 3, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
-    case 6: launch_ba<64, 4, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
-    case 7: launch_ba<32, 4, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
     default: launch_ba<64, 3, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
   }
   count_launch();
