@@ -43,9 +43,9 @@ void set_err(const std::string& s) { tl_err = s; }
 struct Options {
   long window_bits = 13;
   long msm_blocks_per_blob = 0;
-  long chunk_blobs = 512;
+  long chunk_blobs = 256;
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
-  long msm_ba_min_blobs = 512;
+  long msm_ba_min_blobs = 256;
   long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode)
   Options() {
     if (const char* e = getenv("LWKZG_MODE")) mode = atol(e);
@@ -53,6 +53,7 @@ struct Options {
     if (const char* e = getenv("LWKZG_CHUNK_BLOBS")) chunk_blobs = atol(e);
     if (const char* e = getenv("LWKZG_MSM_BLOCKS_PER_BLOB")) msm_blocks_per_blob = atol(e);
     if (const char* e = getenv("LWKZG_MSM_ALGO")) msm_algo = atol(e);
+    if (const char* e = getenv("LWKZG_MSM_BA_MIN_BLOBS")) msm_ba_min_blobs = atol(e);
   }
 };
 Options& opts() {
@@ -81,7 +82,7 @@ struct DevBuf {
 };
 
 constexpr uint64_t CTX_MAGIC = 0x4c574b5a47423230ull;  // "LWKZGB20"
-constexpr int NSLOT = 2;
+constexpr int NSLOT = 4;
 
 struct Slot {
   cudaStream_t st = nullptr, aux = nullptr;

@@ -32,6 +32,14 @@ __device__ __noinline__ Fp2x mul_pair_k(Fp a1, Fp b1, Fp a2, Fp b2) {
   return r;
 }
 
+// two independent integer-pipe products in one instruction stream (ILP 2 for a lone warp)
+__device__ __noinline__ Fp2x mul_pair_ii(Fp a1, Fp b1, Fp a2, Fp b2) {
+  Fp2x r;
+  mont_mul<FpCfg>(r.a.l, a1.l, b1.l);
+  mont_mul<FpCfg>(r.b.l, a2.l, b2.l);
+  return r;
+}
+
 // MODE 0 imad, 1 karatsuba, 2 dp, 3 warp-mix (odd warps dp), 4 fused pair, 5 fused pair (karatsuba), 6 sqr imad, 7 sqr dp
 // 8: warp-mix with 1 of 4 .. generalised: warp w uses dp if (w % MIXDEN) < MIXNUM
 template <int MODE, int MINB, int MIXNUM = 1, int MIXDEN = 2>
@@ -54,6 +62,7 @@ __global__ void __launch_bounds__(128, MINB) kmul(uint32_t* out, uint32_t seed) 
     }
     if (MODE == 4) { Fp2x r = mul_pair(x, y, u, v); x = r.a; u = r.b; r = mul_pair(y, x, v, u); y = r.a; v = r.b; }
     if (MODE == 5) { Fp2x r = mul_pair_k(x, y, u, v); x = r.a; u = r.b; r = mul_pair_k(y, x, v, u); y = r.a; v = r.b; }
+    if (MODE == 8) { Fp2x r = mul_pair_ii(x, y, u, v); x = r.a; u = r.b; r = mul_pair_ii(y, x, v, u); y = r.a; v = r.b; }
     if (MODE == 6) { x = sqr_i(x); y = sqr_i(y); u = sqr_i(u); v = sqr_i(v); }
     if (MODE == 7) { x = sqr_d(x); y = sqr_d(y); u = sqr_d(u); v = sqr_d(v); }
   }
@@ -76,9 +85,10 @@ __global__ void kcheck(uint32_t* bad, uint32_t seed) {
   if (nb) atomicAdd(bad, nb);
 }
 
+static int g_blocks = 148 * 12;
 template <int MODE, int MINB, int MIXNUM = 1, int MIXDEN = 2>
 void run(const char* name) {
-  uint32_t* o; int blocks = 148 * 12;
+  uint32_t* o; int blocks = g_blocks;
   cudaMalloc(&o, blocks * 128 * 4);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   kmul<MODE, MINB, MIXNUM, MIXDEN><<<blocks, 128>>>(o, 7); cudaDeviceSynchronize();
@@ -114,5 +124,12 @@ int main(int argc, char** argv) {
   { if (g_only < 0 || g_only == g_idx) run<5, 3>("fused pair karatsuba+dfma (minb 3)"); g_idx++; }
   { if (g_only < 0 || g_only == g_idx) run<6, 3>("sqr imad (minb 3)"); g_idx++; }
   { if (g_only < 0 || g_only == g_idx) run<7, 3>("sqr dfma (minb 3)"); g_idx++; }
+  // few warps per scheduler: can a lone warp keep the multiplier pipe busy?
+  for (int per_sm = 1; per_sm <= 3; per_sm++) {
+    g_blocks = 148 * per_sm;
+    printf("-- %d block(s) of 4 warps per SM\n", per_sm);
+    { if (g_only < 0 || g_only == g_idx) run<0, 3>("imad, one product per call"); g_idx++; }
+    { if (g_only < 0 || g_only == g_idx) run<8, 2>("imad, two products per call (ILP 2)"); g_idx++; }
+  }
   printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
 }

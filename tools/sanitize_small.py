@@ -15,6 +15,14 @@ for mode in (0, 1):
         blobs = [b"".join(b[i:i + 32][::-1] for i in range(0, len(b), 32)) for b in blobs]
     coms, proofs, st = lw.commit_and_prove_batch(b"".join(blobs), n, s)
     assert st == [0] * n
+    # the same batch through the batched-affine MSM kernel (normally used from 256 blobs up), plus degenerate blobs
+    lw.set_option("msm_ba_min_blobs", 1)
+    for variant in (0, 3):
+        lw.set_option("msm_ba_variant", variant)
+        coms2, proofs2, st2 = lw.commit_and_prove_batch(b"".join(blobs) + bytes(131072) + (bytes(31) + b"\x01") * 4096, n + 2, s)
+        assert st2 == [0] * (n + 2) and coms2[:n] == coms and proofs2[:n] == proofs
+    lw.set_option("msm_ba_variant", 0)
+    lw.set_option("msm_ba_min_blobs", 256)
     assert lw.verify_blob_kzg_proof_batch(blobs, coms, proofs, s) is True
     assert lw.verify_blob_kzg_proof(blobs[0], coms[0], proofs[0], s) is True
     z = bytes(31) + b"\x07" if mode == 0 else b"\x07" + bytes(31)
