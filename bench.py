@@ -137,6 +137,15 @@ def main():
     ap.add_argument("--blobs", type=int, default=BLOBS_PER_GPU)
     ap.add_argument("--window-bits", type=int, default=15, help="fixed-base window c (15 -> 108 GiB table; shrinks automatically if HBM is short)")
     args = ap.parse_args()
+    # Exactly ONE line on stdout (the JSON): native libraries (NCCL's version banner, CUDA warnings) write to fd 1
+    # behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,7 +162,7 @@ def main():
                 "config": {"workload": workload_name(n, args.window_bits) + "; CPU arm: bounded sample per step, see cpu_baseline.sample"},
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -165,7 +174,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
@@ -297,7 +305,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * BLOB_BYTES, "d2h_bytes_per_step": n * (48 + 48 + 4),
                         "api": "lwkzg_commit_and_prove_batch (host buffers, pinned)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
-        print(json.dumps(line))
+        emit(line)
     settings.free()
     if dist is not None:
         dist.destroy_process_group()
