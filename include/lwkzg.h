@@ -211,14 +211,19 @@ int lwkzg_window_bits(const KZGSettings *s);
 
 /* Options: "window_bits" (fixed-base table window c, 4..15; default 13; must
  * be set before the settings are first used), "msm_blocks_per_blob" (0 = auto),
- * "chunk_blobs" (host-batch pipeline chunk, default 512), "mode": 0 =
+ * "chunk_blobs" (host-batch pipeline chunk, default 256; 4 chunks in flight),
+ * "msm_algo" (1 = default: batches of at least "msm_ba_min_blobs" (256) blobs use
+ * the batched-affine MSM kernel, smaller ones the XYZZ kernel; 0 = XYZZ only;
+ * both give identical bytes), "msm_ba_variant" (tuning: accumulators per thread
+ * x threads per blob, see csrc/msm.cu), "mode": 0 =
  * MODE_REFERENCE (default: exactly what lambdaworks_kzg computes -- big-endian
  * scalars reduced mod r, blob = monomial coefficients, every failure
  * C_KZG_ERROR), 1 = MODE_CKZG_LE (the little-endian-era c-kzg-4844 semantics of
  * the YAML vectors under the reference's tests/: canonical little-endian
  * scalars, blob = evaluations, Lagrange SRS derived at load, BADARGS for invalid
  * input, empty batch verifies).  The mode is captured when a KZGSettings is
- * loaded / first used.  Env: LWKZG_WINDOW_BITS, LWKZG_CHUNK_BLOBS, LWKZG_MODE.
+ * loaded / first used.  Env: LWKZG_WINDOW_BITS, LWKZG_CHUNK_BLOBS, LWKZG_MODE,
+ * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS.
  * Returns 0 on success. */
 int lwkzg_set_option(const char *name, long value);
 long lwkzg_get_option(const char *name);
