@@ -288,7 +288,11 @@ def main():
                     "kernel_share_of_step": 2 * k_ms / ms_per_step,
                     # second half of BASELINE's metric: G1 MSM points/s (fixed-base MSM over the 4096-point SRS, this kernel)
                     "g1_msm_points_per_s": n * 4096 / (k_ms * 1e-3),
-                    "traffic": None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
+                    # profiles/r01_ncu_msm_summary.md (26.54 + 4.94 GB per 512-blob launch of the batched-affine kernel,
+                    # 6.88 + 0.04 GB for the XYZZ kernel), scaled to this launch's blob count
+                    "traffic": n * ((26.54e9 + 4.94e9) / 512 if batch_affine else (6.88e9 + 0.04e9) / 512),
+                    "traffic_source": "ncu capture, per-blob figure x blobs in this launch (profiles/r01_ncu_msm_summary.md)",
                     "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "alg_bytes_per_launch": alg_bytes,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
