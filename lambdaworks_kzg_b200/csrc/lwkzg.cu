@@ -863,7 +863,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
   if (n == "msm_algo") { if (value != 0 && value != 1) return 1; opts().msm_algo = value; return 0; }
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
-  if (n == "msm_ba_variant") { if (value < 0 || value > 5) return 1; msm_ba_set_variant((int)value); return 0; }
+  if (n == "msm_ba_variant") { if (value < 0 || value > 7) return 1; msm_ba_set_variant((int)value); return 0; }
   return 1;
 }
 long lwkzg_get_option(const char* name) {

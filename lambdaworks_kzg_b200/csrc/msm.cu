@@ -65,15 +65,22 @@ __device__ __forceinline__ G1Xyzz xyzz_from_smem(const uint32_t* smem, int strid
   return p;
 }
 
-// Block-wide sum of per-thread XYZZ accumulators; result valid in thread 0.
+// Block-wide sum of per-thread XYZZ accumulators; result valid in thread 0.  THREADS need not be a
+// power of two: the tree starts at the next power of two and skips partners beyond the block.
+__host__ __device__ constexpr int reduce_half(int threads) {
+  int s = 1;
+  while (2 * s < threads) s *= 2;
+  return s;
+}
 template <int THREADS>
-__device__ __forceinline__ void block_reduce_xyzz(G1Xyzz& acc, uint32_t* red /* 48 * THREADS/2 words */) {
+__device__ __forceinline__ void block_reduce_xyzz(G1Xyzz& acc, uint32_t* red /* 48 * reduce_half(THREADS) words */) {
+  constexpr int H = reduce_half(THREADS);
   const int tid = threadIdx.x;
-  for (int s = THREADS / 2; s > 0; s >>= 1) {
-    if (tid >= s && tid < 2 * s) xyzz_to_smem(red, THREADS / 2, tid - s, acc);
+  for (int s = H; s > 0; s >>= 1) {
+    if (tid >= s && tid < 2 * s && tid < THREADS) xyzz_to_smem(red, H, tid - s, acc);
     __syncthreads();
-    if (tid < s) {
-      G1Xyzz o = xyzz_from_smem(red, THREADS / 2, tid);
+    if (tid < s && tid + s < THREADS) {
+      G1Xyzz o = xyzz_from_smem(red, H, tid);
       xyzz_add_ni(acc, o);
     }
     __syncthreads();
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(MSM_THREADS, LWKZG_MSM_MIN_BLOCKS)
 msm_gather_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
                   int c, int pt_threads, int wsplit) {
   __shared__ uint32_t sk[8][MSM_THREADS];
-  __shared__ uint32_t red[48 * (MSM_THREADS / 2)];
+  __shared__ uint32_t red[48 * reduce_half(MSM_THREADS)];
 
   const int W = 255 / c + 1;
   const int tid = threadIdx.x;
@@ -231,7 +238,7 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
                      uint4* __restrict__ scratch, int c, int pt_threads) {
   __shared__ uint32_t sk[8][TH];
   __shared__ uint32_t sidx[K][TH];   // entry index | sign << 31, or BA_NONE
-  __shared__ uint32_t red[48 * (TH / 2)];
+  __shared__ uint32_t red[48 * reduce_half(TH)];
 
   const int W = 255 / c + 1;
   const int tid = threadIdx.x;
@@ -383,7 +390,7 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
 
 // variant = accumulators per thread (K), threads per blob (= block size) and register budget
 struct BaVariant { int k, threads; };
-static const BaVariant BA_VARIANTS[] = {{64, 128}, {32, 128}, {64, 64}, {32, 64}, {64, 32}, {16, 128}};
+static const BaVariant BA_VARIANTS[] = {{64, 128}, {32, 128}, {64, 64}, {32, 64}, {64, 32}, {16, 128}, {64, 96}, {48, 96}};
 static int g_ba_variant = 0;
 void msm_ba_set_variant(int v) { if (v >= 0 && v < (int)(sizeof(BA_VARIANTS) / sizeof(BA_VARIANTS[0]))) g_ba_variant = v; }
 int msm_ba_threads() { return BA_VARIANTS[g_ba_variant].threads; }
@@ -412,6 +419,8 @@ void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const vo
     case 3: launch_ba<32, 6, 64>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
     case 4: launch_ba<64, 12, 32>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
     case 5: launch_ba<16, 3, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    case 6: launch_ba<64, 4, 96>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    case 7: launch_ba<48, 4, 96>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
     default: launch_ba<64, 3, 128>(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
   }
   count_launch();
