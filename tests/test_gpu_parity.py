@@ -482,6 +482,24 @@ def test_large_batch_with_degenerate_blobs_both_kernels(lw, ref, settings13):
         assert out[1][1][k] == ref.compute_blob_kzg_proof(blobs[k], c), k
 
 
+@pytest.mark.parametrize("n", [256, 257, 300])
+def test_batch_sizes_around_the_kernel_switch(lw, ref, settings8, n):
+    """Chunks of 256 blobs go to the batched-affine kernel, the remainder chunk (1 .. 255 blobs) to the XYZZ kernel:
+    same bytes as an XYZZ-only run, oracle on blobs either side of the boundary."""
+    cat = b"".join(lw.synth_blob_host(k) for k in range(n))
+    lw.set_option("msm_algo", 1)
+    coms, proofs, st = lw.commit_and_prove_batch(cat, n, settings8)
+    lw.set_option("msm_algo", 0)
+    coms0, proofs0, st0 = lw.commit_and_prove_batch(cat, n, settings8)
+    lw.set_option("msm_algo", 1)
+    assert st == st0 == [0] * n
+    assert coms == coms0 and proofs == proofs0
+    for k in (0, 255, n - 1):
+        blob = lw.synth_blob_host(k)
+        c = ref.blob_to_kzg_commitment(blob)
+        assert coms[k] == c and proofs[k] == ref.compute_blob_kzg_proof(blob, c), k
+
+
 # ------------------------------------------------------------------ device API + full-size properties
 def test_device_api_and_large_batch_properties(lw, settings13, ref):
     import torch
