@@ -73,7 +73,10 @@ LW_COLD Fp fp_pow_const(const Fp& a, const uint32_t* e, int ne) {
   }
   return acc;
 }
-LW_COLD Fp fp_inv(const Fp& a) { return fp_pow_const(a, k::FP_P_MINUS_2, 12); }  // 0 -> 0
+// Fermat inversion a^(p-2), 0 -> 0.  Kept as the independent cross-check of fp_inv (fpinv.cuh: binary GCD, ~10x
+// less latency), which is what every caller uses.
+LW_COLD Fp fp_inv_fermat(const Fp& a) { return fp_pow_const(a, k::FP_P_MINUS_2, 12); }
+LW_COLD Fp fp_inv(const Fp& a);  // defined in fpinv.cuh (included at the end of this header)
 // sqrt candidate a^((p+1)/4); caller must check candidate^2 == a
 LW_COLD Fp fp_sqrt_candidate(const Fp& a) { return fp_pow_const(a, k::FP_SQRT_EXP, 12); }
 
@@ -168,3 +171,5 @@ LW_INL void fr_canon_to_be32(uint8_t* b, const Fr& canon) {
 }
 
 }  // namespace lw
+
+#include "fpinv.cuh"

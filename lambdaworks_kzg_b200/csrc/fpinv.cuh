@@ -190,4 +190,7 @@ LW_INL Fp fp_inv_gcd(const Fp& y) {
   return fp_mul_nv(V, kk);
 }
 
+// The inversion every cold caller uses (to_affine, Fp2 inverse, table build): same value as fp_inv_fermat.
+LW_COLD Fp fp_inv(const Fp& a) { return fp_inv_gcd(a); }
+
 }  // namespace lw

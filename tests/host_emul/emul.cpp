@@ -39,6 +39,7 @@ void emul_fr_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { mod_sub<Fr
 void emul_fp_to_mont(uint32_t* r, const uint32_t* a) { Fp x; memcpy(x.l, a, 48); x = fp_to_mont(x); memcpy(r, x.l, 48); }
 void emul_fp_from_mont(uint32_t* r, const uint32_t* a) { Fp x; memcpy(x.l, a, 48); x = fp_from_mont(x); memcpy(r, x.l, 48); }
 void emul_fp_inv(uint32_t* r, const uint32_t* a) { Fp x; memcpy(x.l, a, 48); x = fp_inv(x); memcpy(r, x.l, 48); }
+void emul_fp_inv_fermat(uint32_t* r, const uint32_t* a) { Fp x; memcpy(x.l, a, 48); x = fp_inv_fermat(x); memcpy(r, x.l, 48); }
 void emul_fp_inv_gcd(uint32_t* r, const uint32_t* a) { Fp x; memcpy(x.l, a, 48); x = fp_inv_gcd(x); memcpy(r, x.l, 48); }
 void emul_fr_inv(uint32_t* r, const uint32_t* a) { Fr x; memcpy(x.l, a, 32); x = fr_inv(x); memcpy(r, x.l, 32); }
 void emul_fr_from_be32(uint32_t* r, const uint8_t* b) { Fr x = fr_canon_from_be32(b); memcpy(r, x.l, 32); }

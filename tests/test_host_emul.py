@@ -61,7 +61,9 @@ def test_inversions(lib):
     rnd = random.Random(3)
     out = (ctypes.c_uint32 * 12)()
     for a in [1, 2, P - 1, rnd.randrange(P), rnd.randrange(P)]:
-        lib.emul_fp_inv(out, u32(a * RP % P, 12))
+        lib.emul_fp_inv(out, u32(a * RP % P, 12))            # binary GCD (fpinv.cuh): what the kernels call
+        assert from_u32(out) == pow(a, -1, P) * RP % P
+        lib.emul_fp_inv_fermat(out, u32(a * RP % P, 12))     # a^(p-2): the independent cross-check
         assert from_u32(out) == pow(a, -1, P) * RP % P
     out8 = (ctypes.c_uint32 * 8)()
     for a in [1, 2, R - 1, rnd.randrange(R)]:
