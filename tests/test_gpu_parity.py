@@ -500,6 +500,31 @@ def test_batch_sizes_around_the_kernel_switch(lw, ref, settings8, n):
         assert coms[k] == c and proofs[k] == ref.compute_blob_kzg_proof(blob, c), k
 
 
+@pytest.mark.parametrize("n", [1, 130, 300, 700])
+def test_device_api_odd_batch_sizes(lw, ref, settings8, n):
+    """Device-pointer entry point with batch sizes that leave a remainder chunk (a small chunk needs more block
+    partials per blob than a full one: the slots are sized for the whole chunk plan before anything is enqueued)."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    blobs = torch.empty(n * kzg.BYTES_PER_BLOB, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lw.synth_blobs_device(blobs.data_ptr(), 0, n, st)
+    coms = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+    proofs = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+    status = torch.ones(n, dtype=torch.int32, device=dev)
+    lw.commit_and_prove_batch_device(coms.data_ptr(), proofs.data_ptr(), blobs.data_ptr(), n, settings8, st, status.data_ptr())
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    cb, pb = bytes(coms.cpu().numpy().tobytes()), bytes(proofs.cpu().numpy().tobytes())
+    hc, hp, hs = lw.commit_and_prove_batch(bytes(blobs.cpu().numpy().tobytes()), n, settings8)
+    assert hs == [0] * n and b"".join(hc) == cb and b"".join(hp) == pb
+    for k in sorted({0, n // 2, n - 1}):
+        blob = lw.synth_blob_host(k)
+        c = ref.blob_to_kzg_commitment(blob)
+        assert cb[48 * k: 48 * k + 48] == c and pb[48 * k: 48 * k + 48] == ref.compute_blob_kzg_proof(blob, c), k
+
+
 # ------------------------------------------------------------------ device API + full-size properties
 def test_device_api_and_large_batch_properties(lw, settings13, ref):
     import torch
