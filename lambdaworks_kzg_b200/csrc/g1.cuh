@@ -222,6 +222,55 @@ LW_COLD G1Xyzz g1_mul_scalar(const G1Affine& p, const uint32_t* kk, int nlimbs) 
   return acc;
 }
 
+// [k]p with the GLV split of BLS12-381: r = x^4 - x^2 + 1 and phi(P) = (beta x, y) = [-x^2]P, so with
+// k = q x^2 + m (m < x^2 < 2^128, q < 2^128 for every k < r) one gets [k]P = [m]P + [q](beta x, -y): 128
+// doublings and two conditional mixed additions per bit instead of 255 doublings (batched verification's
+// r^i-multiples, /root/reference/src/lib.rs:651-685).  k: canonical 256-bit little-endian, < r.
+LW_COLD void glv_split(uint32_t* q4, uint32_t* m4, const uint32_t* k8) {
+  uint32_t rem[5] = {0, 0, 0, 0, 0};
+  uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int bit = 255; bit >= 0; bit--) {
+    // rem = 2 rem + bit
+    for (int i = 4; i > 0; i--) rem[i] = (rem[i] << 1) | (rem[i - 1] >> 31);
+    rem[0] = (rem[0] << 1) | ((k8[bit >> 5] >> (bit & 31)) & 1u);
+    // rem >= x^2 ?
+    uint32_t t[5];
+    uint32_t borrow = 0;
+    for (int i = 0; i < 5; i++) {
+      const uint32_t s = i < 4 ? k::BLS_X2[i] : 0u;
+      const uint64_t d = (uint64_t)rem[i] - s - borrow;
+      t[i] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+    if (!borrow) {
+      for (int i = 0; i < 5; i++) rem[i] = t[i];
+      q[bit >> 5] |= 1u << (bit & 31);
+    }
+  }
+  for (int i = 0; i < 4; i++) { q4[i] = q[i]; m4[i] = rem[i]; }
+}
+LW_COLD G1Xyzz g1_mul_scalar_glv(const G1Affine& p, const uint32_t* k8) {
+  uint32_t q[4], m[4];
+  glv_split(q, m, k8);
+  G1Affine p2;
+  Fp beta;
+  for (int i = 0; i < 12; i++) beta.l[i] = k::FP_BETA[i];
+  p2.x = fp_mul(p.x, beta);
+  p2.y = fp_neg(p.y);
+  G1Xyzz acc = xyzz_inf();
+  if (g1a_is_inf(p)) return acc;
+  bool started = false;
+  for (int w = 3; w >= 0; w--) {
+    const uint32_t wm = m[w], wq = q[w];
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) xyzz_dbl_ni(acc);
+      if ((wm >> bit) & 1u) { xyzz_madd_ni(acc, p); started = true; }
+      if ((wq >> bit) & 1u) { xyzz_madd_ni(acc, p2); started = true; }
+    }
+  }
+  return acc;
+}
+
 // ---------------------------------------------------------------- codecs
 // /root/reference/src/compression.rs:33-60
 LW_COLD void g1_compress(uint8_t* out48, const G1Affine& p) {

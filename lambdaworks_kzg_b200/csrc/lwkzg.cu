@@ -790,12 +790,14 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   // proofs: decode status into the (still unused) tuples buffer, then merge
   launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, s0, le);
   launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, (int)n, s0);
-  CU_TRY(cudaStreamSynchronize(s0));
+  // the blob copies and SHA midstates do not need the decoded points: only the challenge tail does, so the
+  // slot streams wait for the decompression through an event instead of the host waiting here
+  CU_TRY(cudaEventRecord(c->slot[0].ev_in, s0));
   size_t k = 0;
   for (size_t off = 0; off < n; off += chunk, k++) {
     int m = (int)std::min<size_t>(chunk, n - off);
     Slot& sl = c->slot[k % NSLOT];
-    CU_TRY(cudaStreamSynchronize(sl.st));
+    if (&sl != &c->slot[0] || k >= (size_t)NSLOT) CU_TRY(cudaStreamSynchronize(sl.st));
     if (!slot_reserve(sl, m, 1, true)) return false;
     CU_TRY(cudaMemcpyAsync(sl.blobs.p, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, sl.st));
     CU_TRY(cudaEventRecord(sl.ev_fork, sl.st));
@@ -803,6 +805,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     launch_challenge_midstate(sl.states.p, sl.blobs.p, m, sl.aux);
     CU_TRY(cudaEventRecord(sl.ev_aux, sl.aux));
     CU_TRY(cudaStreamWaitEvent(sl.st, sl.ev_aux, 0));
+    CU_TRY(cudaStreamWaitEvent(sl.st, c->slot[0].ev_in, 0));
     if (le) {
       CU_TRY(cudaMemsetAsync(sl.status2.p, 0, (size_t)m * sizeof(int), sl.st));
       launch_le_blob_check((int*)sl.status2.p, sl.blobs.p, m, sl.st);

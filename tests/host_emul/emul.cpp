@@ -89,6 +89,10 @@ void emul_g1_mul(uint8_t* out, const uint8_t* a, const uint32_t* k8) {
   G1Affine A = load_aff(a);
   store_aff(out, xyzz_to_affine(g1_mul_scalar(A, k8, 8)));
 }
+void emul_g1_mul_glv(uint8_t* out, const uint8_t* a, const uint32_t* k8) {
+  G1Affine A = load_aff(a);
+  store_aff(out, xyzz_to_affine(g1_mul_scalar_glv(A, k8)));
+}
 int emul_g1_on_curve(const uint8_t* a) { return g1a_on_curve(load_aff(a)) ? 1 : 0; }
 int emul_g1_in_subgroup(const uint8_t* a) { return g1_in_subgroup(load_aff(a)) ? 1 : 0; }
 void emul_g1_compress(uint8_t* out48, const uint8_t* a) { g1_compress(out48, load_aff(a)); }

@@ -110,6 +110,21 @@ def test_g1_scalar_mul(lib):
         assert aff_from(out) == bls.g1_mul(p, k)
 
 
+def test_g1_scalar_mul_glv(lib):
+    """k P = (k mod x^2) P + (k div x^2) (beta x, -y) for every canonical k < r (batched verification's multiples)."""
+    rnd = random.Random(66)
+    out = (ctypes.c_uint8 * 96)()
+    x2 = bls.BLS_X ** 2
+    ks = [0, 1, 2, x2 - 1, x2, x2 + 1, 2 * x2, R - 1, R - 2, (R - 1) // 2, (1 << 128) - 1, 1 << 128, 1 << 254]
+    ks += [rnd.randrange(R) for _ in range(12)]
+    for i, k in enumerate(ks):
+        p = _rand_pt(rnd) if i % 4 == 0 else p
+        lib.emul_g1_mul_glv(out, aff_bytes(p), u32(k % R, 8))
+        assert aff_from(out) == bls.g1_mul(p, k % R), hex(k)
+    lib.emul_g1_mul_glv(out, aff_bytes(None), u32(12345, 8))
+    assert aff_from(out) is None
+
+
 def _curve_point_not_in_subgroup(rnd):
     while True:
         x = rnd.randrange(P)
