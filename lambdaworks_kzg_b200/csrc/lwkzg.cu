@@ -844,7 +844,7 @@ C_KZG_RET bad_code() { return g_bad_code == 1 ? C_KZG_BADARGS : C_KZG_ERROR; }
 bool verify_single_from_workspace(Ctx* c, bool& ok) {
   cudaStream_t s0 = c->slot[0].st;
   // reference: KZG::verify subtracts y * srs[0] (= G for a monomial setup); c-kzg uses the generator itself
-  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->mode == 1 ? c->d_gen : c->d_srs, c->d_prep0, c->d_prep1, s0);
+  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->mode == 1 ? c->d_gen : c->d_srs, c->d_prep0, c->d_prep1, c->mode == 1 || c->srs_in_g1, s0);
   int okv = 0;
   CU_TRY(cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
   CU_TRY(cudaStreamSynchronize(s0));

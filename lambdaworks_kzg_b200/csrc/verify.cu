@@ -69,23 +69,43 @@ __device__ __forceinline__ bool two_pairing_check(const G1Affine* pts, const G2P
 __global__ void __launch_bounds__(32) verify_single_kernel(int* __restrict__ ok_out, const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
                                                             const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
                                                             const G1Affine* __restrict__ g1_0, const G2Prepared* __restrict__ prep0,
-                                                            const G2Prepared* __restrict__ prep1) {
-  __shared__ G1Xyzz sh_pt[2];
+                                                            const G2Prepared* __restrict__ prep1, int g1_0_in_subgroup) {
+  __shared__ G1Xyzz sh_pt[4];
   __shared__ WarpPairingMem sh_m;
   __shared__ G1Affine sh_pair[2];
   const int lane = threadIdx.x;
   G1Affine C = *c_aff, PI = *pi_aff;
-  if (lane < 2) {
-    uint32_t k[8];
-    for (int i = 0; i < 8; i++) k[i] = lane == 0 ? y[i] : z[i];
-    G1Affine base = lane == 0 ? *g1_0 : PI;
-    sh_pt[lane] = g1_mul_scalar(base, k, 8);
+  if (lane < 4) {
+    // four lanes share the two scalar multiplications: GLV halves k = q x^2 + m, [k]P = [m]P + [q](beta x, -y)
+    // (z and y are canonical, < r), 128 doublings each instead of 255
+    const int which = lane >> 1, half = lane & 1;
+    uint32_t k[8], q[4], m[4];
+    for (int i = 0; i < 8; i++) k[i] = which == 0 ? y[i] : z[i];
+    glv_split(q, m, k);
+    G1Affine base = which == 0 ? *g1_0 : PI;
+    // phi(P) = [-x^2]P holds on the r-torsion only: pi was subgroup-checked when decoded, a hand-built setup's
+    // g1[0] need not be (srs.rs:155-172 checks the curve equation only) -> plain 255-bit ladder on lane 0
+    const bool glv = which == 1 || g1_0_in_subgroup != 0;
+    if (!glv) {
+      sh_pt[lane] = half == 0 ? g1_mul_scalar(base, k, 8) : xyzz_inf();
+    } else {
+    if (half == 1 && !g1a_is_inf(base)) {
+      Fp beta;
+      for (int i = 0; i < 12; i++) beta.l[i] = k::FP_BETA[i];
+      base.x = fp_mul(base.x, beta);
+      base.y = fp_neg(base.y);
+    }
+    sh_pt[lane] = g1_mul_scalar(base, half == 0 ? m : q, 4);
+    }
   }
   __syncthreads();
   if (lane == 0) {
     G1Xyzz acc = xyzz_from_affine(C);
-    xyzz_add_ni(acc, xyzz_neg(sh_pt[0]));
-    xyzz_add_ni(acc, sh_pt[1]);
+    G1Xyzz yg = sh_pt[0];
+    xyzz_add_ni(yg, sh_pt[1]);
+    xyzz_add_ni(acc, xyzz_neg(yg));
+    xyzz_add_ni(acc, sh_pt[2]);
+    xyzz_add_ni(acc, sh_pt[3]);
     sh_pair[0] = xyzz_to_affine(acc);
     sh_pair[1] = g1a_neg(PI);
   }
@@ -371,9 +391,9 @@ void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st)
   count_launch();
 }
 void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y, const void* d_g1_0_aff,
-                          const void* d_prep0, const void* d_prep1, cudaStream_t st) {
+                          const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st) {
   verify_single_kernel<<<1, 32, 0, st>>>(d_ok, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
-                                         (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
+                                         (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1, g1_0_in_subgroup ? 1 : 0);
   count_launch();
 }
 void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le) {
