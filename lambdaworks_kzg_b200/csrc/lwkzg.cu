@@ -401,6 +401,16 @@ bool slot_reserve(Slot& s, int n, int bpb, bool need_blobs) {
          s.status.ensure((size_t)n * sizeof(int)) && s.status2.ensure((size_t)n * sizeof(int)) && s.zbe.ensure((size_t)n * 32);
 }
 
+// true when slot_reserve(s, n, bpb, need_blobs) would not have to reallocate anything
+bool slot_fits(const Slot& s, int n, int bpb, bool need_blobs) {
+  const size_t m = (size_t)n;
+  if (use_batch_affine(n) && s.ba_scratch.cap < msm_ba_scratch_bytes(n)) return false;
+  if (need_blobs && s.blobs.cap < m * BLOB_BYTES) return false;
+  return s.q.cap >= m * BLOB_BYTES && s.partials.cap >= m * bpb * XYZZ_BYTES && s.states.cap >= m * 32 && s.z.cap >= m * 32 &&
+         s.y.cap >= m * 32 && s.ybe.cap >= m * 32 && s.c48.cap >= m * 48 && s.cin48.cap >= m * 48 && s.p48.cap >= m * 48 &&
+         s.caff.cap >= m * AFFINE_BYTES && s.status.cap >= m * sizeof(int) && s.status2.cap >= m * sizeof(int) && s.zbe.cap >= m * 32;
+}
+
 void run_msm(Slot& s, const Ctx* c, const void* d_scalars, bool be_input, int n, int bpb, cudaStream_t st) {
   if (bpb == 1 && use_batch_affine(n) && s.ba_scratch.cap >= msm_ba_scratch_bytes(n))
     launch_msm_gather_ba(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, s.ba_scratch.p, st);
@@ -606,9 +616,17 @@ C_KZG_RET device_batch(Mode mode, const KZGSettings* s, size_t n, const void* d_
     plan.emplace_back(off, m);
     off += m;
   }
-  for (int k = 0; k < NSLOT && k < (int)plan.size(); k++) cudaStreamSynchronize(c->slot[k].st);
-  for (size_t k = 0; k < plan.size(); k++)
-    if (!slot_reserve(c->slot[k % NSLOT], (int)plan[k].second, auto_bpb((int)plan[k].second), false)) return C_KZG_ERROR;
+  // The host only waits for earlier work when a buffer really has to grow: back-to-back calls (also from
+  // different user streams) then queue behind each other on the slot streams and the tail of one batch
+  // overlaps the head of the next.
+  bool fits = true;
+  for (size_t k = 0; k < plan.size() && fits; k++)
+    fits = slot_fits(c->slot[k % NSLOT], (int)plan[k].second, auto_bpb((int)plan[k].second), false);
+  if (!fits) {
+    for (auto& sl : c->slot) { cudaStreamSynchronize(sl.st); cudaStreamSynchronize(sl.aux); }
+    for (size_t k = 0; k < plan.size(); k++)
+      if (!slot_reserve(c->slot[k % NSLOT], (int)plan[k].second, auto_bpb((int)plan[k].second), false)) return C_KZG_ERROR;
+  }
   cudaEvent_t ev_user;
   if (cudaEventCreateWithFlags(&ev_user, cudaEventDisableTiming) != cudaSuccess) { set_err("event"); return C_KZG_ERROR; }
   cudaEventRecord(ev_user, user);
