@@ -46,7 +46,7 @@ int msm_threads_per_block();
 
 // ---- Fiat-Shamir + polynomial (poly.cu)
 // SHA-256 midstate over domain || le64(4096) || le64(0) || blob[0 .. 131040)
-void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st);
+void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st, bool latency = false);
 // finish with blob tail + 48 commitment bytes -> z canonical (8 u32 LE per blob)
 void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st, bool le_digest = false);
 // z from caller bytes (big-endian, reduced)
@@ -80,6 +80,12 @@ void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, 
 void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le = false);
 // r = H(domain || le64(4096) || le64(n_total) || tuples) -> canonical r (8 u32)
 void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, bool le = false);
+// the same hash over a block range of the message, state carried in d_state (first: start from the IV; last: absorb
+// the rest of the message from blk0 on and write r).  blocks_ready(k) = full 64-byte blocks covered by the head and k tuples
+size_t batch_challenge_state_bytes();
+int batch_challenge_blocks_ready(size_t tuples_ready);
+void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples160, size_t n_total, int blk0, int blk1, bool first, bool last,
+                                 cudaStream_t st, bool le = false);
 // partial sums over [first, first+n_local): 3 XYZZ blocks-partials then reduced to 3 affine (canonical BE 96 B each)
 void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
                            size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st);

@@ -110,6 +110,11 @@ struct Ctx {
   // batched-verification workspace (sized for the largest batch seen)
   DevBuf vb_cin, vb_pin, vb_caff, vb_piaff, vb_c48r, vb_p48r, vb_z, vb_y, vb_tuples, vb_status, vb_r, vb_partial, vb_scratch, vb_ok, vb_zy_in;
   size_t vb_n = 0;  // items currently held by the workspace (phase1 -> phase2)
+  // the batch challenge r is one sequential SHA-256 over all tuples: it is absorbed chunk by chunk on its own
+  // stream while later chunks are still being copied and evaluated
+  cudaStream_t hash_st = nullptr;
+  cudaEvent_t ev_hash = nullptr;
+  DevBuf vb_hstate;
   // pinned host staging for batch results: a D2H copy into pageable memory would block the host
   // until the chunk's kernels finish and serialise the two pipeline slots
   void* h_stage = nullptr;
@@ -157,9 +162,12 @@ void destroy_ctx(Ctx* c) {
     if (s.st) cudaStreamDestroy(s.st);
     if (s.aux) cudaStreamDestroy(s.aux);
   }
+  if (c->hash_st) cudaStreamSynchronize(c->hash_st);
   for (DevBuf* b : {&c->vb_cin, &c->vb_pin, &c->vb_caff, &c->vb_piaff, &c->vb_c48r, &c->vb_p48r, &c->vb_z, &c->vb_y, &c->vb_tuples, &c->vb_status,
-                    &c->vb_r, &c->vb_partial, &c->vb_scratch, &c->vb_ok, &c->vb_zy_in})
+                    &c->vb_r, &c->vb_partial, &c->vb_scratch, &c->vb_ok, &c->vb_zy_in, &c->vb_hstate})
     b->release();
+  if (c->ev_hash) cudaEventDestroy(c->ev_hash);
+  if (c->hash_st) cudaStreamDestroy(c->hash_st);
   if (c->d_srs) cudaFree(c->d_srs);
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_prep0) cudaFree(c->d_prep0);
@@ -183,6 +191,8 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
     CU_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
   }
+  CU_TRY(cudaStreamCreateWithPriority(&c->hash_st, cudaStreamNonBlocking, hi));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_hash, cudaEventDisableTiming));
   cudaStream_t st = c->slot[0].st;
 
   // ---- SRS import
@@ -442,7 +452,7 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
     if (mode == Mode::CommitProve || mode == Mode::BlobProof) {
       CU_TRY(cudaEventRecord(s.ev_fork, st));
       CU_TRY(cudaStreamWaitEvent(s.aux, s.ev_fork, 0));
-      launch_challenge_midstate(s.states.p, d_blobs, n, s.aux);
+      launch_challenge_midstate(s.states.p, d_blobs, n, s.aux, mode == Mode::BlobProof);
       CU_TRY(cudaEventRecord(s.ev_aux, s.aux));
     }
     if (mode == Mode::CommitProve) {
@@ -478,7 +488,7 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
     // fork: SHA-256 midstate over the blob on the high-priority aux stream
     CU_TRY(cudaEventRecord(s.ev_fork, st));
     CU_TRY(cudaStreamWaitEvent(s.aux, s.ev_fork, 0));
-    launch_challenge_midstate(s.states.p, d_blobs, n, s.aux);
+    launch_challenge_midstate(s.states.p, d_blobs, n, s.aux, mode == Mode::BlobProof);
     CU_TRY(cudaEventRecord(s.ev_aux, s.aux));
   }
   if (mode == Mode::CommitProve) {
@@ -785,7 +795,8 @@ bool vb_reserve(Ctx* c, size_t n) {
   return c->vb_cin.ensure(n * 48) && c->vb_pin.ensure(n * 48) && c->vb_caff.ensure(n * AFFINE_BYTES) && c->vb_piaff.ensure(n * AFFINE_BYTES) &&
          c->vb_c48r.ensure(n * 48) && c->vb_p48r.ensure(n * 48) && c->vb_z.ensure(n * 32) && c->vb_y.ensure(n * 32) && c->vb_tuples.ensure(n * 160) &&
          c->vb_status.ensure(n * sizeof(int)) && c->vb_r.ensure(32) && c->vb_partial.ensure(288) && c->vb_ok.ensure(sizeof(int)) &&
-         c->vb_zy_in.ensure(n * 64) && c->vb_scratch.ensure(batch_partials_scratch_bytes((int)n));
+         c->vb_zy_in.ensure(n * 64) && c->vb_scratch.ensure(batch_partials_scratch_bytes((int)n)) &&
+         c->vb_hstate.ensure(batch_challenge_state_bytes());
 }
 
 // Per-blob preparation of a batched verification (lib.rs:562-596): decode C_i
@@ -793,7 +804,9 @@ bool vb_reserve(Ctx* c, size_t n) {
 // the context's verify workspace.  Host blobs are streamed through the two
 // slots in chunks.  Returns false on CUDA failure; invalid items are reported
 // through vb_status.
-bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n) {
+// hash_r: also derive the batch challenge r (utils.rs:166-206) into vb_r, absorbing each chunk's tuples as soon as
+// they exist.
+bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n, bool hash_r = false) {
   if (!vb_reserve(c, n)) return false;
   long chunk;
   {
@@ -812,6 +825,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   // slot streams wait for the decompression through an event instead of the host waiting here
   CU_TRY(cudaEventRecord(c->slot[0].ev_in, s0));
   size_t k = 0;
+  int hashed_blocks = 0;   // 64-byte blocks of the batch-challenge message absorbed so far
   for (size_t off = 0; off < n; off += chunk, k++) {
     int m = (int)std::min<size_t>(chunk, n - off);
     Slot& sl = c->slot[k % NSLOT];
@@ -820,7 +834,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     CU_TRY(cudaMemcpyAsync(sl.blobs.p, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, sl.st));
     CU_TRY(cudaEventRecord(sl.ev_fork, sl.st));
     CU_TRY(cudaStreamWaitEvent(sl.aux, sl.ev_fork, 0));
-    launch_challenge_midstate(sl.states.p, sl.blobs.p, m, sl.aux);
+    launch_challenge_midstate(sl.states.p, sl.blobs.p, m, sl.aux, true);
     CU_TRY(cudaEventRecord(sl.ev_aux, sl.aux));
     CU_TRY(cudaStreamWaitEvent(sl.st, sl.ev_aux, 0));
     CU_TRY(cudaStreamWaitEvent(sl.st, c->slot[0].ev_in, 0));
@@ -834,13 +848,23 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
       launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, sl.states.p, sl.blobs.p, (const uint8_t*)c->vb_c48r.p + off * 48, m, sl.st);
       launch_poly_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, sl.blobs.p, (const uint8_t*)c->vb_z.p + off * 32, m, sl.st);
     }
+    launch_make_tuples((uint8_t*)c->vb_tuples.p + off * 160, (const uint8_t*)c->vb_c48r.p + off * 48, (const uint8_t*)c->vb_z.p + off * 32,
+                       (const uint8_t*)c->vb_y.p + off * 32, (const uint8_t*)c->vb_p48r.p + off * 48, m, sl.st, le);
+    if (hash_r) {
+      // chunks reach the hash stream in order; each launch absorbs the blocks its chunk completed
+      CU_TRY(cudaEventRecord(sl.ev_done, sl.st));
+      CU_TRY(cudaStreamWaitEvent(c->hash_st, sl.ev_done, 0));
+      const bool last = off + (size_t)m >= n;
+      const int ready = batch_challenge_blocks_ready(off + (size_t)m);
+      launch_batch_challenge_part(c->vb_r.p, c->vb_hstate.p, c->vb_tuples.p, n, hashed_blocks, ready, k == 0, last, c->hash_st, le);
+      hashed_blocks = ready;
+    }
   }
   for (auto& sl : c->slot) {
     CU_TRY(cudaStreamSynchronize(sl.st));
     CU_TRY(cudaStreamSynchronize(sl.aux));
   }
-  launch_make_tuples(c->vb_tuples.p, c->vb_c48r.p, c->vb_z.p, c->vb_y.p, c->vb_p48r.p, (int)n, s0, le);
-  CU_TRY(cudaStreamSynchronize(s0));
+  if (hash_r) CU_TRY(cudaStreamSynchronize(c->hash_st));
   CU_TRY(cudaGetLastError());
   c->vb_n = n;
   return true;
@@ -1093,13 +1117,12 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
-  if (!verify_prepare(c, blobs, commitments_bytes, proofs_bytes, n)) return C_KZG_ERROR;
+  if (!verify_prepare(c, blobs, commitments_bytes, proofs_bytes, n, true)) return C_KZG_ERROR;  // leaves r in vb_r
   bool bad = false;
   if (!any_bad_status(c, n, bad)) return C_KZG_ERROR;
   if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   cudaStream_t s0 = c->slot[0].st;
-  launch_batch_challenge(c->vb_r.p, c->vb_tuples.p, n, s0, c->mode == 1);
   launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, 0, (int)n, c->vb_scratch.p, s0);
   launch_batch_final((int*)c->vb_ok.p, c->vb_partial.p, 1, c->d_prep0, c->d_prep1, s0);
   int okv = 0;

@@ -174,9 +174,12 @@ __global__ void __launch_bounds__(POLY_WARPS * 32) poly_eval_quot_kernel(uint32_
   }
 }
 
-void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st) {
+// latency = true: nothing else runs beside the hash (blob proofs for given commitments, verification), so the
+// warp-per-blob kernel's ~2x shorter critical path is what counts; false: the hash hides under a commitment MSM and
+// the thread-per-blob kernel leaves the issue slots to it.
+void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st, bool latency) {
   if (n <= 0) return;
-  if (n <= 64)
+  if (n <= 64 || latency)
     challenge_midstate_warp_kernel<<<n, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n);
   else
     challenge_midstate_kernel<<<(n + 31) / 32, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n);

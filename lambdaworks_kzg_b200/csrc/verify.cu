@@ -135,7 +135,16 @@ __global__ void make_tuples_kernel(uint8_t* __restrict__ tuples, const uint8_t* 
 
 // r = H("RCKZGBATCH___V1_" || le64(4096) || le64(n) || tuples), read big-endian, mod r.
 // One SHA-256 stream: the warp expands message schedules in parallel, lane 0 runs the rounds.
-__global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restrict__ r_out, const uint8_t* __restrict__ tuples, unsigned long long n_total, int le) {
+//
+// The hash is sequential, but its input becomes available chunk by chunk while a batch is being prepared
+// (tuple i exists as soon as blob i has been copied, hashed and evaluated), so the kernel works on a block
+// range of the message: [blk0, blk1) 64-byte blocks, state carried in `state` between launches
+// (FLAG_INIT: start from the SHA-256 IV; FLAG_FINAL: also absorb everything after blk1 -- the remaining
+// full blocks and the padded tail -- and write r).  One launch with both flags and blk0 = blk1 = 0 is
+// the monolithic hash.
+constexpr int BCH_INIT = 1, BCH_FINAL = 2, BCH_LE = 4;
+__global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restrict__ r_out, Sha256State* __restrict__ state, const uint8_t* __restrict__ tuples,
+                                                              unsigned long long n_total, int blk0, int blk1, int flags) {
   __shared__ uint32_t wk[64 * 32];
   __shared__ uint8_t head[32];
   const int lane = threadIdx.x;
@@ -149,10 +158,12 @@ __global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restric
   __syncwarp();
   const unsigned long long total = 32ull + 160ull * n_total;
   const int nfull = (int)(total / 64);
+  if (flags & BCH_FINAL) blk1 = nfull;
   auto byte_at = [&](unsigned long long off) -> uint8_t { return off < 32 ? head[off] : tuples[off - 32]; };
   Sha256State s;
-  sha256_init(s);
-  sha256_warp_blocks(s, nfull, [&](int blk, uint32_t* w) {
+  if (flags & BCH_INIT) sha256_init(s); else s = *state;
+  sha256_warp_blocks(s, blk1 - blk0, [&](int rel, uint32_t* w) {
+    const int blk = blk0 + rel;
     unsigned long long off = 64ull * blk;
     if (blk >= 1) {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(tuples + (off - 32));  // 32-byte aligned
@@ -163,6 +174,7 @@ __global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restric
     }
   }, wk);
   if (lane != 0) return;
+  if (!(flags & BCH_FINAL)) { *state = s; return; }
   uint32_t w[16];
   unsigned long long off = 64ull * nfull;
   uint8_t tail[128];
@@ -178,6 +190,7 @@ __global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restric
       w[i] = ((uint32_t)tail[o + 4 * i] << 24) | ((uint32_t)tail[o + 4 * i + 1] << 16) | ((uint32_t)tail[o + 4 * i + 2] << 8) | tail[o + 4 * i + 3];
     sha256_compress(s, w);
   }
+  const int le = flags & BCH_LE;
   Fr r;
   for (int i = 0; i < 8; i++) r.l[i] = le ? bswap32(s.h[i]) : s.h[7 - i];
   mod_reduce_small<FrCfg, 2>(r.l);
@@ -403,7 +416,17 @@ void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, c
   count_launch();
 }
 void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, bool le) {
-  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (const uint8_t*)d_tuples160, (unsigned long long)n_total, le ? 1 : 0);
+  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, nullptr, (const uint8_t*)d_tuples160, (unsigned long long)n_total, 0, 0,
+                                           BCH_INIT | BCH_FINAL | (le ? BCH_LE : 0));
+  count_launch();
+}
+size_t batch_challenge_state_bytes() { return sizeof(Sha256State); }
+int batch_challenge_blocks_ready(size_t tuples_ready) { return (int)((32 + 160 * tuples_ready) / 64); }
+void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples160, size_t n_total, int blk0, int blk1, bool first, bool last,
+                                 cudaStream_t st, bool le) {
+  if (!last && blk1 <= blk0 && !first) return;
+  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (Sha256State*)d_state, (const uint8_t*)d_tuples160, (unsigned long long)n_total, blk0, blk1,
+                                           (first ? BCH_INIT : 0) | (last ? BCH_FINAL : 0) | (le ? BCH_LE : 0));
   count_launch();
 }
 size_t batch_partials_scratch_bytes(int n_local) {
