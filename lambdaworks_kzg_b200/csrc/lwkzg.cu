@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -112,9 +114,10 @@ struct Ctx {
   size_t vb_n = 0;  // items currently held by the workspace (phase1 -> phase2)
   // the batch challenge r is one sequential SHA-256 over all tuples: it is absorbed chunk by chunk on its own
   // stream while later chunks are still being copied and evaluated
-  cudaStream_t hash_st = nullptr;
+  cudaStream_t hash_st = nullptr, copy_st = nullptr;
   cudaEvent_t ev_hash = nullptr;
-  DevBuf vb_hstate;
+  std::vector<cudaEvent_t> ev_pool;   // per chunk: blob copy landed / tuples written
+  DevBuf vb_hstate, vb_blobs, vb_states, vb_status2;
   // pinned host staging for batch results: a D2H copy into pageable memory would block the host
   // until the chunk's kernels finish and serialise the two pipeline slots
   void* h_stage = nullptr;
@@ -164,9 +167,11 @@ void destroy_ctx(Ctx* c) {
   }
   if (c->hash_st) cudaStreamSynchronize(c->hash_st);
   for (DevBuf* b : {&c->vb_cin, &c->vb_pin, &c->vb_caff, &c->vb_piaff, &c->vb_c48r, &c->vb_p48r, &c->vb_z, &c->vb_y, &c->vb_tuples, &c->vb_status,
-                    &c->vb_r, &c->vb_partial, &c->vb_scratch, &c->vb_ok, &c->vb_zy_in, &c->vb_hstate})
+                    &c->vb_r, &c->vb_partial, &c->vb_scratch, &c->vb_ok, &c->vb_zy_in, &c->vb_hstate, &c->vb_blobs, &c->vb_states, &c->vb_status2})
     b->release();
   if (c->ev_hash) cudaEventDestroy(c->ev_hash);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
   if (c->hash_st) cudaStreamDestroy(c->hash_st);
   if (c->d_srs) cudaFree(c->d_srs);
   if (c->d_table) cudaFree(c->d_table);
@@ -192,6 +197,7 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
     CU_TRY(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
   }
   CU_TRY(cudaStreamCreateWithPriority(&c->hash_st, cudaStreamNonBlocking, hi));
+  CU_TRY(cudaStreamCreateWithPriority(&c->copy_st, cudaStreamNonBlocking, hi));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_hash, cudaEventDisableTiming));
   cudaStream_t st = c->slot[0].st;
 
@@ -791,12 +797,15 @@ C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, si
 }
 
 // ------------------------------------------------------------------ verification
+// blobs of a batched verification are staged on the device VB_SUPER_BLOBS at a time (2 GiB)
+constexpr size_t VB_SUPER_BLOBS = 16384;
 bool vb_reserve(Ctx* c, size_t n) {
   return c->vb_cin.ensure(n * 48) && c->vb_pin.ensure(n * 48) && c->vb_caff.ensure(n * AFFINE_BYTES) && c->vb_piaff.ensure(n * AFFINE_BYTES) &&
          c->vb_c48r.ensure(n * 48) && c->vb_p48r.ensure(n * 48) && c->vb_z.ensure(n * 32) && c->vb_y.ensure(n * 32) && c->vb_tuples.ensure(n * 160) &&
          c->vb_status.ensure(n * sizeof(int)) && c->vb_r.ensure(32) && c->vb_partial.ensure(288) && c->vb_ok.ensure(sizeof(int)) &&
          c->vb_zy_in.ensure(n * 64) && c->vb_scratch.ensure(batch_partials_scratch_bytes((int)n)) &&
-         c->vb_hstate.ensure(batch_challenge_state_bytes());
+         c->vb_hstate.ensure(batch_challenge_state_bytes()) && c->vb_blobs.ensure(std::min<size_t>(n, VB_SUPER_BLOBS) * BLOB_BYTES) &&
+         c->vb_states.ensure(n * 32) && c->vb_status2.ensure(n * sizeof(int));
 }
 
 // Per-blob preparation of a batched verification (lib.rs:562-596): decode C_i
@@ -814,55 +823,114 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     chunk = std::max(1L, opts().chunk_blobs);
   }
   cudaStream_t s0 = c->slot[0].st;
-  CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitments, n * 48, cudaMemcpyHostToDevice, s0));
-  CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proofs, n * 48, cudaMemcpyHostToDevice, s0));
   const bool le = c->mode == 1;
+  // commitments on s0, proofs on the hash stream (idle until the first tuples exist): the two decompressions are
+  // latency-bound thread-per-point kernels and run side by side
+  CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitments, n * 48, cudaMemcpyHostToDevice, s0));
+  CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proofs, n * 48, cudaMemcpyHostToDevice, c->hash_st));
   launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0, le);
   // proofs: decode status into the (still unused) tuples buffer, then merge
-  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, s0, le);
+  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, c->hash_st, le);
+  CU_TRY(cudaEventRecord(c->ev_hash, c->hash_st));
+  CU_TRY(cudaStreamWaitEvent(s0, c->ev_hash, 0));
   launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, (int)n, s0);
   // the blob copies and SHA midstates do not need the decoded points: only the challenge tail does, so the
   // slot streams wait for the decompression through an event instead of the host waiting here
   CU_TRY(cudaEventRecord(c->slot[0].ev_in, s0));
+  // Blobs land in a verify-owned staging area big enough for a whole super-batch, so no chunk ever waits for a
+  // buffer: one copy stream issues the H2D copies back to back, and each chunk's kernels (SHA midstate ->
+  // challenge -> evaluation -> tuple) start on one of 2 * NSLOT compute streams as soon as its copy has landed.
+  // The copy engine is the only thing that runs the whole time.
+  const size_t super = std::min<size_t>(n, VB_SUPER_BLOBS);
+  const size_t chunks_per_super = (super + (size_t)chunk - 1) / (size_t)chunk;
+  while (c->ev_pool.size() < 2 * chunks_per_super) {
+    cudaEvent_t e;
+    CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_pool.push_back(e);
+  }
+  cudaStream_t cs[2 * NSLOT];
+  for (int i = 0; i < NSLOT; i++) { cs[2 * i] = c->slot[i].st; cs[2 * i + 1] = c->slot[i].aux; }
+  auto sync_all = [&]() -> bool {
+    CU_TRY(cudaStreamSynchronize(c->copy_st));
+    for (auto st : cs) CU_TRY(cudaStreamSynchronize(st));
+    return true;
+  };
+  static const bool trace = getenv("LWKZG_VERIFY_TRACE") != nullptr;
+  cudaEvent_t tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> trace_chunks;
+  if (trace) {
+    for (auto& e : tr) cudaEventCreate(&e);
+    cudaEventRecord(tr[0], c->copy_st);
+    cudaEventRecord(tr[3], s0);   // end of point decompression (s0 has only that queued so far)
+  }
   size_t k = 0;
   int hashed_blocks = 0;   // 64-byte blocks of the batch-challenge message absorbed so far
-  for (size_t off = 0; off < n; off += chunk, k++) {
-    int m = (int)std::min<size_t>(chunk, n - off);
-    Slot& sl = c->slot[k % NSLOT];
-    if (&sl != &c->slot[0] || k >= (size_t)NSLOT) CU_TRY(cudaStreamSynchronize(sl.st));
-    if (!slot_reserve(sl, m, 1, true)) return false;
-    CU_TRY(cudaMemcpyAsync(sl.blobs.p, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, sl.st));
-    CU_TRY(cudaEventRecord(sl.ev_fork, sl.st));
-    CU_TRY(cudaStreamWaitEvent(sl.aux, sl.ev_fork, 0));
-    launch_challenge_midstate(sl.states.p, sl.blobs.p, m, sl.aux, true);
-    CU_TRY(cudaEventRecord(sl.ev_aux, sl.aux));
-    CU_TRY(cudaStreamWaitEvent(sl.st, sl.ev_aux, 0));
-    CU_TRY(cudaStreamWaitEvent(sl.st, c->slot[0].ev_in, 0));
-    if (le) {
-      CU_TRY(cudaMemsetAsync(sl.status2.p, 0, (size_t)m * sizeof(int), sl.st));
-      launch_le_blob_check((int*)sl.status2.p, sl.blobs.p, m, sl.st);
-      launch_status_or((int*)c->vb_status.p + off, (const int*)sl.status2.p, m, sl.st);
-      launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, sl.states.p, sl.blobs.p, (const uint8_t*)c->vb_cin.p + off * 48, m, sl.st, true);
-      launch_le_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, sl.blobs.p, (const uint8_t*)c->vb_z.p + off * 32, c->d_roots, m, sl.st);
-    } else {
-      launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, sl.states.p, sl.blobs.p, (const uint8_t*)c->vb_c48r.p + off * 48, m, sl.st);
-      launch_poly_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, sl.blobs.p, (const uint8_t*)c->vb_z.p + off * 32, m, sl.st);
-    }
-    launch_make_tuples((uint8_t*)c->vb_tuples.p + off * 160, (const uint8_t*)c->vb_c48r.p + off * 48, (const uint8_t*)c->vb_z.p + off * 32,
-                       (const uint8_t*)c->vb_y.p + off * 32, (const uint8_t*)c->vb_p48r.p + off * 48, m, sl.st, le);
-    if (hash_r) {
-      // chunks reach the hash stream in order; each launch absorbs the blocks its chunk completed
-      CU_TRY(cudaEventRecord(sl.ev_done, sl.st));
-      CU_TRY(cudaStreamWaitEvent(c->hash_st, sl.ev_done, 0));
-      const bool last = off + (size_t)m >= n;
-      const int ready = batch_challenge_blocks_ready(off + (size_t)m);
-      launch_batch_challenge_part(c->vb_r.p, c->vb_hstate.p, c->vb_tuples.p, n, hashed_blocks, ready, k == 0, last, c->hash_st, le);
-      hashed_blocks = ready;
+  for (size_t base = 0; base < n; base += super) {
+    if (base > 0 && !sync_all()) return false;   // the staging area is about to be overwritten
+    const size_t top = std::min(n, base + super);
+    size_t j = 0;
+    for (size_t off = base; off < top; off += chunk, k++, j++) {
+      const int m = (int)std::min<size_t>(chunk, top - off);
+      uint8_t* d_blobs = (uint8_t*)c->vb_blobs.p + (off - base) * BLOB_BYTES;
+      void* d_states = (uint8_t*)c->vb_states.p + off * 32;
+      cudaEvent_t ev_copied = c->ev_pool[2 * j], ev_tuples = c->ev_pool[2 * j + 1];
+      cudaStream_t st = cs[k % (2 * NSLOT)];
+      CU_TRY(cudaMemcpyAsync(d_blobs, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, c->copy_st));
+      CU_TRY(cudaEventRecord(ev_copied, c->copy_st));
+      CU_TRY(cudaStreamWaitEvent(st, ev_copied, 0));
+      cudaEvent_t tc[3] = {nullptr, nullptr, nullptr};
+      // (measured: a hash kernel that starts while the two decompression kernels are still running takes 9-15 ms
+      // instead of 2.7 -- so every chunk waits for them, ~2 ms after the call began, before anything else)
+      // (small batches use the warp-per-blob hash, which does not show this, and want the overlap)
+      if (n > 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
+      if (trace) { for (auto& e : tc) cudaEventCreate(&e); cudaEventRecord(tc[0], st); }
+      launch_challenge_midstate(d_states, d_blobs, m, st, true);
+      if (trace) cudaEventRecord(tc[1], st);
+      if (n <= 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
+      if (le) {
+        int* st2 = (int*)c->vb_status2.p + off;
+        CU_TRY(cudaMemsetAsync(st2, 0, (size_t)m * sizeof(int), st));
+        launch_le_blob_check(st2, d_blobs, m, st);
+        launch_status_or((int*)c->vb_status.p + off, st2, m, st);
+        launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, d_states, d_blobs, (const uint8_t*)c->vb_cin.p + off * 48, m, st, true);
+        launch_le_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, d_blobs, (const uint8_t*)c->vb_z.p + off * 32, c->d_roots, m, st);
+      } else {
+        launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, d_states, d_blobs, (const uint8_t*)c->vb_c48r.p + off * 48, m, st);
+        launch_poly_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, d_blobs, (const uint8_t*)c->vb_z.p + off * 32, m, st);
+      }
+      launch_make_tuples((uint8_t*)c->vb_tuples.p + off * 160, (const uint8_t*)c->vb_c48r.p + off * 48, (const uint8_t*)c->vb_z.p + off * 32,
+                         (const uint8_t*)c->vb_y.p + off * 32, (const uint8_t*)c->vb_p48r.p + off * 48, m, st, le);
+      if (trace) { cudaEventRecord(tc[2], st); for (auto e : tc) trace_chunks.push_back(e); }
+      if (hash_r) {
+        // chunks reach the hash stream in order; each launch absorbs the blocks its chunk completed
+        CU_TRY(cudaEventRecord(ev_tuples, st));
+        CU_TRY(cudaStreamWaitEvent(c->hash_st, ev_tuples, 0));
+        const bool last = off + (size_t)m >= n;
+        const int ready = batch_challenge_blocks_ready(off + (size_t)m);
+        launch_batch_challenge_part(c->vb_r.p, c->vb_hstate.p, c->vb_tuples.p, n, hashed_blocks, ready, k == 0, last, c->hash_st, le);
+        hashed_blocks = ready;
+      }
     }
   }
-  for (auto& sl : c->slot) {
-    CU_TRY(cudaStreamSynchronize(sl.st));
-    CU_TRY(cudaStreamSynchronize(sl.aux));
+  if (trace) { cudaEventRecord(tr[1], c->copy_st); cudaEventRecord(tr[2], c->hash_st); cudaEventRecord(tr[4], cs[(k - 1) % (2 * NSLOT)]); }
+  if (!sync_all()) return false;
+  if (trace) {
+    cudaStreamSynchronize(c->hash_st);
+    float a = 0, b = 0, d = 0, e = 0;
+    cudaEventElapsedTime(&a, tr[0], tr[1]);
+    cudaEventElapsedTime(&b, tr[0], tr[2]);
+    cudaEventElapsedTime(&d, tr[0], tr[3]);
+    cudaEventElapsedTime(&e, tr[0], tr[4]);
+    fprintf(stderr, "[lwkzg] prepare n=%zu: decompress done at %.2f ms, copies done at %.2f ms, last chunk's tuples at %.2f ms, challenge hash done at %.2f ms\n", n, d, a, e, b);
+    for (size_t q = 0; q + 2 < trace_chunks.size() + 0 && n > 1; q += 3) {
+      float x = 0, y = 0, z = 0;
+      cudaEventElapsedTime(&x, tr[0], trace_chunks[q]);
+      cudaEventElapsedTime(&y, tr[0], trace_chunks[q + 1]);
+      cudaEventElapsedTime(&z, tr[0], trace_chunks[q + 2]);
+      fprintf(stderr, "[lwkzg]   chunk %zu: hash starts %.2f, hash done %.2f, tuples %.2f\n", q / 3, x, y, z);
+    }
+    for (auto e : trace_chunks) cudaEventDestroy(e);
+    for (auto& ev : tr) cudaEventDestroy(ev);
   }
   if (hash_r) CU_TRY(cudaStreamSynchronize(c->hash_st));
   CU_TRY(cudaGetLastError());
@@ -1056,11 +1124,14 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
   memcpy(zy + 32, y_bytes, 32);
   bool good = [&]() -> bool {
     CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitment_bytes, 48, cudaMemcpyHostToDevice, s0));
-    CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proof_bytes, 48, cudaMemcpyHostToDevice, s0));
+    CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proof_bytes, 48, cudaMemcpyHostToDevice, c->hash_st));
     CU_TRY(cudaMemcpyAsync(c->vb_zy_in.p, zy, 64, cudaMemcpyHostToDevice, s0));
     const bool le = c->mode == 1;
+    // the two point decompressions (sqrt + subgroup check, ~2 ms each on one thread) run side by side
     launch_g1_decompress(c->vb_caff.p, nullptr, (int*)c->vb_status.p, c->vb_cin.p, 1, s0, le);
-    launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, s0, le);
+    launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, c->hash_st, le);
+    CU_TRY(cudaEventRecord(c->ev_hash, c->hash_st));
+    CU_TRY(cudaStreamWaitEvent(s0, c->ev_hash, 0));
     launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, 1, s0);
     if (le) {
       CU_TRY(cudaMemsetAsync(c->vb_tuples.p, 0, 2 * sizeof(int), s0));
@@ -1117,11 +1188,16 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
+  static const bool trace = getenv("LWKZG_VERIFY_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   if (!verify_prepare(c, blobs, commitments_bytes, proofs_bytes, n, true)) return C_KZG_ERROR;  // leaves r in vb_r
+  const double t1 = now();
   bool bad = false;
   if (!any_bad_status(c, n, bad)) return C_KZG_ERROR;
   if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  const double t2 = now();
   cudaStream_t s0 = c->slot[0].st;
   launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, 0, (int)n, c->vb_scratch.p, s0);
   launch_batch_final((int*)c->vb_ok.p, c->vb_partial.p, 1, c->d_prep0, c->d_prep1, s0);
@@ -1131,6 +1207,7 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
     set_err("CUDA failure in batch verification");
     return C_KZG_ERROR;
   }
+  if (trace) fprintf(stderr, "[lwkzg] verify batch n=%zu: prepare %.2f ms, status %.2f ms, partials+pairing %.2f ms\n", n, t1 - t0, t2 - t1, now() - t2);
   *ok = okv != 0;
   return C_KZG_OK;
 }
