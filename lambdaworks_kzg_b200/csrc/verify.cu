@@ -226,17 +226,19 @@ __device__ __forceinline__ void block_reduce_xyzz(G1Xyzz& acc, uint32_t* red) {
 
 constexpr int BV_THREADS = 64;
 
-// grid = (blocks, 3).  which = blockIdx.y:
+// grid = (blocks, 6).  which = blockIdx.y % 3:
 //   0: sum r^i pi_i      1: sum (r^i z_i) pi_i      2: sum r^i C_i - (sum r^i y_i) G
-// One thread per blob (double-and-add by a 255-bit scalar), block tree, one
-// XYZZ partial per block into scratch[which][block].
+// half = blockIdx.y / 3: the GLV split k = q x^2 + m turns every scalar multiplication into two independent
+// 128-bit ones ([m]P and [q](beta x, -y)); the kernel is bound by the latency of one thread's double-and-add
+// chain, so the halves go to different threads (192 instead of 256 sequential group operations each).
+// Block tree, one XYZZ partial per block into scratch[blockIdx.y][block].
 __global__ void __launch_bounds__(BV_THREADS) batch_partials_kernel(G1Xyzz* __restrict__ scratch, const uint32_t* __restrict__ r_in,
                                                                      const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
                                                                      const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
                                                                      unsigned long long first, int n_local) {
   __shared__ uint32_t red[48 * (BV_THREADS / 2)];
   __shared__ uint32_t ysum[BV_THREADS][8];
-  const int which = blockIdx.y;
+  const int which = blockIdx.y % 3, half = blockIdx.y / 3;
   const int i = blockIdx.x * BV_THREADS + threadIdx.x;
   G1Xyzz acc = xyzz_inf();
   Fr ys = fr_zero();  // canonical
@@ -267,26 +269,40 @@ __global__ void __launch_bounds__(BV_THREADS) batch_partials_kernel(G1Xyzz* __re
       base = c_aff[i];
       Fr yc;
       for (int k = 0; k < 8; k++) yc.l[k] = y[i * 8 + k];
-      ys = fr_mul(pw, yc);  // canonical r^i y_i
+      if (half == 0) ys = fr_mul(pw, yc);  // canonical r^i y_i
     }
-    acc = g1_mul_scalar_glv(base, sc.l);   // sc is canonical (< r): GLV split, 128 instead of 255 doublings
+    // sc is canonical (< r): [sc]P = [m]P + [q](beta x, -y), 128 doublings each
+    if (!g1a_is_inf(base)) {
+      uint32_t q4[4], m4[4];
+      glv_split(q4, m4, sc.l);
+      if (half == 0) {
+        acc = g1_mul_scalar(base, m4, 4);
+      } else {
+        Fp beta;
+        for (int k = 0; k < 12; k++) beta.l[k] = k::FP_BETA[k];
+        G1Affine p2;
+        p2.x = fp_mul(base.x, beta);
+        p2.y = fp_neg(base.y);
+        acc = g1_mul_scalar(p2, q4, 4);
+      }
+    }
   }
-  if (which == 2) {
+  if (which == 2 && half == 0) {
     for (int k = 0; k < 8; k++) ysum[threadIdx.x][k] = ys.l[k];
   }
   block_reduce_xyzz<BV_THREADS>(acc, red);
   if (threadIdx.x == 0) {
-    if (which == 2) {
+    if (which == 2 && half == 0) {
       Fr tot = fr_zero();
       for (int t = 0; t < BV_THREADS; t++) {
         Fr v;
         for (int k = 0; k < 8; k++) v.l[k] = ysum[t][k];
         tot = fr_add(tot, v);
       }
-      uint32_t* ys_out = reinterpret_cast<uint32_t*>(scratch + (size_t)3 * gridDim.x) + (size_t)blockIdx.x * 8;
+      uint32_t* ys_out = reinterpret_cast<uint32_t*>(scratch + (size_t)6 * gridDim.x) + (size_t)blockIdx.x * 8;
       for (int k = 0; k < 8; k++) ys_out[k] = tot.l[k];
     }
-    scratch[(size_t)which * gridDim.x + blockIdx.x] = acc;
+    scratch[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
   }
 }
 
@@ -297,16 +313,29 @@ __global__ void __launch_bounds__(BV_THREADS) batch_partials_kernel(G1Xyzz* __re
 __global__ void __launch_bounds__(32) batch_partials_finish_kernel(uint8_t* __restrict__ out288, const G1Xyzz* __restrict__ scratch, int blocks) {
   __shared__ uint32_t red[48 * 16];
   __shared__ uint32_t tot_s[8];
+  __shared__ G1Xyzz part_s[30];
   const int which = threadIdx.x, lane = threadIdx.x;
   G1Xyzz acc = xyzz_inf();
+  // sum w has 2 * blocks partials (both GLV halves): rows w and w + 3 of scratch.  Lanes 10 w .. 10 w + 9 take
+  // every tenth of them, lane w (< 3) then adds the ten pieces.
+  if (lane < 30) {
+    const int w = lane / 10, j = lane % 10;
+    G1Xyzz part = xyzz_inf();
+    for (int b = j; b < 2 * blocks; b += 10) {
+      G1Xyzz o = scratch[(size_t)(b < blocks ? w : w + 3) * blocks + (b < blocks ? b : b - blocks)];
+      xyzz_add_ni(part, o);
+    }
+    part_s[lane] = part;
+  }
+  __syncwarp();
   if (which < 3) {
-    for (int b = 0; b < blocks; b++) {
-      G1Xyzz o = scratch[(size_t)which * blocks + b];
+    for (int j = 0; j < 10; j++) {
+      G1Xyzz o = part_s[which * 10 + j];
       xyzz_add_ni(acc, o);
     }
   }
   if (which == 2) {
-    const uint32_t* ys = reinterpret_cast<const uint32_t*>(scratch + (size_t)3 * blocks);
+    const uint32_t* ys = reinterpret_cast<const uint32_t*>(scratch + (size_t)6 * blocks);
     Fr tot = fr_zero();
     for (int b = 0; b < blocks; b++) {
       Fr v;
@@ -432,13 +461,13 @@ void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples1
 size_t batch_partials_scratch_bytes(int n_local) {
   size_t blocks = (size_t)((n_local + BV_THREADS - 1) / BV_THREADS);
   if (blocks < 1) blocks = 1;
-  return blocks * (3 * sizeof(G1Xyzz) + 32);
+  return blocks * (6 * sizeof(G1Xyzz) + 32);
 }
 void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
                            size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st) {
   int blocks = (n_local + BV_THREADS - 1) / BV_THREADS;
   if (blocks < 1) blocks = 1;
-  dim3 grid(blocks, 3);
+  dim3 grid(blocks, 6);
   batch_partials_kernel<<<grid, BV_THREADS, 0, st>>>((G1Xyzz*)d_scratch_xyzz, (const uint32_t*)d_r, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff,
                                                     (const uint32_t*)d_z, (const uint32_t*)d_y, (unsigned long long)first, n_local);
   batch_partials_finish_kernel<<<1, 32, 0, st>>>((uint8_t*)d_partial288, (const G1Xyzz*)d_scratch_xyzz, blocks);
