@@ -215,7 +215,8 @@ int lwkzg_window_bits(const KZGSettings *s);
  * "msm_algo" (1 = default: batches of at least "msm_ba_min_blobs" (256) blobs use
  * the batched-affine MSM kernel, smaller ones the XYZZ kernel; 0 = XYZZ only;
  * both give identical bytes), "msm_ba_variant" (tuning: accumulators per thread
- * x threads per blob, see csrc/msm.cu), "mode": 0 =
+ * x threads per blob, see csrc/msm.cu), "verify_super_blobs" (blobs of a batched
+ * verification staged on the device at a time, default 16384 = 2 GiB), "mode": 0 =
  * MODE_REFERENCE (default: exactly what lambdaworks_kzg computes -- big-endian
  * scalars reduced mod r, blob = monomial coefficients, every failure
  * C_KZG_ERROR), 1 = MODE_CKZG_LE (the little-endian-era c-kzg-4844 semantics of
@@ -227,6 +228,11 @@ int lwkzg_window_bits(const KZGSettings *s);
  * Returns 0 on success. */
 int lwkzg_set_option(const char *name, long value);
 long lwkzg_get_option(const char *name);
+
+/* Test hook: the batch challenge r = H(domain || 4096 || n || tuples) mod r (utils.rs:166-206) that the last
+ * verify_blob_kzg_proof_batch / lwkzg_verify_batch_phase2 on these settings derived, as 32 little-endian
+ * bytes.  The monolithic hash (phase 2) and the chunk-by-chunk one (single-GPU batch) must agree. */
+C_KZG_RET lwkzg_debug_batch_challenge(uint8_t *out32, const KZGSettings *s);
 
 /* kernels launched by this library since load (the bench's gpu_launches) */
 uint64_t lwkzg_kernel_launches(void);

@@ -41,6 +41,7 @@ from .api import (  # noqa: F401
     set_option,
     synth_blob_host,
     synth_blobs_device,
+    debug_batch_challenge,
     verify_batch_phase1,
     verify_batch_phase2,
     verify_batch_phase3,

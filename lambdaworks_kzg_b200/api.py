@@ -68,6 +68,7 @@ def load_library() -> ctypes.CDLL:
         "lwkzg_verify_batch_phase1": [vp, vp, vp, vp, sz, sp],
         "lwkzg_verify_batch_phase2": [vp, vp, sz, sz, sz, sp],
         "lwkzg_verify_batch_phase3": [bp, vp, sz, sp],
+        "lwkzg_debug_batch_challenge": [vp, sp],
         "lwkzg_synth_blobs_device": [vp, ctypes.c_uint64, sz, vp],
         "lwkzg_synth_blob_host": [vp, ctypes.c_uint64],
         "lwkzg_set_option": [ctypes.c_char_p, ctypes.c_long],
@@ -331,6 +332,13 @@ def synth_blob_host(k: int) -> bytes:
 
 
 # ------------------------------------------------------------------ multi-GPU verification phases
+def debug_batch_challenge(s) -> int:
+    """The batch challenge r left by the last batched verification / phase 2 on these settings (test hook)."""
+    out = ctypes.create_string_buffer(32)
+    _check(load_library().lwkzg_debug_batch_challenge(out, _sp(s)), "lwkzg_debug_batch_challenge")
+    return int.from_bytes(out.raw, "little")
+
+
 def verify_batch_phase1(blobs: bytes, commitments: bytes, proofs: bytes, n_local: int, s) -> bytes:
     out = ctypes.create_string_buffer(160 * max(n_local, 1))
     _check(load_library().lwkzg_verify_batch_phase1(out, blobs, commitments, proofs, n_local, _sp(s)), "lwkzg_verify_batch_phase1")

@@ -48,6 +48,7 @@ struct Options {
   long chunk_blobs = 256;
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
   long msm_ba_min_blobs = 256;
+  long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode)
   Options() {
     if (const char* e = getenv("LWKZG_MODE")) mode = atol(e);
@@ -797,9 +798,13 @@ C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, si
 }
 
 // ------------------------------------------------------------------ verification
-// blobs of a batched verification are staged on the device VB_SUPER_BLOBS at a time (2 GiB)
-constexpr size_t VB_SUPER_BLOBS = 16384;
+// blobs of a batched verification are staged on the device "verify_super_blobs" at a time (default 16384 = 2 GiB)
+size_t vb_super_blobs() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return (size_t)std::max(1L, opts().verify_super_blobs);
+}
 bool vb_reserve(Ctx* c, size_t n) {
+  const size_t VB_SUPER_BLOBS = vb_super_blobs();
   return c->vb_cin.ensure(n * 48) && c->vb_pin.ensure(n * 48) && c->vb_caff.ensure(n * AFFINE_BYTES) && c->vb_piaff.ensure(n * AFFINE_BYTES) &&
          c->vb_c48r.ensure(n * 48) && c->vb_p48r.ensure(n * 48) && c->vb_z.ensure(n * 32) && c->vb_y.ensure(n * 32) && c->vb_tuples.ensure(n * 160) &&
          c->vb_status.ensure(n * sizeof(int)) && c->vb_r.ensure(32) && c->vb_partial.ensure(288) && c->vb_ok.ensure(sizeof(int)) &&
@@ -841,7 +846,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   // buffer: one copy stream issues the H2D copies back to back, and each chunk's kernels (SHA midstate ->
   // challenge -> evaluation -> tuple) start on one of 2 * NSLOT compute streams as soon as its copy has landed.
   // The copy engine is the only thing that runs the whole time.
-  const size_t super = std::min<size_t>(n, VB_SUPER_BLOBS);
+  const size_t super = std::min<size_t>(n, vb_super_blobs());
   const size_t chunks_per_super = (super + (size_t)chunk - 1) / (size_t)chunk;
   while (c->ev_pool.size() < 2 * chunks_per_super) {
     cudaEvent_t e;
@@ -988,6 +993,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
   if (n == "msm_algo") { if (value != 0 && value != 1) return 1; opts().msm_algo = value; return 0; }
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
+  if (n == "verify_super_blobs") { if (value < 1) return 1; opts().verify_super_blobs = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value > 7) return 1; msm_ba_set_variant((int)value); return 0; }
   return 1;
 }
@@ -1000,6 +1006,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "mode") return opts().mode;
   if (n == "msm_algo") return opts().msm_algo;
   if (n == "msm_ba_min_blobs") return opts().msm_ba_min_blobs;
+  if (n == "verify_super_blobs") return opts().verify_super_blobs;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel
   if (n == "msm_ba_slots") return msm_ba_slots();       // read-only: affine accumulators per thread
   return -1;
@@ -1302,6 +1309,15 @@ double lwkzg_bench_msm_kernel(const void* d_blobs, size_t n, int blocks_per_blob
   cudaEventDestroy(e1);
   if (cudaGetLastError() != cudaSuccess) return -1.0;
   return (double)ms / iters;
+}
+// test hook: the batch challenge r (canonical, 8 little-endian u32) left in the workspace by the last batched
+// verification / phase 2 on these settings
+C_KZG_RET lwkzg_debug_batch_challenge(uint8_t* out32, const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  if (!c || !out32 || !c->vb_r.p) return C_KZG_ERROR;
+  CtxLock L(c);
+  if (cudaMemcpy(out32, c->vb_r.p, 32, cudaMemcpyDeviceToHost) != cudaSuccess) { set_err("D2H failed"); return C_KZG_ERROR; }
+  return C_KZG_OK;
 }
 int lwkzg_window_bits(const KZGSettings* s) {
   Ctx* c = ctx_of(s);

@@ -344,6 +344,48 @@ def test_batch_verify_outcomes(lw, settings8, ref):
         assert lw.verify_batch_phase3(b"".join(parts), world, settings8) is True
 
 
+@pytest.mark.parametrize("n,super_blobs,chunk", [(67, 16384, 256), (130, 64, 256), (300, 128, 50)])
+def test_batch_verify_staged_pipeline(lw, settings8, n, super_blobs, chunk):
+    """Large-batch verification path: group SHA-256 kernel with a batch size that is not a multiple of its 8 blobs
+    per warp, several staging super-batches with a partial last one, odd chunk sizes, and the batch challenge r
+    absorbed chunk by chunk -- r is checked against hashlib over the tuples (utils.rs:166-206) and against the
+    monolithic hash of the multi-GPU phase 2."""
+    import hashlib
+
+    blobs = [lw.synth_blob_host(5000 + k) for k in range(n)]
+    flat = b"".join(blobs)
+    coms, proofs, st = lw.commit_and_prove_batch(flat, n, settings8)
+    assert st == [0] * n
+    p2, st2 = lw.compute_blob_kzg_proof_batch(flat, b"".join(coms), n, settings8)   # hash not hidden under an MSM here
+    assert st2 == [0] * n and p2 == proofs
+    lw.set_option("verify_super_blobs", super_blobs)
+    lw.set_option("chunk_blobs", chunk)
+    try:
+        assert lw.verify_blob_kzg_proof_batch(blobs, coms, proofs, settings8) is True
+        r_chunked = lw.debug_batch_challenge(settings8)
+        tuples = lw.verify_batch_phase1(flat, b"".join(coms), b"".join(proofs), n, settings8)
+        assert len(tuples) == 160 * n and tuples[:48] == coms[0] and tuples[112:160] == proofs[0]
+        msg = b"RCKZGBATCH___V1_" + (4096).to_bytes(8, "little") + n.to_bytes(8, "little") + tuples
+        expect = int.from_bytes(hashlib.sha256(msg).digest(), "big") % R
+        assert r_chunked == expect
+        part = lw.verify_batch_phase2(tuples, n, 0, n, settings8)
+        assert lw.debug_batch_challenge(settings8) == expect
+        assert lw.verify_batch_phase3(part, 1, settings8) is True
+        bad = list(proofs)
+        bad[n - 1] = coms[0]
+        assert lw.verify_blob_kzg_proof_batch(blobs, coms, bad, settings8) is False
+        bad = list(proofs)
+        bad[0], bad[1] = bad[1], bad[0]
+        assert lw.verify_blob_kzg_proof_batch(blobs, coms, bad, settings8) is False
+        inval = list(coms)
+        inval[n // 2] = bytes(48)
+        with pytest.raises(lw.KzgError):
+            lw.verify_blob_kzg_proof_batch(blobs, inval, proofs, settings8)
+    finally:
+        lw.set_option("verify_super_blobs", 16384)
+        lw.set_option("chunk_blobs", 256)
+
+
 def test_g1_lincomb(lw, py_setup):
     rnd = random.Random(5)
     n = 37
