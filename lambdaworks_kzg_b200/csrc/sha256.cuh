@@ -45,13 +45,16 @@ LW_INL void sha256_compress(Sha256State& s, uint32_t* w) {
       uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
       w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
     }
-    uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
-    uint32_t ch = (e & f) ^ (~e & g);
-    uint32_t t1 = h + S1 + ch + SHA_K[i] + w[i & 15];
-    uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
-    uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-    uint32_t t2 = S0 + mj;
-    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    // The hash is one dependency chain; written so that the chain through e is three instructions per round
+    // (rotate -> xor3 -> add3): everything that does not need this round's e is summed beforehand.
+    const uint32_t dhk = d + h + (SHA_K[i] + w[i & 15]);
+    const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+    const uint32_t ch = g ^ (e & (f ^ g));
+    const uint32_t e_new = dhk + S1 + ch;                 // d + t1
+    const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+    const uint32_t mj = (a & b) | (c & (a | b));
+    const uint32_t t2md = S0 + mj - d;                    // t2 - d
+    h = g; g = f; f = e; d = c; c = b; b = a; a = e_new + t2md; e = e_new;   // a = t1 + t2
   }
   s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
@@ -62,13 +65,14 @@ LW_INL void sha256_rounds_wk(Sha256State& s, const uint32_t* wk, int b) {
   uint32_t a = s.h[0], bb = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
 #pragma unroll
   for (int i = 0; i < 64; i++) {
-    uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
-    uint32_t ch = (e & f) ^ (~e & g);
-    uint32_t t1 = h + S1 + ch + wk[i * 32 + b];
-    uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
-    uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
-    uint32_t t2 = S0 + mj;
-    h = g; g = f; f = e; e = d + t1; d = c; c = bb; bb = a; a = t1 + t2;
+    const uint32_t dhk = d + h + wk[i * 32 + b];          // off the e-chain (see sha256_compress)
+    const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+    const uint32_t ch = g ^ (e & (f ^ g));
+    const uint32_t e_new = dhk + S1 + ch;
+    const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+    const uint32_t mj = (a & bb) | (c & (a | bb));
+    const uint32_t t2md = S0 + mj - d;
+    h = g; g = f; f = e; d = c; c = bb; bb = a; a = e_new + t2md; e = e_new;
   }
   s.h[0] += a; s.h[1] += bb; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
