@@ -29,6 +29,24 @@ for mode in (0, 1):
     p, y = lw.compute_kzg_proof(blobs[1], z, s)
     assert lw.verify_kzg_proof(coms[1], z, y, p, s) is True
     assert lw.verify_kzg_proof(coms[1], z, y, proofs[0], s) is False
+    # the large-batch verification pipeline at a small size: group SHA kernel (n > 64, n % 8 != 0), several staging
+    # super-batches with a partial last one, odd chunks, chunk-by-chunk batch challenge; blob proofs for given commitments
+    n2 = int(os.environ.get("SAN_VERIFY_BLOBS", "70"))
+    blobs2 = [lw.synth_blob_host(100 + k) for k in range(n2)]
+    if mode == 1:
+        blobs2 = [b"".join(b[i:i + 32][::-1] for i in range(0, len(b), 32)) for b in blobs2]
+    c2, p2, st2 = lw.commit_and_prove_batch(b"".join(blobs2), n2, s)
+    assert st2 == [0] * n2
+    p3, st3 = lw.compute_blob_kzg_proof_batch(b"".join(blobs2), b"".join(c2), n2, s)
+    assert st3 == [0] * n2 and p3 == p2
+    lw.set_option("verify_super_blobs", 32)
+    lw.set_option("chunk_blobs", 20)
+    assert lw.verify_blob_kzg_proof_batch(blobs2, c2, p2, s) is True
+    bad = list(p2); bad[-1] = c2[0]
+    assert lw.verify_blob_kzg_proof_batch(blobs2, c2, bad, s) is False
+    lw.set_option("verify_super_blobs", 16384)
+    lw.set_option("chunk_blobs", 256)
+    assert lw.verify_blob_kzg_proof_batch(blobs2, c2, p2, s) is True
     s.free()
 lw.set_option("mode", 0)
 pts = bytes(96) + b"".join(bytes.fromhex("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1") for _ in range(40))
