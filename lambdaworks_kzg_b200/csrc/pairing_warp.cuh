@@ -23,6 +23,7 @@ struct WarpFp12 {
 };
 struct WarpScratch {
   Fp2 prod[18];
+  Fp2 coef[9];   // coefficient i of the k-th Fp6 product at coef[3 k + i]
 };
 
 // ---- phase 1 of dst = a * b: lane L < 18 computes one Karatsuba product
@@ -30,11 +31,20 @@ LW_COLD void wfp12_mul_phase1(WarpScratch& sc, const WarpFp12& a, const WarpFp12
   if (lane >= 18) return;
   const int k = lane / 6, m = lane % 6;
   const int sel = (m == 0) ? 1 : (m == 1) ? 2 : (m == 2) ? 4 : (m == 3) ? 6 : (m == 4) ? 3 : 5;  // subset of {x0,x1,x2}
+  // A, B = sums of the selected coefficients; the first term is copied, not added to zero (the additions are on
+  // the critical path of every Fp12 product)
   Fp2 A = fp2_zero(), B = fp2_zero();
+  bool first = true;
   for (int i = 0; i < 3; i++) {
     if (!((sel >> i) & 1)) continue;
-    if (k == 0 || k == 2) { A = fp2_add(A, a.c[i]); B = fp2_add(B, b.c[i]); }
-    if (k == 1 || k == 2) { A = fp2_add(A, a.c[3 + i]); B = fp2_add(B, b.c[3 + i]); }
+    if (k == 0 || k == 2) {
+      if (first) { A = a.c[i]; B = b.c[i]; first = false; }
+      else { A = fp2_add(A, a.c[i]); B = fp2_add(B, b.c[i]); }
+    }
+    if (k == 1 || k == 2) {
+      if (first) { A = a.c[3 + i]; B = b.c[3 + i]; first = false; }
+      else { A = fp2_add(A, a.c[3 + i]); B = fp2_add(B, b.c[3 + i]); }
+    }
   }
   sc.prod[lane] = fp2_mul(A, B);
 }
@@ -45,19 +55,24 @@ LW_COLD Fp2 wfp6_coeff(const WarpScratch& sc, int k, int i) {
   if (i == 1) return fp2_add(fp2_sub(fp2_sub(v[4], v[0]), v[1]), fp2_mul_xi(v[2]));
   return fp2_add(fp2_sub(fp2_sub(v[5], v[0]), v[2]), v[1]);
 }
-// ---- phase 2: lane o < 6 writes output coefficient o
-LW_COLD void wfp12_mul_phase2(WarpFp12& dst, const WarpScratch& sc, int lane) {
+// ---- phase 2a: lane L < 9 recombines coefficient L % 3 of Fp6 product L / 3 (nine lanes instead of each of the six
+// output lanes recomputing up to three of them)
+LW_COLD void wfp12_mul_phase2a(WarpScratch& sc, int lane) {
+  if (lane >= 9) return;
+  sc.coef[lane] = wfp6_coeff(sc, lane / 3, lane % 3);
+}
+// ---- phase 2b: lane o < 6 writes output coefficient o
+LW_COLD void wfp12_mul_phase2b(WarpFp12& dst, const WarpScratch& sc, int lane) {
   if (lane >= 6) return;
   Fp2 r;
   if (lane < 3) {
     // r.c0 = T0 + v * T1,  v * (c0, c1, c2) = (xi c2, c0, c1)
-    Fp2 t0 = wfp6_coeff(sc, 0, lane);
-    Fp2 t1 = wfp6_coeff(sc, 1, (lane + 2) % 3);
+    Fp2 t1 = sc.coef[3 + (lane + 2) % 3];
     if (lane == 0) t1 = fp2_mul_xi(t1);
-    r = fp2_add(t0, t1);
+    r = fp2_add(sc.coef[lane], t1);
   } else {
     int i = lane - 3;  // r.c1 = T2 - T0 - T1
-    r = fp2_sub(fp2_sub(wfp6_coeff(sc, 2, i), wfp6_coeff(sc, 0, i)), wfp6_coeff(sc, 1, i));
+    r = fp2_sub(fp2_sub(sc.coef[6 + i], sc.coef[i]), sc.coef[3 + i]);
   }
   dst.c[lane] = r;
 }
@@ -99,7 +114,9 @@ LW_COLD void wfp12_line_lane(WarpFp12& dst, const G2Line& ln, const G1Affine& p,
 LW_COLD void wfp12_mul(WarpFp12& dst, const WarpFp12& a, const WarpFp12& b, WarpScratch& sc) {
   LW_FOR_LANES(lane) wfp12_mul_phase1(sc, a, b, lane);
   LW_WARP_SYNC();
-  LW_FOR_LANES(lane) wfp12_mul_phase2(dst, sc, lane);
+  LW_FOR_LANES(lane) wfp12_mul_phase2a(sc, lane);
+  LW_WARP_SYNC();
+  LW_FOR_LANES(lane) wfp12_mul_phase2b(dst, sc, lane);
   LW_WARP_SYNC();
 }
 LW_COLD void wfp12_conj(WarpFp12& dst, const WarpFp12& a) {
