@@ -24,10 +24,14 @@ struct WarpFp12 {
 struct WarpScratch {
   Fp2 prod[18];
   Fp2 coef[9];   // coefficient i of the k-th Fp6 product at coef[3 k + i]
+  // the 18 Fp2 products as 54 Fp products (Karatsuba: a0 b0, a1 b1, (a0 + a1)(b0 + b1)): operands and results
+  Fp opa[54], opb[54], pr[54];
 };
 
-// ---- phase 1 of dst = a * b: lane L < 18 computes one Karatsuba product
-LW_COLD void wfp12_mul_phase1(WarpScratch& sc, const WarpFp12& a, const WarpFp12& b, int lane) {
+// ---- phase 1 of dst = a * b: lane L < 18 prepares the operands of one Karatsuba product (1a), all 32 lanes share
+// the 54 Fp multiplications behind the 18 Fp2 products -- two each instead of three in a row (1b) -- and lane L < 18
+// assembles its Fp2 product (1c)
+LW_COLD void wfp12_mul_phase1a(WarpScratch& sc, const WarpFp12& a, const WarpFp12& b, int lane) {
   if (lane >= 18) return;
   const int k = lane / 6, m = lane % 6;
   const int sel = (m == 0) ? 1 : (m == 1) ? 2 : (m == 2) ? 4 : (m == 3) ? 6 : (m == 4) ? 3 : 5;  // subset of {x0,x1,x2}
@@ -46,7 +50,25 @@ LW_COLD void wfp12_mul_phase1(WarpScratch& sc, const WarpFp12& a, const WarpFp12
       else { A = fp2_add(A, a.c[3 + i]); B = fp2_add(B, b.c[3 + i]); }
     }
   }
-  sc.prod[lane] = fp2_mul(A, B);
+  sc.opa[3 * lane] = A.c0;     sc.opb[3 * lane] = B.c0;
+  sc.opa[3 * lane + 1] = A.c1; sc.opb[3 * lane + 1] = B.c1;
+  sc.opa[3 * lane + 2] = fp_add(A.c0, A.c1);
+  sc.opb[3 * lane + 2] = fp_add(B.c0, B.c1);
+}
+LW_COLD void wfp12_mul_phase1b(WarpScratch& sc, int lane) {
+  for (int idx = lane; idx < 54; idx += 32) {
+    Fp t;
+    fp_mul_ni(t, sc.opa[idx], sc.opb[idx]);
+    sc.pr[idx] = t;
+  }
+}
+LW_COLD void wfp12_mul_phase1c(WarpScratch& sc, int lane) {
+  if (lane >= 18) return;
+  const Fp t0 = sc.pr[3 * lane], t1 = sc.pr[3 * lane + 1], t2 = sc.pr[3 * lane + 2];
+  Fp2 r;   // as fp2_mul
+  r.c0 = fp_sub(t0, t1);
+  r.c1 = fp_sub(fp_sub(t2, t0), t1);
+  sc.prod[lane] = r;
 }
 // coefficient i of the k-th Fp6 product from its six Karatsuba pieces
 LW_COLD Fp2 wfp6_coeff(const WarpScratch& sc, int k, int i) {
@@ -112,7 +134,11 @@ LW_COLD void wfp12_line_lane(WarpFp12& dst, const G2Line& ln, const G1Affine& p,
 
 // dst = a * b (dst may alias a and/or b)
 LW_COLD void wfp12_mul(WarpFp12& dst, const WarpFp12& a, const WarpFp12& b, WarpScratch& sc) {
-  LW_FOR_LANES(lane) wfp12_mul_phase1(sc, a, b, lane);
+  LW_FOR_LANES(lane) wfp12_mul_phase1a(sc, a, b, lane);
+  LW_WARP_SYNC();
+  LW_FOR_LANES(lane) wfp12_mul_phase1b(sc, lane);
+  LW_WARP_SYNC();
+  LW_FOR_LANES(lane) wfp12_mul_phase1c(sc, lane);
   LW_WARP_SYNC();
   LW_FOR_LANES(lane) wfp12_mul_phase2a(sc, lane);
   LW_WARP_SYNC();
