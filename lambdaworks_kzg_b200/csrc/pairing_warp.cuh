@@ -18,6 +18,11 @@
 
 namespace lw {
 
+// The cooperating group is one block of LW_PAIR_LANES = 64 threads (two warps): an Fp12 product is 54 independent Fp
+// products, and with 64 lanes they are ONE multiplication deep.  Every function below must be called by all 64
+// threads of the block with the same arguments (the phases are separated by block barriers).
+constexpr int LW_PAIR_LANES = 64;
+
 struct WarpFp12 {
   Fp2 c[6];
 };
@@ -28,9 +33,9 @@ struct WarpScratch {
   Fp opa[54], opb[54], pr[54];
 };
 
-// ---- phase 1 of dst = a * b: lane L < 18 prepares the operands of one Karatsuba product (1a), all 32 lanes share
-// the 54 Fp multiplications behind the 18 Fp2 products -- two each instead of three in a row (1b) -- and lane L < 18
-// assembles its Fp2 product (1c)
+// ---- phase 1 of dst = a * b: lane L < 18 prepares the operands of one Karatsuba product (1a), 54 lanes do one of
+// the 54 Fp multiplications behind the 18 Fp2 products each -- one multiplication deep instead of three (1b) -- and
+// lane L < 18 assembles its Fp2 product (1c)
 LW_COLD void wfp12_mul_phase1a(WarpScratch& sc, const WarpFp12& a, const WarpFp12& b, int lane) {
   if (lane >= 18) return;
   const int k = lane / 6, m = lane % 6;
@@ -56,7 +61,7 @@ LW_COLD void wfp12_mul_phase1a(WarpScratch& sc, const WarpFp12& a, const WarpFp1
   sc.opb[3 * lane + 2] = fp_add(B.c0, B.c1);
 }
 LW_COLD void wfp12_mul_phase1b(WarpScratch& sc, int lane) {
-  for (int idx = lane; idx < 54; idx += 32) {
+  for (int idx = lane; idx < 54; idx += LW_PAIR_LANES) {
     Fp t;
     fp_mul_ni(t, sc.opa[idx], sc.opb[idx]);
     sc.pr[idx] = t;
@@ -126,10 +131,10 @@ LW_COLD void wfp12_line_lane(WarpFp12& dst, const G2Line& ln, const G1Affine& p,
 
 #if defined(LWKZG_HOST_EMUL)
 #define LW_WARP_SYNC()
-#define LW_FOR_LANES(lane) for (int lane = 0; lane < 32; lane++)
+#define LW_FOR_LANES(lane) for (int lane = 0; lane < LW_PAIR_LANES; lane++)
 #else
-#define LW_WARP_SYNC() __syncwarp()
-#define LW_FOR_LANES(lane) for (int lane = (int)(threadIdx.x & 31), _once = 1; _once; _once = 0)
+#define LW_WARP_SYNC() __syncthreads()
+#define LW_FOR_LANES(lane) for (int lane = (int)threadIdx.x, _once = 1; _once; _once = 0)
 #endif
 
 // dst = a * b (dst may alias a and/or b)

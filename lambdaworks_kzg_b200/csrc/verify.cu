@@ -54,9 +54,9 @@ __global__ void g2_check_kernel(int* __restrict__ bad, const uint32_t* __restric
   bad[i] = g2a_on_curve(q) ? 0 : 1;
 }
 
-// ---- two-pairing check, warp-cooperative (pairing_warp.cuh): every Fp12 product is
-// spread over 18 lanes.  `pts` (2 points) and `m` live in shared memory; all 32
-// lanes of the block's single warp must call this.
+// ---- two-pairing check, block-cooperative (pairing_warp.cuh): every Fp12 product is
+// spread over the lanes.  `pts` (2 points) and `m` live in shared memory; all
+// LW_PAIR_LANES threads of the block must call this.
 __device__ __forceinline__ bool two_pairing_check(const G1Affine* pts, const G2Prepared* prep0, const G2Prepared* prep1, WarpPairingMem& m) {
   const G2Prepared* qs[2] = {prep0, prep1};
   warp_pairing_product(m, pts, qs, 2);
@@ -66,7 +66,7 @@ __device__ __forceinline__ bool two_pairing_check(const G1Affine* pts, const G2P
 }
 
 // ok = [ e(C - y g1_0 + z pi, g2_0) * e(-pi, g2_1) == 1 ]
-__global__ void __launch_bounds__(32) verify_single_kernel(int* __restrict__ ok_out, const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
+__global__ void __launch_bounds__(LW_PAIR_LANES) verify_single_kernel(int* __restrict__ ok_out, const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
                                                             const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
                                                             const G1Affine* __restrict__ g1_0, const G2Prepared* __restrict__ prep0,
                                                             const G2Prepared* __restrict__ prep1, int g1_0_in_subgroup) {
@@ -399,7 +399,7 @@ __device__ __forceinline__ G1Affine affine_from_be96(const uint8_t* b) {
 
 // partials: n_ranks x (proof_lincomb, proof_z_lincomb, c_minus_y_lincomb), canonical BE affine.
 // ok = [ e(c_minus_y + proof_z, g2_0) == e(proof_lincomb, g2_1) ]   (lib.rs:679-691)
-__global__ void __launch_bounds__(32) batch_final_kernel(int* __restrict__ ok_out, const uint8_t* __restrict__ partials, int n_ranks,
+__global__ void __launch_bounds__(LW_PAIR_LANES) batch_final_kernel(int* __restrict__ ok_out, const uint8_t* __restrict__ partials, int n_ranks,
                                                           const G2Prepared* __restrict__ prep0, const G2Prepared* __restrict__ prep1) {
   __shared__ WarpPairingMem sh_m;
   __shared__ G1Affine sh_pts[2];
@@ -434,7 +434,7 @@ void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st)
 }
 void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y, const void* d_g1_0_aff,
                           const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st) {
-  verify_single_kernel<<<1, 32, 0, st>>>(d_ok, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
+  verify_single_kernel<<<1, LW_PAIR_LANES, 0, st>>>(d_ok, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
                                          (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1, g1_0_in_subgroup ? 1 : 0);
   count_launch();
 }
@@ -474,7 +474,7 @@ void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_
   count_launch(2);
 }
 void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const void* d_prep0, const void* d_prep1, cudaStream_t st) {
-  batch_final_kernel<<<1, 32, 0, st>>>(d_ok, (const uint8_t*)d_partials288, n_ranks, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
+  batch_final_kernel<<<1, LW_PAIR_LANES, 0, st>>>(d_ok, (const uint8_t*)d_partials288, n_ranks, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
   count_launch();
 }
 }  // namespace lw
