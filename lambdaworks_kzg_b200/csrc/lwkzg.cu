@@ -879,7 +879,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
       uint8_t* d_blobs = (uint8_t*)c->vb_blobs.p + (off - base) * BLOB_BYTES;
       void* d_states = (uint8_t*)c->vb_states.p + off * 32;
       cudaEvent_t ev_copied = c->ev_pool[2 * j], ev_tuples = c->ev_pool[2 * j + 1];
-      cudaStream_t st = cs[k % (2 * NSLOT)];
+      cudaStream_t st = cs[(k + 1) % (2 * NSLOT)];   // chunk 0 not on s0: its hash runs beside the commitment decompression
       CU_TRY(cudaMemcpyAsync(d_blobs, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, c->copy_st));
       CU_TRY(cudaEventRecord(ev_copied, c->copy_st));
       CU_TRY(cudaStreamWaitEvent(st, ev_copied, 0));
@@ -917,7 +917,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
       }
     }
   }
-  if (trace) { cudaEventRecord(tr[1], c->copy_st); cudaEventRecord(tr[2], c->hash_st); cudaEventRecord(tr[4], cs[(k - 1) % (2 * NSLOT)]); }
+  if (trace) { cudaEventRecord(tr[1], c->copy_st); cudaEventRecord(tr[2], c->hash_st); cudaEventRecord(tr[4], cs[k % (2 * NSLOT)]); }
   if (!sync_all()) return false;
   if (trace) {
     cudaStreamSynchronize(c->hash_st);
