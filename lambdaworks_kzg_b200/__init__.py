@@ -40,6 +40,8 @@ from .api import (  # noqa: F401
     load_trusted_setup_file,
     set_option,
     synth_blob_host,
+    synth_point_dlogs,
+    table_geometry,
     synth_blobs_device,
     debug_batch_challenge,
     verify_batch_phase1,

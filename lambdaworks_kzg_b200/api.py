@@ -321,6 +321,40 @@ def window_bits(s) -> int:
     return int(load_library().lwkzg_window_bits(_sp(s)))
 
 
+_X2 = 0xD201000000010000 ** 2          # BLS12-381: x^2, the GLV split modulus (csrc/recode.cuh)
+_R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def table_geometry(c: int):
+    """(windows, [multiples stored per point for each window]) of the fixed-base digit table for window c --
+    host mirror of csrc/recode.cuh."""
+    w = -(-128 // c)
+    counts = [1 << (c - 1)] * (w - 1) + [((_X2 - 1) >> (c * (w - 1))) + 1]
+    return w, counts
+
+
+def synth_point_dlogs(s, n: int, tau: int) -> List[int]:
+    """Discrete logs (base G, mod r) of the n synthetic points bench_var_msm uses: point t is entry
+    (t * 2654435761) mod entries of the fixed-base table, i.e. d * 2^(c j) * tau^i * G for a monomial setup
+    (csrc/varmsm.cu vm_synth_kernel, csrc/table.cu layout)."""
+    c = window_bits(s)
+    w, counts = table_geometry(c)
+    per_window = 4096 << (c - 1)
+    entries = per_window * (w - 1) + 4096 * counts[-1]
+    tau_pow = [1] * 4096
+    for i in range(1, 4096):
+        tau_pow[i] = tau_pow[i - 1] * tau % _R
+    two_pow = [pow(2, c * j, _R) for j in range(w)]
+    out = []
+    for t in range(n):
+        e = (t * 2654435761) % entries
+        j = min(e // per_window, w - 1)
+        off = e - j * per_window
+        i, d = divmod(off, counts[j])
+        out.append((d + 1) * two_pow[j] * tau_pow[i] % _R)
+    return out
+
+
 def synth_blobs_device(d_blobs: int, first_blob: int, n: int, stream: int = 0):
     _check(load_library().lwkzg_synth_blobs_device(d_blobs, first_blob, n, stream), "lwkzg_synth_blobs_device")
 

@@ -23,8 +23,13 @@ void count_launch(int n = 1);
 void launch_srs_import(void* d_aff_out, const void* d_canon_in, int* d_not_on_curve, int* d_not_in_subgroup, int n, cudaStream_t st);
 // bases[j][i] = 2^(c j) P_i  (affine, Montgomery), j < nwin
 void launch_table_bases(void* d_bases, const void* d_aff, int c, int nwin, int npoints, cudaStream_t st);
-// table[(j*npoints+i) << (c-1) | (d-1)] = d * bases[j][i], d = 1..2^(c-1)
-void launch_table_fill(void* d_table, const void* d_bases, int c, int nwin, int npoints, cudaStream_t st);
+// GLV digit table (csrc/recode.cuh): entry(j, i, d) = ((j*npoints) << (c-1)) + i*cnt_j + (d-1) = d * bases[j][i],
+// cnt_j = 2^(c-1) for j < nwin-1, cnt_top for the (unsigned) top window
+void launch_table_fill(void* d_table, const void* d_bases, int c, int nwin, int npoints, uint32_t cnt_top, cudaStream_t st);
+// window geometry of the table for 128-bit scalar halves (host mirror of csrc/recode.cuh)
+int table_num_windows(int c);
+uint32_t table_top_count(int c);
+unsigned long long table_entries(int c, int npoints);
 
 // ---- fixed-base MSM (msm.cu)
 // scalars: n blobs of 4096 x 32 bytes; be_input: raw big-endian blob words
@@ -39,6 +44,7 @@ void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const vo
 size_t msm_ba_scratch_bytes(int n_blobs);
 int msm_ba_threads();
 int msm_ba_slots();
+int msm_ba_num_variants();
 void msm_ba_set_variant(int v);   // tuning: index into BA_VARIANTS (accumulators per thread x threads per blob), msm.cu
 // sum partials, normalise, compress.  d_aff_out (may be NULL): Montgomery affine.
 void launch_msm_finalize(void* d_out48, void* d_aff_out, const void* d_partials, int parts_per_blob, int n_blobs, cudaStream_t st);

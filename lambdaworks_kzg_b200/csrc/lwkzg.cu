@@ -43,7 +43,7 @@ void set_err(const std::string& s) { tl_err = s; }
   } while (0)
 
 struct Options {
-  long window_bits = 13;
+  long window_bits = 16;     // fixed-base window; shrunk automatically to what free HBM allows
   long msm_blocks_per_blob = 0;
   long chunk_blobs = 256;
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
@@ -53,7 +53,7 @@ struct Options {
   Options() {
     if (const char* e = getenv("LWKZG_MODE")) mode = atol(e);
     if (const char* e = getenv("LWKZG_WINDOW_BITS")) window_bits = atol(e);
-    if (const char* e = getenv("LWKZG_CHUNK_BLOBS")) chunk_blobs = atol(e);
+    if (const char* e = getenv("LWKZG_CHUNK_BLOBS")) chunk_blobs = std::min(std::max(atol(e), 1L), 1L << 20);
     if (const char* e = getenv("LWKZG_MSM_BLOCKS_PER_BLOB")) msm_blocks_per_blob = atol(e);
     if (const char* e = getenv("LWKZG_MSM_ALGO")) msm_algo = atol(e);
     if (const char* e = getenv("LWKZG_MSM_BA_MIN_BLOBS")) msm_ba_min_blobs = atol(e);
@@ -276,23 +276,23 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
     launch_write_generator(c->d_gen, st);
   }
   if (want_c < 4) want_c = 4;
-  if (want_c > 15) want_c = 15;
+  if (want_c > 16) want_c = 16;
   size_t free_b = 0, total_b = 0;
   CU_TRY(cudaMemGetInfo(&free_b, &total_b));
   int cbits = (int)want_c;
   for (;; cbits--) {
-    int nw = 255 / cbits + 1;
-    size_t need = ((size_t)nw * N_POINTS << (cbits - 1)) * AFFINE_BYTES;
-    if (need + (size_t(6) << 30) <= free_b || cbits <= 4) break;
+    const size_t need = (size_t)table_entries(cbits, N_POINTS) * AFFINE_BYTES;
+    if (need + (size_t(8) << 30) <= free_b || cbits <= 4) break;   // keep room for the batch slots and the verify workspace
   }
   c->c = cbits;
-  c->nwin = 255 / cbits + 1;
-  size_t entries = (size_t)c->nwin * N_POINTS << (cbits - 1);
+  c->nwin = table_num_windows(cbits);
+  const size_t entries = (size_t)table_entries(cbits, N_POINTS);
+  if (entries >= (size_t(1) << 31)) { set_err("table index does not fit 31 bits"); return false; }   // entry | sign << 31 (msm.cu)
   CU_TRY(cudaMalloc(&c->d_table, entries * AFFINE_BYTES));
   void* d_bases = nullptr;
   CU_TRY(cudaMalloc(&d_bases, (size_t)c->nwin * N_POINTS * AFFINE_BYTES));
   launch_table_bases(d_bases, c->d_srs, c->c, c->nwin, N_POINTS, st);
-  launch_table_fill(c->d_table, d_bases, c->c, c->nwin, N_POINTS, st);
+  launch_table_fill(c->d_table, d_bases, c->c, c->nwin, N_POINTS, table_top_count(c->c), st);
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaGetLastError());
   cudaFree(d_bases);
@@ -987,14 +987,14 @@ uint64_t lwkzg_kernel_launches(void) { return lw::launches(); }
 int lwkzg_set_option(const char* name, long value) {
   std::lock_guard<std::mutex> lk(g_mu);
   std::string n(name ? name : "");
-  if (n == "window_bits") { if (value < 4 || value > 15) return 1; opts().window_bits = value; return 0; }
-  if (n == "msm_blocks_per_blob") { if (value < 0 || value > 128 || (value > 32 && (value & (value - 1)))) return 1; opts().msm_blocks_per_blob = value; return 0; }
-  if (n == "chunk_blobs") { if (value < 1) return 1; opts().chunk_blobs = value; return 0; }
+  if (n == "window_bits") { if (value < 4 || value > 16) return 1; opts().window_bits = value; return 0; }
+  if (n == "msm_blocks_per_blob") { if (value < 0 || value > 256 || (value > 64 && (value & (value - 1)))) return 1; opts().msm_blocks_per_blob = value; return 0; }
+  if (n == "chunk_blobs") { if (value < 1 || value > (1 << 20)) return 1; opts().chunk_blobs = value; return 0; }
   if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
   if (n == "msm_algo") { if (value != 0 && value != 1) return 1; opts().msm_algo = value; return 0; }
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
   if (n == "verify_super_blobs") { if (value < 1) return 1; opts().verify_super_blobs = value; return 0; }
-  if (n == "msm_ba_variant") { if (value < 0 || value > 7) return 1; msm_ba_set_variant((int)value); return 0; }
+  if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
   return 1;
 }
 long lwkzg_get_option(const char* name) {
@@ -1340,7 +1340,7 @@ double lwkzg_bench_var_msm(Bytes48* out, size_t n, int iters, uint64_t seed, con
     CU_TRY(cudaMalloc(&d_sc, n * 32));
     CU_TRY(cudaMalloc(&d_scratch, var_msm_scratch_bytes(n)));
     CU_TRY(cudaMalloc(&d_out, 48));
-    unsigned long long entries = (unsigned long long)c->nwin * N_POINTS << (c->c - 1);
+    unsigned long long entries = table_entries(c->c, N_POINTS);
     launch_var_msm_synth(d_pts, d_sc, c->d_table, entries, seed, n, st);
     launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, st);  // warm-up
     cudaEvent_t e0, e1;

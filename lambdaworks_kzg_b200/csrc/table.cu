@@ -4,6 +4,7 @@
 // the fixed-base digit table used by msm.cu.
 #include "g1.cuh"
 #include "kernels.h"
+#include "recode.cuh"
 
 namespace lw {
 
@@ -43,8 +44,11 @@ __global__ void table_bases_kernel(G1Affine* __restrict__ bases, const G1Affine*
   }
 }
 
-// One thread per (window, point): running sum d*B in XYZZ, normalised to
-// affine in batches of TB with Montgomery's simultaneous-inversion trick.
+// Table layout (csrc/recode.cuh): window j < W - 1 holds 2^(c-1) multiples per point, the top window cnt_top:
+//   entry(j, i, d) = ((j * npoints) << (c-1)) + i * cnt_j + (d - 1),  d = 1 .. cnt_j,  value d * 2^(c j) * P_i.
+// One thread per (window, point, segment): a segment is a run of consecutive multiples; it starts from
+// (d0 - 1) * B (one short double-and-add) and continues with the running sum in XYZZ, normalised to affine in
+// batches of TB with Montgomery's simultaneous-inversion trick.
 constexpr int TB = 32;
 
 __device__ __forceinline__ void store_entry(uint4* __restrict__ table, size_t idx, const G1Affine& e) {
@@ -57,26 +61,38 @@ __device__ __forceinline__ void store_entry(uint4* __restrict__ table, size_t id
   p[5] = make_uint4(e.y.l[8], e.y.l[9], e.y.l[10], e.y.l[11]);
 }
 
-__global__ void __launch_bounds__(64) table_fill_kernel(uint4* __restrict__ table, const G1Affine* __restrict__ bases, int c, int n_pairs) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_pairs) return;
-  const G1Affine B = bases[t];
-  const size_t out_base = (size_t)t << (c - 1);
-  const int half = 1 << (c - 1);
+__global__ void __launch_bounds__(64) table_fill_kernel(uint4* __restrict__ table, const G1Affine* __restrict__ bases, int c, int nwin,
+                                                        int npoints, uint32_t cnt_top, int segs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_pairs = nwin * npoints;
+  if (t >= n_pairs * segs) return;
+  const int pair = t % n_pairs, seg = t / n_pairs;   // consecutive threads: consecutive points of one window
+  const int j = pair / npoints, i = pair % npoints;
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t cnt = (j == nwin - 1) ? cnt_top : half;
+  const uint32_t per = (cnt + segs - 1) / segs;
+  const uint32_t d_lo = seg * per, d_hi = min(cnt, d_lo + per);   // multiples d_lo + 1 .. d_hi
+  if (d_lo >= d_hi) return;
+  const G1Affine B = bases[pair];
+  const size_t out_base = (((size_t)j * npoints) << (c - 1)) + (size_t)i * cnt;
   G1Xyzz acc = xyzz_inf();
+  if (d_lo) {
+    uint32_t kk[1] = {d_lo};
+    acc = g1_mul_scalar(B, kk, 1);
+  }
   G1Xyzz pts[TB];
   Fp pref[TB];
-  for (int d0 = 0; d0 < half; d0 += TB) {
-    const int cnt = (half - d0 < TB) ? (half - d0) : TB;
+  for (uint32_t d0 = d_lo; d0 < d_hi; d0 += TB) {
+    const int n = (d_hi - d0 < (uint32_t)TB) ? (int)(d_hi - d0) : TB;
     Fp run = fp_one();
-    for (int k = 0; k < cnt; k++) {
+    for (int k = 0; k < n; k++) {
       xyzz_madd(acc, B);
       pts[k] = acc;
       pref[k] = run;
       if (!xyzz_is_inf(acc)) run = fp_mul(run, acc.zzz);
     }
     Fp inv = fp_inv(run);
-    for (int k = cnt - 1; k >= 0; k--) {
+    for (int k = n - 1; k >= 0; k--) {
       G1Affine e;
       if (xyzz_is_inf(pts[k])) {
         e = g1a_inf();
@@ -93,6 +109,10 @@ __global__ void __launch_bounds__(64) table_fill_kernel(uint4* __restrict__ tabl
   }
 }
 
+int table_num_windows(int c) { return glv_num_windows(c); }
+uint32_t table_top_count(int c) { return glv_top_max(c) + 1u; }
+unsigned long long table_entries(int c, int npoints) { return glv_table_entries(c, npoints); }
+
 void launch_srs_import(void* d_aff_out, const void* d_canon_in, int* d_not_on_curve, int* d_not_in_subgroup, int n, cudaStream_t st) {
   srs_import_kernel<<<(n + 63) / 64, 64, 0, st>>>((G1Affine*)d_aff_out, (const uint32_t*)d_canon_in, d_not_on_curve, d_not_in_subgroup, n);
   count_launch();
@@ -101,9 +121,13 @@ void launch_table_bases(void* d_bases, const void* d_aff, int c, int nwin, int n
   table_bases_kernel<<<(npoints + 31) / 32, 32, 0, st>>>((G1Affine*)d_bases, (const G1Affine*)d_aff, c, nwin, npoints);
   count_launch();
 }
-void launch_table_fill(void* d_table, const void* d_bases, int c, int nwin, int npoints, cudaStream_t st) {
-  int n_pairs = nwin * npoints;
-  table_fill_kernel<<<(n_pairs + 63) / 64, 64, 0, st>>>((uint4*)d_table, (const G1Affine*)d_bases, c, n_pairs);
+void launch_table_fill(void* d_table, const void* d_bases, int c, int nwin, int npoints, uint32_t cnt_top, cudaStream_t st) {
+  const int n_pairs = nwin * npoints;
+  // enough threads to fill the GPU whatever the window (16-bit windows: 8 x 4096 pairs of 32768+ multiples each)
+  int segs = 1;
+  while (n_pairs * segs < 200000 && (1 << (c - 1)) / (segs * 2) >= 4 * TB) segs *= 2;
+  const long total = (long)n_pairs * segs;
+  table_fill_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>((uint4*)d_table, (const G1Affine*)d_bases, c, nwin, npoints, cnt_top, segs);
   count_launch();
 }
 

@@ -105,9 +105,16 @@ int emul_g1_decompress(uint8_t* out96, const uint8_t* in48) {
 
 void emul_sha256(uint8_t* out32, const uint8_t* msg, size_t len) { sha256_oneshot(out32, msg, len); }
 
-// signed-digit recoding: digits[nwin] as int32
-void emul_recode(int32_t* digits, const uint32_t* k8, int c, int nwin) {
-  for (int j = 0, carry = 0; j < nwin; j++) digits[j] = recode_next_digit(k8, c, j, carry);
+// GLV split + signed-digit recoding of both halves: q4, m4 and digits[2][W] as int32 (half 0 = m, half 1 = q)
+int emul_glv_windows(int c) { return glv_num_windows(c); }
+uint32_t emul_glv_window_count(int c, int j) { return glv_window_count(c, j); }
+void emul_glv_recode(uint32_t* q4, uint32_t* m4, int32_t* digits, const uint32_t* k8, int c) {
+  glv_split_barrett(q4, m4, k8);
+  const int W = glv_num_windows(c);
+  for (int h = 0; h < 2; h++) {
+    const uint32_t* v = h ? q4 : m4;
+    for (int j = 0, carry = 0; j < W; j++) digits[h * W + j] = glv_digit([&](int w) { return v[w]; }, c, W, j, carry);
+  }
 }
 
 // Horner + quotient over n canonical coefficients (n*8 u32) at z (canonical)

@@ -437,7 +437,7 @@ def force_batch_affine(lw):
     lw.set_option("msm_ba_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_batch_affine_edge_blobs_vs_oracle(lw, ref, settings8, force_batch_affine, variant):
     lw.set_option("msm_ba_variant", variant)
     blobs = edge_blobs()
@@ -627,18 +627,11 @@ def _synth_scalar(seed, t):
 @pytest.mark.parametrize("n", [1, 2, 63, 4096, 1 << 14, 1 << 16])
 def test_var_msm_synthetic_sizes(lw, settings8, py_setup, n):
     """Points = pseudo-random entries d * 2^(c j) * P_i of the fixed-base table (tau known => known discrete logs)."""
-    c = lw.window_bits(settings8)
-    nwin = 255 // c + 1
-    entries = nwin * 4096 << (c - 1)
     ms, got = lw.bench_var_msm(n, settings8, iters=1, seed=5)
-    tau = py_setup.tau
+    dlog = lw.synth_point_dlogs(settings8, n, py_setup.tau)
     acc = 0
     for t in range(n):
-        e = (t * 2654435761) % entries
-        d = (e & ((1 << (c - 1)) - 1)) + 1
-        i = (e >> (c - 1)) & 4095
-        j = e >> (c - 1 + 12)
-        acc = (acc + _synth_scalar(5, t) * d * pow(2, c * j, R) * pow(tau, i, R)) % R
+        acc = (acc + _synth_scalar(5, t) * dlog[t]) % R
     assert got == bls.g1_compress(bls.g1_mul(bls.G1, acc)), n
 
 

@@ -193,16 +193,33 @@ def test_sha256(lib):
         assert bytes(out) == hashlib.sha256(msg).digest()
 
 
-@pytest.mark.parametrize("c", [4, 8, 10, 12, 13, 14, 15, 16])
-def test_recode(lib, c):
+@pytest.mark.parametrize("c", [4, 5, 7, 8, 10, 12, 13, 14, 15, 16])
+def test_glv_recode(lib, c):
+    """csrc/recode.cuh: k = m + q x^2 with m, q < x^2; signed digits with an unsigned top window; every digit
+    addresses an entry the table holds (glv_window_count)."""
     rnd = random.Random(10 + c)
-    nwin = 255 // c + 1
-    digits = (ctypes.c_int32 * nwin)()
-    for k in [0, 1, R - 1, R - 2, (1 << 254) - 1] + [rnd.randrange(R) for _ in range(200)]:
-        lib.emul_recode(digits, u32(k, 8), c, nwin)
+    X2 = 0xD201000000010000 ** 2
+    W = lib.emul_glv_windows(c)
+    assert W == -(-128 // c)
+    lib.emul_glv_window_count.restype = ctypes.c_uint32
+    counts = [lib.emul_glv_window_count(c, j) for j in range(W)]
+    assert counts[:-1] == [1 << (c - 1)] * (W - 1) and counts[-1] == ((X2 - 1) >> (c * (W - 1))) + 1
+    digits = (ctypes.c_int32 * (2 * W))()
+    q4, m4 = (ctypes.c_uint32 * 4)(), (ctypes.c_uint32 * 4)()
+    special = [0, 1, R - 1, R - 2, (1 << 254) - 1, X2 - 1, X2, X2 + 1, (X2 - 2) * X2 + X2 - 1, 5 * X2 - 1, 5 * X2,
+               ((1 << 128) - 1) % R, (X2 - 1) * X2]
+    for k in special + [rnd.randrange(R) for _ in range(300)]:
+        assert k < R
+        lib.emul_glv_recode(q4, m4, digits, u32(k, 8), c)
+        q, m = from_u32(q4), from_u32(m4)
+        assert (q, m) == divmod(k, X2)
         d = list(digits)
-        assert sum(x << (c * j) for j, x in enumerate(d)) == k
-        assert all(-(1 << (c - 1)) < x <= (1 << (c - 1)) for x in d)
+        for h, v in ((0, m), (1, q)):
+            dd = d[h * W:(h + 1) * W]
+            assert sum(x << (c * j) for j, x in enumerate(dd)) == v
+            assert all(-(1 << (c - 1)) < x <= (1 << (c - 1)) for x in dd[:-1])
+            assert 0 <= dd[-1] <= counts[-1]
+            assert all(abs(x) <= counts[j] for j, x in enumerate(dd))
 
 
 @pytest.mark.parametrize("chunks", [1, 4, 32, 128])
