@@ -25,6 +25,9 @@ namespace lw {
 LW_COLD Fp fp_inv_gcd_ni(Fp y) { return fp_inv_gcd(y); }
 LW_COLD G1Affine g1a_dbl_ni(G1Affine p) { return xyzz_to_affine(xyzz_dbl_affine(p)); }
 
+#ifndef LWKZG_BA_PREFETCH
+#define LWKZG_BA_PREFETCH false
+#endif
 constexpr uint32_t BA_NONE = 0xffffffffu;
 
 template <int TH>
@@ -68,16 +71,54 @@ __device__ __forceinline__ void prefetch_slot_l2(const uint4* p) {
   for (int w = 0; w < 9; w++) prefetch_l2(p + w * TH);
 }
 
-template <bool BE, int K, int MINB, int TH>
-__global__ void __launch_bounds__(TH, MINB)
-msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
-                     uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top) {
+// ---- operand staging through shared memory (cp.async)
+// Every table entry, accumulator and prefix product a slot needs is requested one slot AHEAD with cp.async into a
+// per-thread column of shared memory.  Two reasons it has to be cp.async and not loads into registers: (1) the
+// multiplier is an out-of-line function and a CALL waits for every outstanding register load, so register
+// prefetching stalls at the first product of each slot (ncu: `CALL fp_mul_nv` and the first use of the loaded
+// words were the top stall sites, 13 % of all warp samples); (2) the 60 registers a slot's operands occupy are
+// not available under the 168-register budget of three blocks per SM.
+__device__ __forceinline__ void cp_async16(uint4* smem_dst, const uint4* gsrc) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int TH>
+__device__ __forceinline__ Fp fp_from_stage(const uint4* p /* 3 words, stride TH */) {
+  const uint4 v0 = p[0], v1 = p[TH], v2 = p[2 * TH];
+  Fp e;
+  e.l[0] = v0.x; e.l[1] = v0.y; e.l[2] = v0.z; e.l[3] = v0.w;
+  e.l[4] = v1.x; e.l[5] = v1.y; e.l[6] = v1.z; e.l[7] = v1.w;
+  e.l[8] = v2.x; e.l[9] = v2.y; e.l[10] = v2.z; e.l[11] = v2.w;
+  return e;
+}
+
+constexpr int BA_STAGE_WORDS = 15;   // T.x T.y (6) + A.x A.y (6) + prefix product (3) 128-bit words per thread
+template <int K, int TH>
+constexpr size_t ba_smem_bytes() { return (size_t)BA_STAGE_WORDS * TH * 16 + (size_t)K * TH * 2 + 4 * TH * 4; }
+
+// A slot's digit is kept as 16 bits (two's complement for the signed windows -- 0x8000 can only be +2^15, the
+// most negative digit is -2^15 + 1 -- and plain unsigned for the top window); 0 = nothing to add this round.
+__device__ __forceinline__ uint32_t ba_entry_of(uint32_t code, int c, int nwin, uint32_t cnt_top, int j, int pi) {
+  if (code == 0) return BA_NONE;
+  int d = (int)code;
+  if (j < nwin - 1 && code > 0x8000u) d = (int)code - 65536;
+  return entry_index(c, nwin, cnt_top, j, pi, d < 0 ? -d : d) | (d < 0 ? 0x80000000u : 0u);
+}
+
+template <bool BE, int K, int TH, bool PF>
+__device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
+                                                   uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top) {
   static_assert(K <= 64, "slot masks are 64 bits wide");
+  static_assert(48 * (TH / 2) * 4 <= BA_STAGE_WORDS * TH * 16, "the block-reduction scratch aliases the staging area");
   constexpr int HT = TH / 2;              // threads per GLV half
   constexpr int NPT = N_POINTS / HT;      // points per thread
-  __shared__ uint32_t sk[4][TH];
-  __shared__ uint32_t sidx[K][TH];   // entry index | sign << 31, or BA_NONE
-  __shared__ uint32_t red[48 * HT];
+  extern __shared__ uint4 dyn_smem[];
+  uint4* stage = dyn_smem + threadIdx.x;                                                  // word w at stage[w * TH]
+  uint16_t (*sdig)[TH] = reinterpret_cast<uint16_t (*)[TH]>(dyn_smem + BA_STAGE_WORDS * TH);   // digit codes of the round
+  uint32_t (*sk)[TH] = reinterpret_cast<uint32_t (*)[TH]>(reinterpret_cast<uint8_t*>(dyn_smem + BA_STAGE_WORDS * TH) + (size_t)K * TH * 2);
+  uint32_t* red = reinterpret_cast<uint32_t*>(dyn_smem);
 
   const int tid = threadIdx.x;
   const int half = tid / HT, hl = tid % HT;
@@ -92,17 +133,42 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
   const int PPR = K / nwin;
   const int rounds = (NPT + PPR - 1) / PPR;
   uint64_t infmask = K >= 64 ? ~0ull : ((1ull << K) - 1ull);   // accumulators at infinity
-  for (int k = PPR * nwin; k < K; k++) sidx[k][tid] = BA_NONE;
+  for (int k = PPR * nwin; k < K; k++) sdig[k][tid] = 0;
+
+  // requests of pass 1b (T.x, A.x) and pass 2 (T, A, prefix product) for slot k with entry e
+  auto request1 = [&](int k, uint32_t e) {
+    if (e != BA_NONE) {
+      const uint4* tp = table + (size_t)(e & 0x7fffffffu) * 6;
+      cp_async16(stage, tp); cp_async16(stage + TH, tp + 1); cp_async16(stage + 2 * TH, tp + 2);
+      if (!((infmask >> k) & 1ull)) {
+        const uint4* ap = my + (k * 9) * TH;
+        cp_async16(stage + 6 * TH, ap); cp_async16(stage + 7 * TH, ap + TH); cp_async16(stage + 8 * TH, ap + 2 * TH);
+      }
+    }
+    cp_async_commit();
+  };
+  auto request2 = [&](int k, uint32_t e) {
+    if (e != BA_NONE) {
+      const uint4* tp = table + (size_t)(e & 0x7fffffffu) * 6;
+#pragma unroll
+      for (int w = 0; w < 6; w++) cp_async16(stage + w * TH, tp + w);
+      if (!((infmask >> k) & 1ull)) {
+        const uint4* ap = my + (k * 9) * TH;
+#pragma unroll
+        for (int w = 0; w < 9; w++) cp_async16(stage + (6 + w) * TH, ap + w * TH);
+      }
+    }
+    cp_async_commit();
+  };
 
 #pragma unroll 1
   for (int rnd = 0; rnd < rounds; rnd++) {
-    // ------------------------------------------------------------ pass 1a: digits -> entry indices; their table
-    // lines and the accumulator rows are requested into L2 so that pass 1b finds them there
+    const int pi0 = hl + HT * rnd * PPR;   // point of slot group p: pi0 + HT * p
+    // ------------------------------------------------------------ pass 1a: digits of the round's points
 #pragma unroll 1
     for (int p = 0; p < PPR; p++) {
-      const int t_idx = rnd * PPR + p;
-      const bool have = t_idx < NPT;
-      const int pi = hl + HT * t_idx;
+      const bool have = rnd * PPR + p < NPT;
+      const int pi = pi0 + HT * p;
       if (have) {
         uint32_t h4[4];
         load_scalar_half<BE>(h4, sc, pi, half);
@@ -113,14 +179,11 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
 #pragma unroll 1
       for (int j = 0; j < nwin; j++) {
         const int k = p * nwin + j;
-        uint32_t e = BA_NONE;
-        if (have) {
-          const int d = glv_digit(limb, c, nwin, j, carry);
-          if (d != 0) e = entry_index(c, nwin, cnt_top, j, pi, d < 0 ? -d : d) | (d < 0 ? 0x80000000u : 0u);
-        }
-        sidx[k][tid] = e;
-        if (e != BA_NONE) {
-          prefetch_l2(table + (size_t)(e & 0x7fffffffu) * 6);
+        int d = 0;
+        if (have) d = glv_digit(limb, c, nwin, j, carry);
+        sdig[k][tid] = (uint16_t)d;
+        if (PF && d != 0) {   // table line and accumulator row on their way into L2
+          prefetch_l2(table + (size_t)entry_index(c, nwin, cnt_top, j, pi, d < 0 ? -d : d) * 6);
           if (!((infmask >> k) & 1ull)) prefetch_fp_scratch<TH>(my + (k * 9) * TH);
         }
       }
@@ -128,31 +191,34 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
     // ------------------------------------------------------------ pass 1b: differences and prefix products
     Fp prod = fp_one();
     uint64_t specmask = 0;   // slots with T.x == A.x
-    uint32_t e_next = sidx[0][tid];
-    Fp tx_next = fp_zero(), ax_next = fp_zero();
-    if (e_next != BA_NONE) {
-      tx_next = load_entry_x(table, e_next & 0x7fffffffu);
-      if (!(infmask & 1ull)) ax_next = load_fp_scratch<TH>(my);
-    }
+    uint32_t e_next = ba_entry_of(sdig[0][tid], c, nwin, cnt_top, 0, pi0);
+    request1(0, e_next);
+    int jn = 0, pin = pi0;   // (window, point) of slot k + 1
 #pragma unroll 1
     for (int k = 0; k < K; k++) {
-      uint32_t e = e_next;
-      const Fp tx = tx_next, ax = ax_next;
-      if (k + 1 < K) {   // operands of the next slot are in flight while this one multiplies
-        e_next = sidx[k + 1][tid];
-        if (e_next != BA_NONE) {
-          tx_next = load_entry_x(table, e_next & 0x7fffffffu);
-          if (!((infmask >> (k + 1)) & 1ull)) ax_next = load_fp_scratch<TH>(my + ((k + 1) * 9) * TH);
-        }
+      const uint32_t e = e_next;
+      cp_async_wait_all();
+      const bool inf = (infmask >> k) & 1ull;
+      Fp d = fp_zero();
+      bool tx_zero = false;
+      if (e != BA_NONE) {
+        const Fp tx = fp_from_stage<TH>(stage);
+        tx_zero = fp_is_zero(tx);
+        if (!inf) d = fp_sub(tx, fp_from_stage<TH>(stage + 6 * TH));
+      }
+      // the staged words are consumed (d, tx_zero depend on all of them): the column may be overwritten
+      if (k + 1 < K) {
+        if (++jn == nwin) { jn = 0; pin += HT; }
+        e_next = ba_entry_of(sdig[k + 1][tid], c, nwin, cnt_top, jn, pin);
+        request1(k + 1, e_next);
       }
       if (e == BA_NONE) continue;
-      if (fp_is_zero(tx)) {
+      if (tx_zero) {
         // (0, 0) encodes infinity in the table (hand-built setups); x == 0 with y != 0 is a curve point
         const G1Affine t = load_entry(table, e & 0x7fffffffu);
-        if (fp_is_zero(t.y)) { sidx[k][tid] = BA_NONE; continue; }
+        if (fp_is_zero(t.y)) { sdig[k][tid] = 0; continue; }
       }
-      if ((infmask >> k) & 1ull) continue;
-      const Fp d = fp_sub(tx, ax);
+      if (inf) continue;
       if (fp_is_zero(d)) {
         specmask |= 1ull << k;
       } else {
@@ -163,28 +229,35 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
     // ------------------------------------------------------------ shared inversion
     Fp inv = fp_inv_gcd_ni(prod);
     // ------------------------------------------------------------ pass 2
-    for (int k = K - 1; k >= K - 2 && k >= 0; k--) {
-      const uint32_t e = sidx[k][tid];
-      if (e != BA_NONE) { prefetch_entry_l2(table, e & 0x7fffffffu); prefetch_slot_l2<TH>(my + (k * 9) * TH); }
-    }
+    // (window, point) of slot K - 1: slots >= PPR * nwin are empty whatever their coordinates
+    jn = (K - 1) % nwin;
+    pin = pi0 + HT * ((K - 1) / nwin);
+    e_next = ba_entry_of(sdig[K - 1][tid], c, nwin, cnt_top, jn, pin);
+    request2(K - 1, e_next);
 #pragma unroll 1
     for (int k = K - 1; k >= 0; k--) {
-      if (k >= 2) {
-        const uint32_t e2 = sidx[k - 2][tid];
-        if (e2 != BA_NONE) { prefetch_entry_l2(table, e2 & 0x7fffffffu); prefetch_slot_l2<TH>(my + ((k - 2) * 9) * TH); }
+      const uint32_t e = e_next;
+      if (k > 0) {
+        if (--jn < 0) { jn = nwin - 1; pin -= HT; }
+        e_next = ba_entry_of(sdig[k - 1][tid], c, nwin, cnt_top, jn, pin);
       }
-      const uint32_t e = sidx[k][tid];
-      if (e == BA_NONE) continue;
-      G1Affine t = load_entry(table, e & 0x7fffffffu);
-      t.y = fp_cneg(t.y, (e >> 31) != 0);
+      cp_async_wait_all();
+      if (e == BA_NONE) {
+        if (k > 0) request2(k - 1, e_next);
+        continue;
+      }
+      G1Affine t;
+      t.x = fp_from_stage<TH>(stage);
+      t.y = fp_cneg(fp_from_stage<TH>(stage + 3 * TH), (e >> 31) != 0);
       uint4* slot = my + (k * 9) * TH;
       if ((infmask >> k) & 1ull) {
         store_fp_scratch<TH>(slot, t.x);
         store_fp_scratch<TH>(slot + 3 * TH, t.y);
         infmask &= ~(1ull << k);
+        if (k > 0) request2(k - 1, e_next);
         continue;
       }
-      const Fp ax = load_fp_scratch<TH>(slot), ay = load_fp_scratch<TH>(slot + 3 * TH);
+      const Fp ax = fp_from_stage<TH>(stage + 6 * TH), ay = fp_from_stage<TH>(stage + 9 * TH);
       if ((specmask >> k) & 1ull) {
         if (fp_eq(t.y, ay)) {
           const G1Affine dd = g1a_dbl_ni(t);
@@ -193,13 +266,17 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
         } else {
           infmask |= 1ull << k;   // T == -A
         }
+        if (k > 0) request2(k - 1, e_next);
         continue;
       }
-      const Fp ex = load_fp_scratch<TH>(slot + 6 * TH);
       const Fp d = fp_sub(t.x, ax);
-      const Fp dinv = fp_mul_nv(inv, ex);
+      const Fp dy = fp_sub(t.y, ay);
+      const Fp dinv = fp_mul_nv(inv, fp_from_stage<TH>(stage + 12 * TH));
+      // every staged word of this slot now sits in a register: request the next slot while the remaining
+      // four products run
+      if (k > 0) request2(k - 1, e_next);
       inv = fp_mul_nv(inv, d);
-      const Fp lam = fp_mul_nv(fp_sub(t.y, ay), dinv);
+      const Fp lam = fp_mul_nv(dy, dinv);
       const Fp x3 = fp_sub(fp_sub(fp_sqr_nv(lam), ax), t.x);
       const Fp y3 = fp_sub(fp_mul_nv(lam, fp_sub(ax, x3)), ay);
       store_fp_scratch<TH>(slot, x3);
@@ -217,8 +294,24 @@ msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ ta
     a.y = load_fp_scratch<TH>(my + (k * 9 + 3) * TH);
     xyzz_madd_hot(acc, a);
   }
+  __syncthreads();   // the reduction scratch aliases the staging columns
   block_reduce_xyzz_glv<TH>(acc, red);
   if (tid == 0) partials[blob] = acc;
+}
+
+// Two ways to fix the register budget: MINB > 0 -> __launch_bounds__(TH, MINB) (ptxas picks the count),
+// MINB < 0 -> __maxnreg__(-MINB) (the two qualifiers cannot be combined).
+template <bool BE, int K, int MINB, int TH, bool PF>
+__global__ void __launch_bounds__(TH, MINB)
+msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
+                     uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top) {
+  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top);
+}
+template <bool BE, int K, int REGS, int TH, bool PF>
+__global__ void __maxnreg__(REGS)
+msm_gather_ba_kernel_r(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
+                       uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top) {
+  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top);
 }
 
 template <int K, int MINB, int TH>
@@ -226,10 +319,28 @@ static void launch_ba(void* d_partials, const void* d_table, int c, const void* 
                       void* d_scratch, cudaStream_t st) {
   const int nwin = glv_num_windows(c);
   const uint32_t cnt_top = glv_top_max(c) + 1u;
+  constexpr size_t smem = ba_smem_bytes<K, TH>();
+  static bool attr_set = false;
+  void (*kbe)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t);
+  void (*kle)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t);
+  if constexpr (MINB > 0) {
+    kbe = msm_gather_ba_kernel<true, K, MINB, TH, LWKZG_BA_PREFETCH>;
+    kle = msm_gather_ba_kernel<false, K, MINB, TH, LWKZG_BA_PREFETCH>;
+  } else {
+    kbe = msm_gather_ba_kernel_r<true, K, -MINB, TH, LWKZG_BA_PREFETCH>;
+    kle = msm_gather_ba_kernel_r<false, K, -MINB, TH, LWKZG_BA_PREFETCH>;
+  }
+  if (!attr_set) {
+    cudaFuncSetAttribute(kbe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kbe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kle, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set = true;
+  }
   if (be_input)
-    msm_gather_ba_kernel<true, K, MINB, TH><<<n_blobs, TH, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top);
+    kbe<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top);
   else
-    msm_gather_ba_kernel<false, K, MINB, TH><<<n_blobs, TH, 0, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top);
+    kle<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top);
 }
 
 }  // namespace lw

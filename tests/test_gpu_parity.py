@@ -437,7 +437,7 @@ def force_batch_affine(lw):
     lw.set_option("msm_ba_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_batch_affine_edge_blobs_vs_oracle(lw, ref, settings8, force_batch_affine, variant):
     lw.set_option("msm_ba_variant", variant)
     blobs = edge_blobs()
