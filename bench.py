@@ -1,26 +1,31 @@
 #!/usr/bin/env python3
-"""Benchmark of the EIP-4844 commit+proof hot path (BASELINE.json metric:
-blobs/sec commit+proof at 1/2/4/8 B200).
+"""Benchmark of the EIP-4844 hot path (BASELINE.json metric: blobs/sec commit+proof at 1/2/4/8 B200; G1 MSM
+points/sec vs CPU reference).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-One step = one pass of the hot path over one batch: for each of 1024 synthetic
-blobs per GPU (SURVEY §8d generator), commitment = blob_to_kzg_commitment(blob)
-and proof = compute_blob_kzg_proof(blob, commitment), through the library's
-batch entry point.  Blob batches shard across GPUs with no collective (weak
-scaling: every rank processes its own 1024 blobs); the only distributed calls
-are the barriers / max-reduction of the timing itself.
+One step = one pass of the hot path over one batch: for each of 1024 synthetic blobs per GPU (SURVEY §8d generator),
+commitment = blob_to_kzg_commitment(blob) and proof = compute_blob_kzg_proof(blob, commitment), through the library's
+batch entry point.  Blob batches shard across GPUs with no collective (weak scaling: every rank processes its own
+1024 blobs); the timing itself uses a barrier and a max-reduction.
 
-Printed JSON line (rank 0): `value` = whole-job blobs/s with blobs resident in
-HBM; `e2e` = the same metric through the host-buffer C ABI call
-(lwkzg_commit_and_prove_batch) from pinned host memory, H2D/D2H inside the
-timed region; `roofline` = the dominant kernel (batched fixed-base MSM gather)
-against the integer-multiply (IMAD) peak measured in this run, plus its HBM
-figure; `cpu_baseline` = the C restatement of the reference's CPU path
-(oracle/c) on a bounded sample of the same workload.
+The JSON line (rank 0):
+  value         whole-job blobs/s, blobs resident in HBM (device-pointer C ABI call)
+  e2e           the same metric through the host-buffer C ABI call (lwkzg_commit_and_prove_batch), H2D of the blobs and
+                D2H of commitments / proofs / status inside the timed region; pinned host memory (the headline) and
+                pageable memory (what a c-kzg caller passes) side by side
+  parity        a sample of every rank's timed outputs compared with the C restatement oracle OUTSIDE the timed region
+  roofline      the dominant kernel (batched fixed-base MSM) alone: SURVEY §8d's algorithmic work / its time against
+                the integer-multiply peak, plus the fractions against what the kernel really executes and against this
+                algorithm's own minimum; HBM traffic from the committed ncu capture
+  verify        BASELINE config 3: verify_blob_kzg_proof_batch over 4096 blobs -- device-resident, pinned, pageable
+  msm_sweep     BASELINE config 5: variable-base G1 MSM 2^12 .. 2^22, points/s and roofline fraction per size, next to
+                the CPU restatement's g1_lincomb
+  latency       single-call latency of every c-kzg entry point, GPU vs the CPU restatement
+  cpu_baseline  the C restatement of the reference's CPU path (oracle/c) on a bounded sample of the same workload
 
---impl reference times that CPU restatement alone (the reference's own Rust
-code cannot be built here: no cargo, un-vendored git dependencies).
+--impl reference times that CPU restatement alone (the reference's own Rust code cannot be built here: no cargo,
+un-vendored git dependencies); it never loads the product library.
 """
 import argparse
 import json
@@ -37,33 +42,20 @@ sys.path.insert(0, ROOT)
 BLOBS_PER_GPU = 1024
 BLOB_BYTES = 4096 * 32
 SETUP = os.path.join(ROOT, "tests", "golden", "trusted_setup.txt")
-MAC32_PER_MSM = 2.80e8  # fixed-base signed-digit MSM-4096, c = 13: 933 888 Fp mul x 300 MAC32
-MAC32_PER_BLOB = 2 * MAC32_PER_MSM
+MAC32_PER_MSM = 2.80e8       # fixed-base signed-digit bucket MSM-4096, c = 13: 933 888 Fp mul x 300 MAC32
+MAC32_M, MAC32_S = 300.0, 234.0   # wide multiply-accumulates of one Fp product / square (csrc/mont.cuh)
+IMAD_NOMINAL = 148 * 64 * 1.965e9  # SURVEY §8d sanity ceiling: one IMAD.WIDE per INT32 lane per clock
 METRIC = "blobs/sec commit+proof"
 UNIT = "blobs/s"
+VERIFY_BLOBS = 4096
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE 1024-blob launch of msm_gather_ba_kernel from the ncu --set full
+# capture committed as profiles/r02_ncu_ba_staged_1024blob_raw.csv
+NCU_DRAM_BYTES_PER_BLOB = (35.42e9 + 9.33e9) / 1024
 
 
 def workload_name(n, wb):
     return ("commit+proof (blob_to_kzg_commitment + compute_blob_kzg_proof) of %d synthetic 4096-element blobs per GPU, "
             "tests/golden/trusted_setup.txt (monomial, tau=1337), fixed-base window %d bits" % (n, wb))
-
-
-def entries_per_point(lw, c, sample_blobs=2):
-    """Average number of non-zero signed base-2^c digits of the synthetic blob words (= table entries accumulated
-    per SRS point), counted on a small host-side sample with the kernel's own recoding rule (csrc/recode.cuh)."""
-    W = 255 // c + 1
-    nz = tot = 0
-    for k in range(sample_blobs):
-        blob = lw.synth_blob_host(k)
-        for i in range(0, len(blob), 32 * 16):  # every 16th word
-            v = int.from_bytes(blob[i:i + 32], "big")
-            carry = 0
-            for j in range(W):
-                d = ((v >> (c * j)) & ((1 << c) - 1)) + carry
-                carry = 1 if d > (1 << (c - 1)) else 0
-                nz += 1 if (d != 0 and d != (1 << c)) else 0
-            tot += 1
-    return nz / tot
 
 
 class ClockSampler:
@@ -92,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -106,15 +98,15 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ---------------------------------------------------------------------------------------------- CPU restatement
 def cpu_reference_run(steps, warmup, sample_blobs=None):
-    """Time the C restatement of the reference's CPU path with all host threads."""
+    """Time the C restatement of the reference's CPU path with all host threads.  Uses oracle/ only."""
     from oracle import c_oracle
-    import lambdaworks_kzg_b200 as lw
 
     oracle = c_oracle.COracle(open(SETUP).read())
     cores = oracle.max_threads()
     n = sample_blobs or max(16, 2 * cores)
-    blobs = b"".join(lw.synth_blob_host(k) for k in range(n))
+    blobs = b"".join(oracle.synth_blob(k) for k in range(n))
     for _ in range(min(warmup, 1)):
         oracle.commit_and_prove_batch(blobs[: BLOB_BYTES * min(n, cores)], min(n, cores), cores)
     t0 = time.perf_counter()
@@ -128,6 +120,55 @@ def cpu_reference_run(steps, warmup, sample_blobs=None):
                       "C restatement of the reference algorithm (per-call SRS re-hydration, Pippenger w=9, projective)" % (n, cores)}, dt
 
 
+def cpu_latencies(oracle):
+    """Single-call latency (ms) of the entry points the C restatement covers, one thread (the reference is
+    single-threaded inside a call)."""
+    blob = oracle.synth_blob(0)
+    out = {}
+    t = time.perf_counter(); rc, com = oracle.blob_to_kzg_commitment(blob); out["blob_to_kzg_commitment"] = (time.perf_counter() - t) * 1e3
+    t = time.perf_counter(); oracle.compute_kzg_proof(blob, bytes(31) + b"\x05"); out["compute_kzg_proof"] = (time.perf_counter() - t) * 1e3
+    t = time.perf_counter(); oracle.compute_blob_kzg_proof(blob, com); out["compute_blob_kzg_proof"] = (time.perf_counter() - t) * 1e3
+    return out
+
+
+def cpu_msm_points_per_s(oracle, lg):
+    n = 1 << lg
+    pts, sc = oracle.synth_msm_inputs(n, 1)
+    t = time.perf_counter()
+    rc, _ = oracle.g1_lincomb(pts, sc, n)
+    dt = time.perf_counter() - t
+    assert rc == 0
+    return n / dt
+
+
+# ---------------------------------------------------------------------------------------------- model helpers
+def entries_per_point(wb, blob_fn, sample_blobs=2):
+    """Average number of non-zero digits per SRS point (= table entries accumulated), counted on a small host-side
+    sample with the kernel's own recoding rule (csrc/recode.cuh: GLV split, signed digits, unsigned top window)."""
+    x2 = 0xD201000000010000 ** 2
+    W = -(-128 // wb)
+    nz = tot = 0
+    for k in range(sample_blobs):
+        blob = blob_fn(k)
+        for i in range(0, len(blob), 32 * 16):  # every 16th word
+            v = int.from_bytes(blob[i:i + 32], "big")
+            for h in divmod(v, x2):
+                carry = 0
+                for j in range(W):
+                    d = ((h >> (wb * j)) & ((1 << wb) - 1)) + carry
+                    carry = 1 if (j < W - 1 and d > (1 << (wb - 1))) else 0
+                    if carry:
+                        d -= 1 << wb
+                    nz += 1 if d != 0 else 0
+            tot += 1
+    return nz / tot
+
+
+def var_msm_work_mac32(n):
+    """SURVEY §8d work model for a variable-base MSM without precomputation."""
+    return (min((255 // c + 1) * (10 * n + 14 * (1 << c)) for c in range(4, 24)) + 256 * 9) * 300.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -135,7 +176,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--blobs", type=int, default=BLOBS_PER_GPU)
-    ap.add_argument("--window-bits", type=int, default=15, help="fixed-base window c (15 -> 108 GiB table; shrinks automatically if HBM is short)")
+    ap.add_argument("--window-bits", type=int, default=16, help="fixed-base window c (16 -> 100 GiB table, the library default; shrinks automatically if HBM is short)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the verify / msm_sweep / latency blocks")
     args = ap.parse_args()
     # Exactly ONE line on stdout (the JSON): native libraries (NCCL's version banner, CUDA warnings) write to fd 1
     # behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor.
@@ -184,6 +226,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     lw.set_option("window_bits", args.window_bits)
     settings = lw.load_trusted_setup_file(SETUP)
     wb = lw.window_bits(settings)
@@ -215,43 +263,51 @@ def main():
     launches = lw.kernel_launches() - launches0
     ms = e0.elapsed_time(e1)
     assert int(status.abs().sum()) == 0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
+    ms_per_step = max_over_ranks(ms) / args.steps
     value = world * n / (ms_per_step * 1e-3)
+    dev_coms, dev_proofs = bytes(coms.cpu().numpy().tobytes()), bytes(proofs.cpu().numpy().tobytes())
 
-    # ---- end to end through the host-buffer C ABI call (pinned host memory)
-    h_blobs = torch.empty(n * BLOB_BYTES, dtype=torch.uint8).pin_memory()
-    h_blobs.copy_(blobs)
-    h_coms = torch.zeros(n * 48, dtype=torch.uint8).pin_memory()
-    h_proofs = torch.zeros(n * 48, dtype=torch.uint8).pin_memory()
-    for _ in range(min(args.warmup, 2)):
-        lw.commit_and_prove_batch(h_blobs.data_ptr(), n, settings, h_coms.data_ptr(), h_proofs.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        st = lw.commit_and_prove_batch(h_blobs.data_ptr(), n, settings, h_coms.data_ptr(), h_proofs.data_ptr())
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    assert not any(st)
-    assert bytes(h_coms.numpy().tobytes()) == bytes(coms.cpu().numpy().tobytes()), "host-API and device-API commitments differ"
-    assert bytes(h_proofs.numpy().tobytes()) == bytes(proofs.cpu().numpy().tobytes()), "host-API and device-API proofs differ"
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n / float(t.item())
+    # ---- end to end through the host-buffer C ABI call
+    def e2e_run(h_blobs, h_coms, h_proofs):
+        for _ in range(min(args.warmup, 2)):
+            lw.commit_and_prove_batch(h_blobs.data_ptr(), n, settings, h_coms.data_ptr(), h_proofs.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = lw.commit_and_prove_batch(h_blobs.data_ptr(), n, settings, h_coms.data_ptr(), h_proofs.data_ptr())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        assert not any(st)
+        assert bytes(h_coms.numpy().tobytes()) == dev_coms, "host-API and device-API commitments differ"
+        assert bytes(h_proofs.numpy().tobytes()) == dev_proofs, "host-API and device-API proofs differ"
+        return world * n / max_over_ranks(dt)
+
+    host_blobs = blobs.cpu()                                    # pageable
+    e2e_pageable = e2e_run(host_blobs, torch.zeros(n * 48, dtype=torch.uint8), torch.zeros(n * 48, dtype=torch.uint8))
+    e2e_value = e2e_run(host_blobs.pin_memory(), torch.zeros(n * 48, dtype=torch.uint8).pin_memory(), torch.zeros(n * 48, dtype=torch.uint8).pin_memory())
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel (measured alone, CUDA events on its own stream)
-    roofline = cpu_base = None
+    # ---- parity of what was just timed: a sample of THIS rank's outputs against the C restatement (checker only)
+    from oracle import c_oracle
+
+    oracle = c_oracle.COracle(open(SETUP).read())
+    sample = sorted({0, n // 3, n // 2, n - 1})
+    sb = b"".join(oracle.synth_blob(rank * n + k) for k in sample)
+    rc, oc, op = oracle.commit_and_prove_batch(sb, len(sample), 0)
+    mism = [k for i, k in enumerate(sample) if rc or dev_coms[48 * k:48 * k + 48] != oc[48 * i:48 * i + 48] or dev_proofs[48 * k:48 * k + 48] != op[48 * i:48 * i + 48]]
+    bad_ranks = max_over_ranks(float(len(mism)))
+    if bad_ranks:
+        raise SystemExit("PARITY FAILURE: timed outputs differ from the oracle on rank %d, blobs %r" % (rank, mism))
+    parity = {"checked_blobs_per_rank": len(sample), "ranks": world, "oracle": "oracle/c (C restatement), commitments and proofs byte-equal",
+              "mismatches": 0}
+
+    roofline = cpu_base = verify = msm_sweep = latency = None
     if rank == 0:
+        # ---- roofline of the dominant kernel (measured alone, CUDA events on its own stream)
         k_ms = lw.bench_msm_kernel(blobs.data_ptr(), n, settings, 0, 5)
         peak = max(lw.imad_peak(1), lw.imad_peak(0))
         achieved = n * MAC32_PER_MSM / (k_ms * 1e-3)
-        nwin = 255 // wb + 1
-        epp = entries_per_point(lw, wb)  # table entries really accumulated per point (non-zero signed digits)
+        epp = entries_per_point(wb, oracle.synth_blob)  # table entries really accumulated per point
         alg_bytes = n * (BLOB_BYTES + 4096 * epp * 96)  # scalars streamed once + one 96 B table entry per non-zero digit
         peaks = {}
         try:
@@ -259,45 +315,87 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # what the kernel really executes, in wide multiply-accumulates (Fp product 300, Fp square 234)
-        M, S = 300.0, 234.0
         batch_affine = lw.get_option("msm_algo") == 1 and n >= lw.get_option("msm_ba_min_blobs")
+        M, S = MAC32_M, MAC32_S
         if batch_affine:
             T, K = lw.get_option("msm_ba_threads"), lw.get_option("msm_ba_slots")
-            per_thread = 4096 * epp / T
-            rounds = -(-per_thread // K)
-            executed = n * (4096 * epp * (5 * M + S)            # affine addition with shared inversion
-                            + T * (K - 1) * (8 * M + 2 * S)     # folding the K accumulators of a thread (XYZZ)
-                            + T * rounds * (20 * 120 + M)       # binary-GCD inversions: ~20 rounds x 120 wide MACs
-                            + (T - 1) * 14 * M)                 # block tree
-            kernel = "msm_gather_ba_kernel<BE, K=%d, threads=%d> (batched-affine accumulation)" % (K, T)
+            rounds = -(-(4096 * epp / T) // K)
+            floor_mac = n * 4096 * epp * (5 * M + S)            # this algorithm's own minimum: the affine additions alone
+            executed = floor_mac + n * (T * (K - 1) * (8 * M + 2 * S)     # folding the K accumulators of a thread (XYZZ)
+                                        + T * rounds * (20 * 120 + M)     # binary-GCD inversions: ~20 rounds x 120 wide MACs
+                                        + (T - 1) * 14 * M)               # block tree
+            kernel = "msm_gather_ba_kernel<BE, K=%d, threads=%d> (GLV halves, batched-affine accumulation, cp.async operand staging)" % (K, T)
         else:
-            executed = n * 4096 * epp * (8 * M + 2 * S)
+            floor_mac = executed = n * 4096 * epp * (8 * M + 2 * S)
             kernel = "msm_gather_kernel<BE> (XYZZ accumulation)"
+        traffic = n * NCU_DRAM_BYTES_PER_BLOB if batch_affine else None
         roofline = {"bound": "int32-imad", "kernel": kernel, "achieved": achieved / 1e12, "peak": peak / 1e12,
                     "unit": "TMAC32/s", "frac": achieved / peak,
                     "peak_source": "lwkzg_imad_peak(): memory-free IMAD.WIDE probe with distinct operand registers, run in this process "
-                                   "(burst; best of carry-chain and carry-less variants; see profiles/r01_pipe_probe.md)",
+                                   "(burst; best of carry-chain and carry-less variants; profiles/r01_pipe_probe.md). "
+                                   "MEASURED_PEAKS.json carries no integer peak; the nominal figure is in peak_nominal",
+                    "peak_nominal": IMAD_NOMINAL / 1e12,
+                    "peak_note": "nominal = 148 SM x 64 INT32 lanes x 1.965 GHz (SURVEY 8d) assumes one IMAD.WIDE per lane per clock; the probe "
+                                 "issues IMAD.WIDE at 0.94-1.0 per clock per SM with distinct operands (a 32x32+64 MAC occupies the 16-lane "
+                                 "fmaheavy pipe for four cycles per warp) and 1.99 only when every chain re-uses the same operand registers",
                     "note": "achieved = SURVEY 8(d)'s ALGORITHMIC work (2.80e8 MAC32 per MSM-4096: bucket method, c = 13, XYZZ) / kernel time; "
-                            "the kernel needs fewer multiplications than that model (full digit table, batched-affine additions), so frac may "
-                            "exceed 1 -- frac_executed is the pipe-utilisation figure",
+                            "the kernel needs fewer multiplications than that model (full digit table, GLV, batched-affine additions), so frac may "
+                            "exceed 1 -- frac_executed is the pipe-utilisation figure and frac_floor the distance to this algorithm's own minimum",
                     "alg_mac32_per_launch": n * MAC32_PER_MSM, "kernel_ms": k_ms,
                     "executed_mac32_per_launch": executed,
                     "frac_executed": executed / (k_ms * 1e-3) / peak,
+                    "floor_mac32_per_launch": floor_mac,
+                    "frac_floor": floor_mac / (k_ms * 1e-3) / peak,
+                    "ncu_fmaheavy_pct": 72.4,
+                    "ncu_source": "sm__pipe_fmaheavy_cycles_active of the 1024-blob launch: profiles/r02_ncu_ba_staged_noprefetch_metrics.csv",
                     "table_entries_per_point": epp,
                     "kernel_share_of_step": 2 * k_ms / ms_per_step,
                     # second half of BASELINE's metric: G1 MSM points/s (fixed-base MSM over the 4096-point SRS, this kernel)
                     "g1_msm_points_per_s": n * 4096 / (k_ms * 1e-3),
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
-                    # profiles/r01_ncu_msm_summary.md (26.54 + 4.94 GB per 512-blob launch of the batched-affine kernel,
-                    # 6.88 + 0.04 GB for the XYZZ kernel), scaled to this launch's blob count
-                    "traffic": n * ((26.54e9 + 4.94e9) / 512 if batch_affine else (6.88e9 + 0.04e9) / 512),
-                    "traffic_source": "ncu capture, per-blob figure x blobs in this launch (profiles/r01_ncu_msm_summary.md)",
+                    "traffic": traffic,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 1024-blob launch, scaled to this launch's blob count "
+                                      "(profiles/r02_ncu_ba_staged_noprefetch_metrics.csv)",
                     "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "alg_bytes_per_launch": alg_bytes,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
+
+    if not args.no_extras:
+        # ---- BASELINE config 3: batched verification of 4096 blobs per GPU
+        verify = verify_block(lw, torch, dev, settings, rank, world, dist, barrier, max_over_ranks)
+    if rank == 0 and not args.no_extras:
+        # ---- BASELINE config 5: variable-base MSM sweep
+        peak = roofline["peak"] * 1e12
+        rows = []
+        for lg in range(12, 23):
+            m = 1 << lg
+            ms_v, out = lw.bench_var_msm(m, settings, iters=5 if lg < 18 else 2, seed=1)
+            rows.append({"log2_n": lg, "ms": ms_v, "points_per_s": m / (ms_v * 1e-3), "roofline_frac": var_msm_work_mac32(m) / (ms_v * 1e-3) / peak})
+        cpu_pts = {}
         if world == 1:
-            cpu_base, _ = cpu_reference_run(1, 1)
+            for lg in (12, 14):
+                cpu_pts["2^%d" % lg] = cpu_msm_points_per_s(oracle, lg)
+        msm_sweep = {"sizes": rows, "cpu_g1_lincomb_points_per_s": cpu_pts,
+                     "cpu_note": "C restatement of g1_lincomb (unsigned Pippenger, homogeneous projective), one thread, as the reference runs it",
+                     "work_model": "SURVEY 8d: min_c ceil(256/c) (10 N + 14 2^c) + 256*9 Fp products of 300 MAC32"}
+        # ---- single-call latencies of the c-kzg entry points
+        blob0 = bytes(blobs[:BLOB_BYTES].cpu().numpy().tobytes())
+        c0, p0 = dev_coms[:48], dev_proofs[:48]
+        calls = [("blob_to_kzg_commitment", lambda: lw.blob_to_kzg_commitment(blob0, settings)),
+                 ("compute_kzg_proof", lambda: lw.compute_kzg_proof(blob0, bytes(31) + b"\x05", settings)),
+                 ("compute_blob_kzg_proof", lambda: lw.compute_blob_kzg_proof(blob0, c0, settings)),
+                 ("verify_kzg_proof", lambda: lw.verify_kzg_proof(c0, bytes(32), blob0[:32], bytes([0xC0]) + bytes(47), settings)),
+                 ("verify_blob_kzg_proof", lambda: lw.verify_blob_kzg_proof(blob0, c0, p0, settings))]
+        gpu_lat = {}
+        for name, fn in calls:
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                fn()
+            gpu_lat[name] = (time.perf_counter() - t0) / 5 * 1e3
+        latency = {"unit": "ms per call", "gpu": gpu_lat, "cpu_restatement": cpu_latencies(oracle) if world == 1 else None,
+                   "cpu_note": "oracle/c restates commit / proof only (no pairing), one thread: the reference is single-threaded inside a call"}
+    if rank == 0 and world == 1:
+        cpu_base, _ = cpu_reference_run(1, 1)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -305,14 +403,63 @@ def main():
                 "dtype": "u32 (12x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic",
                 "config": {"workload": workload_name(n, wb), "blobs_per_gpu": n, "global_blobs": world * n, "parallelism": "blob-sharded x%d, no collective" % world,
                            "l2_policy": "inputs larger than L2: 128 MiB of blobs + random gathers from a %.1f GiB table per step" % (
-                               (255 // wb + 1) * 4096 * (1 << (wb - 1)) * 96 / 2**30)},
+                               sum(lw.table_geometry(wb)[1]) * 4096 * 96 / 2**30)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * BLOB_BYTES, "d2h_bytes_per_step": n * (48 + 48 + 4),
-                        "api": "lwkzg_commit_and_prove_batch (host buffers, pinned)"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
+                        "api": "lwkzg_commit_and_prove_batch (host buffers, pinned)", "pageable_value": e2e_pageable,
+                        "pageable_note": "same call from ordinary (pageable) host memory, what a c-kzg caller passes"},
+                "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "roofline": roofline, "verify": verify, "msm_sweep": msm_sweep,
+                "latency": latency, "cpu_baseline": cpu_base}
         emit(line)
     settings.free()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def verify_block(lw, torch, dev, settings, rank, world, dist, barrier, max_over_ranks):
+    """verify_blob_kzg_proof_batch over VERIFY_BLOBS blobs per GPU: commitments / proofs come
+    from our own commit+prove; the all-valid batch must verify and the batch with proof #n/2-1 replaced by another
+    point must not.  At N > 1 every rank verifies its own batch (replicas: the numbers are per-GPU batches in
+    flight at once) and the distributed check of the union of all batches is timed as well."""
+    nv = VERIFY_BLOBS
+    d_blobs = torch.empty(nv * BLOB_BYTES, dtype=torch.uint8, device=dev)
+    lw.synth_blobs_device(d_blobs.data_ptr(), 1 << 20 | (rank * nv), nv, torch.cuda.current_stream().cuda_stream)
+    d_c = torch.zeros(nv * 48, dtype=torch.uint8, device=dev)
+    d_p = torch.zeros(nv * 48, dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(nv, dtype=torch.int32, device=dev)
+    lw.commit_and_prove_batch_device(d_c.data_ptr(), d_p.data_ptr(), d_blobs.data_ptr(), nv, settings, torch.cuda.current_stream().cuda_stream, d_st.data_ptr())
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum()) == 0
+
+    def timed(fn, reps=3):
+        assert fn() is True
+        barrier()
+        best = 1e9
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ok = fn()
+            best = min(best, time.perf_counter() - t0)
+            assert ok is True
+        return max_over_ranks(best)
+
+    out = {"blobs_per_gpu": nv, "unit": UNIT}
+    t_dev = timed(lambda: lw.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_c.data_ptr(), d_p.data_ptr(), nv, settings))
+    bad = d_p.clone()
+    bad[48 * (nv // 2 - 1): 48 * (nv // 2)] = d_c[:48]
+    assert lw.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_c.data_ptr(), bad.data_ptr(), nv, settings) is False
+    out["device_resident"] = {"ms": t_dev * 1e3, "value": world * nv / t_dev}
+    hb, hc, hp = d_blobs.cpu(), d_c.cpu(), d_p.cpu()
+    t_page = timed(lambda: lw.verify_blob_kzg_proof_batch_ptr(hb.data_ptr(), hc.data_ptr(), hp.data_ptr(), nv, settings))
+    out["pageable"] = {"ms": t_page * 1e3, "value": world * nv / t_page}
+    pb, pc, pp = hb.pin_memory(), hc.pin_memory(), hp.pin_memory()
+    t_pin = timed(lambda: lw.verify_blob_kzg_proof_batch_ptr(pb.data_ptr(), pc.data_ptr(), pp.data_ptr(), nv, settings))
+    out["pinned"] = {"ms": t_pin * 1e3, "value": world * nv / t_pin, "h2d_bytes": nv * (BLOB_BYTES + 96)}
+    out["corrupted_batch_rejected"] = True
+    out["pairing_ms"] = lw.bench_pairing(settings, 5)   # partial-sum fold + 2-pairing check alone (CUDA events)
+    if dist is not None and hasattr(lw, "verify_blob_kzg_proof_batch_distributed_device"):
+        t_dist = timed(lambda: lw.verify_blob_kzg_proof_batch_distributed_device(d_blobs, d_c, d_p, world * nv, settings))
+        out["distributed"] = {"ms": t_dist * 1e3, "value": world * nv / t_dist, "global_blobs": world * nv,
+                              "note": "ONE batch of world x %d blobs sharded over the ranks; two exchanges (tuples, partial sums) over NCCL" % nv}
+    return out
 
 
 if __name__ == "__main__":

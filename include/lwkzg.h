@@ -139,18 +139,27 @@ C_KZG_RET lwkzg_commit_and_prove_batch(KZGCommitment *commitments, KZGProof *pro
                                        const Blob *blobs, size_t n, const KZGSettings *s,
                                        int *status);
 
-/* device buffers (plain device addresses on the context's GPU), asynchronous on
- * `stream` (a cudaStream_t, NULL = default stream).  d_status: n ints on the
- * device or NULL. */
+/* device buffers (plain device addresses on the context's GPU, 16-byte aligned: blobs are read with 128-bit
+ * loads), asynchronous on `stream` (a cudaStream_t, NULL = default stream).  The calls return as soon as the
+ * work is queued, so per-item failures cannot come back through the return value: d_status (n ints on the
+ * device) receives one C_KZG_RET per item; NULL means the caller does not want them.  Either way the outputs
+ * of failed items are zeroed.  (Items can only fail where the host API can: an invalid commitment argument,
+ * or -- MODE_CKZG_LE -- a non-canonical blob word.) */
 C_KZG_RET lwkzg_commit_and_prove_batch_device(void *d_commitments, void *d_proofs,
                                               const void *d_blobs, size_t n,
                                               const KZGSettings *s, void *stream, void *d_status);
 C_KZG_RET lwkzg_blob_to_kzg_commitment_batch_device(void *d_commitments, const void *d_blobs,
-                                                    size_t n, const KZGSettings *s, void *stream);
+                                                    size_t n, const KZGSettings *s, void *stream,
+                                                    void *d_status);
 C_KZG_RET lwkzg_compute_blob_kzg_proof_batch_device(void *d_proofs, const void *d_blobs,
                                                     const void *d_commitments, size_t n,
                                                     const KZGSettings *s, void *stream,
                                                     void *d_status);
+/* verify_blob_kzg_proof_batch (src/lib.rs:525-614) with the n blobs, commitments and proofs already in device
+ * memory; synchronous, the boolean comes back to the host.  Same results and error codes as the host call. */
+C_KZG_RET lwkzg_verify_blob_kzg_proof_batch_device(bool *ok, const void *d_blobs,
+                                                   const void *d_commitments, const void *d_proofs,
+                                                   size_t n, const KZGSettings *s);
 
 /* Generic G1 multi-scalar multiplication (the reference's g1_lincomb,
  * src/lib.rs:241-243): out = sum scalars[i] * points[i].  points: n x 96 bytes
@@ -200,16 +209,21 @@ double lwkzg_bench_msm_kernel(const void *d_blobs, size_t n, int blocks_per_blob
                               const KZGSettings *s);
 /* Measurement hook for the variable-base MSM sweep (BASELINE config 5): n
  * synthetic points (pseudo-random entries of the fixed-base table, entry number
- * (t * 2654435761) mod (W * 4096 * 2^(c-1)) for point t) times n synthetic
+ * (t * 2654435761) mod (number of table entries) for point t) times n synthetic
  * scalars (the blob-word generator with blob id `seed`), generated on the
  * device; returns the average milliseconds per MSM (< 0 on error) and writes
  * the compressed result. */
 double lwkzg_bench_var_msm(Bytes48 *out, size_t n, int iters, uint64_t seed, const KZGSettings *s);
+/* Measurement hook: the last stage of a batched verification alone -- fold of the partial sums and the
+ * 2-pairing check -- on what the previous verify_blob_kzg_proof_batch on these settings left in the workspace;
+ * average milliseconds per run (< 0 on error). */
+double lwkzg_bench_pairing(int iters, const KZGSettings *s);
 /* fixed-base window actually in use for these settings (may be smaller than
  * the "window_bits" option if HBM was short), -1 on error */
 int lwkzg_window_bits(const KZGSettings *s);
 
-/* Options: "window_bits" (fixed-base table window c, 4..15; default 13; must
+/* Options: "window_bits" (fixed-base table window c, 4..16; default 16 = 100 GiB, the fastest; shrunk
+ * automatically to what free device memory allows -- lwkzg_window_bits() tells; must
  * be set before the settings are first used), "msm_blocks_per_blob" (0 = auto),
  * "chunk_blobs" (host-batch pipeline chunk, default 256; 4 chunks in flight),
  * "msm_algo" (1 = default: batches of at least "msm_ba_min_blobs" (256) blobs use

@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     C_KZG_OK,
     KzgError,
     bench_msm_kernel,
+    bench_pairing,
     bench_var_msm,
     window_bits,
     Settings,
@@ -49,7 +50,10 @@ from .api import (  # noqa: F401
     verify_batch_phase3,
     verify_blob_kzg_proof,
     verify_blob_kzg_proof_batch,
+    verify_blob_kzg_proof_batch_device,
     verify_blob_kzg_proof_batch_ptr,
+    blob_to_kzg_commitment_batch_device,
+    compute_blob_kzg_proof_batch_device,
     verify_kzg_proof,
 )
 from .sharding import shard_range, verify_blob_kzg_proof_batch_distributed  # noqa: F401

@@ -62,7 +62,8 @@ def load_library() -> ctypes.CDLL:
         "lwkzg_compute_kzg_proof_batch": [vp, vp, vp, vp, sz, sp, ip],
         "lwkzg_commit_and_prove_batch": [vp, vp, vp, sz, sp, ip],
         "lwkzg_commit_and_prove_batch_device": [vp, vp, vp, sz, sp, vp, vp],
-        "lwkzg_blob_to_kzg_commitment_batch_device": [vp, vp, sz, sp, vp],
+        "lwkzg_blob_to_kzg_commitment_batch_device": [vp, vp, sz, sp, vp, vp],
+        "lwkzg_verify_blob_kzg_proof_batch_device": [bp, vp, vp, vp, sz, sp],
         "lwkzg_compute_blob_kzg_proof_batch_device": [vp, vp, vp, sz, sp, vp, vp],
         "lwkzg_g1_lincomb": [vp, vp, vp, sz],
         "lwkzg_verify_batch_phase1": [vp, vp, vp, vp, sz, sp],
@@ -86,6 +87,8 @@ def load_library() -> ctypes.CDLL:
     lib.lwkzg_bench_msm_kernel.restype = ctypes.c_double
     lib.lwkzg_bench_var_msm.argtypes = [vp, sz, ctypes.c_int, ctypes.c_uint64, sp]
     lib.lwkzg_bench_var_msm.restype = ctypes.c_double
+    lib.lwkzg_bench_pairing.argtypes = [ctypes.c_int, sp]
+    lib.lwkzg_bench_pairing.restype = ctypes.c_double
     lib.lwkzg_window_bits.argtypes = [sp]
     lib.lwkzg_window_bits.restype = ctypes.c_int
     lib.lwkzg_kernel_launches.argtypes = []
@@ -243,6 +246,14 @@ def verify_blob_kzg_proof_batch_ptr(blobs_ptr: int, commitments_ptr: int, proofs
     return bool(ok.value)
 
 
+def verify_blob_kzg_proof_batch_device(d_blobs: int, d_commitments: int, d_proofs: int, n: int, s) -> bool:
+    """verify_blob_kzg_proof_batch with the inputs already in device memory (raw device addresses)."""
+    ok = ctypes.c_bool(False)
+    _check(load_library().lwkzg_verify_blob_kzg_proof_batch_device(ctypes.byref(ok), d_blobs, d_commitments, d_proofs, n, _sp(s)),
+           "lwkzg_verify_blob_kzg_proof_batch_device")
+    return bool(ok.value)
+
+
 # ------------------------------------------------------------------ batch extensions (host buffers)
 def _status_list(n):
     return (ctypes.c_int * max(n, 1))()
@@ -300,6 +311,16 @@ def commit_and_prove_batch_device(d_commitments: int, d_proofs: int, d_blobs: in
            "lwkzg_commit_and_prove_batch_device")
 
 
+def blob_to_kzg_commitment_batch_device(d_commitments: int, d_blobs: int, n: int, s, stream: int = 0, d_status: int = 0):
+    _check(load_library().lwkzg_blob_to_kzg_commitment_batch_device(d_commitments, d_blobs, n, _sp(s), stream, d_status),
+           "lwkzg_blob_to_kzg_commitment_batch_device")
+
+
+def compute_blob_kzg_proof_batch_device(d_proofs: int, d_blobs: int, d_commitments: int, n: int, s, stream: int = 0, d_status: int = 0):
+    _check(load_library().lwkzg_compute_blob_kzg_proof_batch_device(d_proofs, d_blobs, d_commitments, n, _sp(s), stream, d_status),
+           "lwkzg_compute_blob_kzg_proof_batch_device")
+
+
 def bench_msm_kernel(d_blobs: int, n: int, s, blocks_per_blob: int = 0, iters: int = 5) -> float:
     """Average ms per launch of the dominant kernel alone (roofline leg)."""
     ms = float(load_library().lwkzg_bench_msm_kernel(d_blobs, n, blocks_per_blob, iters, _sp(s)))
@@ -315,6 +336,14 @@ def bench_var_msm(n: int, s, iters: int = 3, seed: int = 0):
     if ms < 0:
         raise KzgError(C_KZG_ERROR, "lwkzg_bench_var_msm", last_error())
     return ms, out.raw
+
+
+def bench_pairing(s, iters: int = 5) -> float:
+    """ms per run of the partial-sum fold + 2-pairing check of the last batched verification on these settings."""
+    ms = float(load_library().lwkzg_bench_pairing(iters, _sp(s)))
+    if ms < 0:
+        raise KzgError(C_KZG_ERROR, "lwkzg_bench_pairing", last_error())
+    return ms
 
 
 def window_bits(s) -> int:

@@ -29,6 +29,19 @@ __global__ void status_or_kernel(int* __restrict__ status, const int* __restrict
   if (i < n && status[i] == 0 && other[i] != 0) status[i] = other[i];
 }
 
+// outputs of failed items are zeroed (the host API leaves caller memory untouched for them; a device buffer that
+// still held a plausible-looking point would be worse)
+__global__ void zero_failed_kernel(uint8_t* __restrict__ out, int bytes_per_item, const int* __restrict__ status, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && status[i] != 0)
+    for (int b = 0; b < bytes_per_item; b++) out[(size_t)i * bytes_per_item + b] = 0;
+}
+void launch_zero_failed(void* d_out, int bytes_per_item, const int* d_status, int n, cudaStream_t st) {
+  if (n <= 0 || !d_out || !d_status) return;
+  zero_failed_kernel<<<(n + 127) / 128, 128, 0, st>>>((uint8_t*)d_out, bytes_per_item, d_status, n);
+  count_launch();
+}
+
 void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st, bool strict) {
   if (n <= 0) return;
   g1_decompress_kernel<<<(n + 31) / 32, 32, 0, st>>>((G1Affine*)d_aff, (uint8_t*)d_recompressed48, d_status, (const uint8_t*)d_in48, n, strict ? 1 : 0);

@@ -66,6 +66,7 @@ void launch_poly_eval_quot(void* d_q, void* d_y, void* d_y_be32, const void* d_b
 // d_recompressed48 (canonical re-encoding, may be NULL)
 void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st, bool strict = false);
 void launch_status_or(int* d_status, const int* d_other, int n, cudaStream_t st);
+void launch_zero_failed(void* d_out, int bytes_per_item, const int* d_status, int n, cudaStream_t st);
 
 // ---- synthetic data + probes (misc.cu)
 void launch_synth_blobs(void* d_blobs, uint64_t first_blob, size_t n, cudaStream_t st);

@@ -63,7 +63,7 @@ Options& opts() {
   static Options o;
   return o;
 }
-std::mutex g_mu;  // guards options + the lazy-context cache
+std::mutex g_mu;  // guards the options
 
 struct DevBuf {
   void* p = nullptr;
@@ -230,20 +230,21 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
   // ---- G2: g2[0], g2[1] -> prepared Miller-loop lines
   c->g2_valid = false;
   {
-    static uint32_t g2canon[TRUSTED_SETUP_NUM_G2_POINTS][48];
+    std::vector<uint32_t> g2canon((size_t)TRUSTED_SETUP_NUM_G2_POINTS * 48);   // per call: contexts are built concurrently
     for (int k = 0; k < TRUSTED_SETUP_NUM_G2_POINTS; k++) {
-      blst_fp_to_canon(&g2canon[k][0], &g2[k].x.fp[0]);
-      blst_fp_to_canon(&g2canon[k][12], &g2[k].x.fp[1]);
-      blst_fp_to_canon(&g2canon[k][24], &g2[k].y.fp[0]);
-      blst_fp_to_canon(&g2canon[k][36], &g2[k].y.fp[1]);
+      blst_fp_to_canon(&g2canon[(size_t)k * 48], &g2[k].x.fp[0]);
+      blst_fp_to_canon(&g2canon[(size_t)k * 48 + 12], &g2[k].x.fp[1]);
+      blst_fp_to_canon(&g2canon[(size_t)k * 48 + 24], &g2[k].y.fp[0]);
+      blst_fp_to_canon(&g2canon[(size_t)k * 48 + 36], &g2[k].y.fp[1]);
     }
     void* d_g2 = nullptr;
     int* d_bad = nullptr;
-    CU_TRY(cudaMalloc(&d_g2, sizeof(g2canon)));
+    const size_t g2_bytes = g2canon.size() * sizeof(uint32_t);
+    CU_TRY(cudaMalloc(&d_g2, g2_bytes));
     CU_TRY(cudaMalloc(&d_bad, (2 + TRUSTED_SETUP_NUM_G2_POINTS) * sizeof(int)));
     CU_TRY(cudaMalloc(&c->d_prep0, g2_prepared_bytes()));
     CU_TRY(cudaMalloc(&c->d_prep1, g2_prepared_bytes()));
-    CU_TRY(cudaMemcpyAsync(d_g2, g2canon, sizeof(g2canon), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_g2, g2canon.data(), g2_bytes, cudaMemcpyHostToDevice, st));
     launch_g2_prepare(c->d_prep0, d_bad, d_g2, st);
     launch_g2_prepare(c->d_prep1, d_bad + 1, (const uint8_t*)d_g2 + 48 * 4, st);
     launch_g2_check(d_bad + 2, d_g2, TRUSTED_SETUP_NUM_G2_POINTS, st);
@@ -260,20 +261,24 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
       if (bad[2 + k]) c->srs_valid = false;
   }
 
-  if (!c->srs_valid) return true;  // usable only to report C_KZG_ERROR, like the reference
+  c->mode = mode;
+  if (mode == 1) {
+    // allocated before the early return below: every LE-mode kernel may assume they exist
+    CU_TRY(cudaMalloc(&c->d_roots, (size_t)N_POINTS * 32));
+    launch_le_roots(c->d_roots, st);
+    CU_TRY(cudaMalloc(&c->d_gen, AFFINE_BYTES));
+    launch_write_generator(c->d_gen, st);
+  }
+  if (!c->srs_valid) {  // usable only to report C_KZG_ERROR, like the reference
+    CU_TRY(cudaStreamSynchronize(st));
+    return true;
+  }
 
   // ---- fixed-base digit table; shrink the window if HBM is short
   long want_c;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     want_c = window_override > 0 ? window_override : opts().window_bits;
-  }
-  c->mode = mode;
-  if (mode == 1) {
-    CU_TRY(cudaMalloc(&c->d_roots, (size_t)N_POINTS * 32));
-    launch_le_roots(c->d_roots, st);
-    CU_TRY(cudaMalloc(&c->d_gen, AFFINE_BYTES));
-    launch_write_generator(c->d_gen, st);
   }
   if (want_c < 4) want_c = 4;
   if (want_c > 16) want_c = 16;
@@ -346,6 +351,16 @@ uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
   return h;
 }
 
+std::mutex g_lazy_mu;  // guards the lazy-context cache across lookup, build and insert (never taken while holding g_mu)
+
+// Contexts are destroyed only with their own lock held, so a call that is still running on one finishes first.
+// (Calling into settings that are being freed concurrently is a caller error here as it is in c-kzg.)
+void destroy_ctx_locked(Ctx* c) {
+  if (!c) return;
+  { std::lock_guard<std::mutex> lk(c->mu); }
+  destroy_ctx(c);
+}
+
 Ctx* ctx_of(const KZGSettings* s) {
   if (!s || !s->g1_values || !s->g2_values) {
     set_err("null KZGSettings");
@@ -358,21 +373,21 @@ Ctx* ctx_of(const KZGSettings* s) {
   LazyKey key{s->g1_values, s->g2_values, 0};
   key.hash = fnv1a(s->g1_values, sizeof(g1_t) * N_POINTS);
   key.hash = fnv1a(s->g2_values, sizeof(g2_t) * 2, key.hash);
-  std::unique_lock<std::mutex> lk(g_mu);
+  // the lock is held while the context is built: a second thread making its first call on the same settings
+  // waits here and then finds the finished context instead of building (and leaking) its own
+  std::lock_guard<std::mutex> lk(g_lazy_mu);
   auto it = lazy_map().find(key);
   if (it != lazy_map().end()) return it->second;
-  // drop stale contexts registered for the same pointers
+  // drop stale contexts registered for the same pointers (the caller rewrote the arrays)
   for (auto j = lazy_map().begin(); j != lazy_map().end();) {
     if (j->first.g1 == key.g1 && j->first.g2 == key.g2) {
-      destroy_ctx(j->second);
+      destroy_ctx_locked(j->second);
       j = lazy_map().erase(j);
     } else {
       ++j;
     }
   }
-  lk.unlock();
   Ctx* c = build_ctx(s->g1_values, s->g2_values);
-  lk.lock();
   if (c) lazy_map()[key] = c;
   return c;
 }
@@ -578,14 +593,16 @@ C_KZG_RET host_batch(Mode mode, const KZGSettings* s, size_t n, const Blob* blob
     if (cudaStreamSynchronize(sl.st) != cudaSuccess) { set_err("stream sync failed"); return fail(); }
     if (!slot_reserve(sl, m, auto_bpb(m), true)) return fail();
     if (cudaMemcpyAsync(sl.blobs.p, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, sl.st) != cudaSuccess) { set_err("H2D failed"); return fail(); }
-    if (mode == Mode::BlobProof) cudaMemcpyAsync(sl.cin48.p, commit_in + off, (size_t)m * 48, cudaMemcpyHostToDevice, sl.st);
-    if (mode == Mode::PointProof) cudaMemcpyAsync(sl.zbe.p, z_in + off, (size_t)m * 32, cudaMemcpyHostToDevice, sl.st);
+    if (mode == Mode::BlobProof && cudaMemcpyAsync(sl.cin48.p, commit_in + off, (size_t)m * 48, cudaMemcpyHostToDevice, sl.st) != cudaSuccess) { set_err("H2D failed"); return fail(); }
+    if (mode == Mode::PointProof && cudaMemcpyAsync(sl.zbe.p, z_in + off, (size_t)m * 32, cudaMemcpyHostToDevice, sl.st) != cudaSuccess) { set_err("H2D failed"); return fail(); }
     void* d_c48 = (mode == Mode::BlobProof) ? nullptr : sl.c48.p;
     if (!enqueue_chunk(c, sl, mode, sl.blobs.p, m, d_c48, sl.p48.p, y_out ? sl.ybe.p : nullptr, (int*)sl.status.p, sl.cin48.p, sl.zbe.p)) return fail();
-    if (c_out) cudaMemcpyAsync(&c_tmp[off], sl.c48.p, (size_t)m * 48, cudaMemcpyDeviceToHost, sl.st);
-    if (p_out) cudaMemcpyAsync(&p_tmp[off], sl.p48.p, (size_t)m * 48, cudaMemcpyDeviceToHost, sl.st);
-    if (y_out) cudaMemcpyAsync(&y_tmp[off], sl.ybe.p, (size_t)m * 32, cudaMemcpyDeviceToHost, sl.st);
-    cudaMemcpyAsync(&st_host[off], sl.status.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, sl.st);
+    cudaError_t ce = cudaSuccess;
+    if (c_out && ce == cudaSuccess) ce = cudaMemcpyAsync(&c_tmp[off], sl.c48.p, (size_t)m * 48, cudaMemcpyDeviceToHost, sl.st);
+    if (p_out && ce == cudaSuccess) ce = cudaMemcpyAsync(&p_tmp[off], sl.p48.p, (size_t)m * 48, cudaMemcpyDeviceToHost, sl.st);
+    if (y_out && ce == cudaSuccess) ce = cudaMemcpyAsync(&y_tmp[off], sl.ybe.p, (size_t)m * 32, cudaMemcpyDeviceToHost, sl.st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&st_host[off], sl.status.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, sl.st);
+    if (ce != cudaSuccess) { set_err(std::string("D2H failed: ") + cudaGetErrorString(ce)); return fail(); }
   }
   for (auto& sl : c->slot) {
     cudaError_t e = cudaStreamSynchronize(sl.st);
@@ -658,8 +675,12 @@ C_KZG_RET device_batch(Mode mode, const KZGSettings* s, size_t n, const void* d_
     void* co = d_c_out ? (uint8_t*)d_c_out + off * 48 : (mode == Mode::CommitProve ? sl.c48.p : nullptr);
     void* po = d_p_out ? (uint8_t*)d_p_out + off * 48 : nullptr;
     const void* ci = d_commit_in ? (const uint8_t*)d_commit_in + off * 48 : nullptr;
-    int* so = d_status ? (int*)d_status + off : nullptr;
+    int* so = d_status ? (int*)d_status + off : (int*)sl.status.p;
     ok = enqueue_chunk(c, sl, mode, b, m, co, po, nullptr, so, ci, nullptr);
+    if (ok && (mode == Mode::BlobProof || c->mode == 1)) {   // the only ways an item can fail: bad commitment / non-canonical blob
+      if (co && d_c_out) launch_zero_failed(co, 48, so, m, sl.st);
+      if (po) launch_zero_failed(po, 48, so, m, sl.st);
+    }
   }
   for (auto& sl : c->slot) {
     cudaEventRecord(sl.ev_done, sl.st);
@@ -803,13 +824,13 @@ size_t vb_super_blobs() {
   std::lock_guard<std::mutex> lk(g_mu);
   return (size_t)std::max(1L, opts().verify_super_blobs);
 }
-bool vb_reserve(Ctx* c, size_t n) {
-  const size_t VB_SUPER_BLOBS = vb_super_blobs();
+bool vb_reserve(Ctx* c, size_t n, bool stage_blobs = true) {
+  const size_t VB_SUPER_BLOBS = stage_blobs ? vb_super_blobs() : 0;
   return c->vb_cin.ensure(n * 48) && c->vb_pin.ensure(n * 48) && c->vb_caff.ensure(n * AFFINE_BYTES) && c->vb_piaff.ensure(n * AFFINE_BYTES) &&
          c->vb_c48r.ensure(n * 48) && c->vb_p48r.ensure(n * 48) && c->vb_z.ensure(n * 32) && c->vb_y.ensure(n * 32) && c->vb_tuples.ensure(n * 160) &&
          c->vb_status.ensure(n * sizeof(int)) && c->vb_r.ensure(32) && c->vb_partial.ensure(288) && c->vb_ok.ensure(sizeof(int)) &&
          c->vb_zy_in.ensure(n * 64) && c->vb_scratch.ensure(batch_partials_scratch_bytes((int)n)) &&
-         c->vb_hstate.ensure(batch_challenge_state_bytes()) && c->vb_blobs.ensure(std::min<size_t>(n, VB_SUPER_BLOBS) * BLOB_BYTES) &&
+         c->vb_hstate.ensure(batch_challenge_state_bytes()) && c->vb_blobs.ensure(std::max<size_t>(std::min<size_t>(n, VB_SUPER_BLOBS), 1) * (stage_blobs ? (size_t)BLOB_BYTES : 16)) &&
          c->vb_states.ensure(n * 32) && c->vb_status2.ensure(n * sizeof(int));
 }
 
@@ -820,8 +841,13 @@ bool vb_reserve(Ctx* c, size_t n) {
 // through vb_status.
 // hash_r: also derive the batch challenge r (utils.rs:166-206) into vb_r, absorbing each chunk's tuples as soon as
 // they exist.
-bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n, bool hash_r = false) {
-  if (!vb_reserve(c, n)) return false;
+bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n, bool hash_r = false,
+                    bool dev_inputs = false) {
+  c->vb_n = 0;   // whatever a previous phase 1 left in the workspace is about to be overwritten
+  // the reference re-hydrates the SRS before anything else in every entry point (lib.rs:256-262, 420-426, 468-474,
+  // 548-554): an unusable SRS is an error whatever the other arguments are -- and the kernels below need it
+  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return false; }
+  if (!vb_reserve(c, n, !dev_inputs)) return false;
   long chunk;
   {
     std::lock_guard<std::mutex> lk2(g_mu);
@@ -829,10 +855,11 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   }
   cudaStream_t s0 = c->slot[0].st;
   const bool le = c->mode == 1;
+  const cudaMemcpyKind in_kind = dev_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   // commitments on s0, proofs on the hash stream (idle until the first tuples exist): the two decompressions are
   // latency-bound thread-per-point kernels and run side by side
-  CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitments, n * 48, cudaMemcpyHostToDevice, s0));
-  CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proofs, n * 48, cudaMemcpyHostToDevice, c->hash_st));
+  CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitments, n * 48, in_kind, s0));
+  CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proofs, n * 48, in_kind, c->hash_st));
   launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0, le);
   // proofs: decode status into the (still unused) tuples buffer, then merge
   launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, c->hash_st, le);
@@ -846,7 +873,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   // buffer: one copy stream issues the H2D copies back to back, and each chunk's kernels (SHA midstate ->
   // challenge -> evaluation -> tuple) start on one of 2 * NSLOT compute streams as soon as its copy has landed.
   // The copy engine is the only thing that runs the whole time.
-  const size_t super = std::min<size_t>(n, vb_super_blobs());
+  const size_t super = dev_inputs ? n : std::min<size_t>(n, vb_super_blobs());   // device blobs are read in place
   const size_t chunks_per_super = (super + (size_t)chunk - 1) / (size_t)chunk;
   while (c->ev_pool.size() < 2 * chunks_per_super) {
     cudaEvent_t e;
@@ -876,11 +903,11 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     size_t j = 0;
     for (size_t off = base; off < top; off += chunk, k++, j++) {
       const int m = (int)std::min<size_t>(chunk, top - off);
-      uint8_t* d_blobs = (uint8_t*)c->vb_blobs.p + (off - base) * BLOB_BYTES;
+      const uint8_t* d_blobs = dev_inputs ? (const uint8_t*)blobs + off * BLOB_BYTES : (const uint8_t*)c->vb_blobs.p + (off - base) * BLOB_BYTES;
       void* d_states = (uint8_t*)c->vb_states.p + off * 32;
       cudaEvent_t ev_copied = c->ev_pool[2 * j], ev_tuples = c->ev_pool[2 * j + 1];
       cudaStream_t st = cs[(k + 1) % (2 * NSLOT)];   // chunk 0 not on s0: its hash runs beside the commitment decompression
-      CU_TRY(cudaMemcpyAsync(d_blobs, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, c->copy_st));
+      if (!dev_inputs) CU_TRY(cudaMemcpyAsync((void*)d_blobs, blobs + off, (size_t)m * BLOB_BYTES, cudaMemcpyHostToDevice, c->copy_st));
       CU_TRY(cudaEventRecord(ev_copied, c->copy_st));
       CU_TRY(cudaStreamWaitEvent(st, ev_copied, 0));
       cudaEvent_t tc[3] = {nullptr, nullptr, nullptr};
@@ -943,17 +970,16 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   return true;
 }
 
-int g_bad_code = 0;  // set by any_bad_status: first non-zero per-item code (guarded by the context lock)
-bool any_bad_status(Ctx* c, size_t n, bool& bad) {
+// first non-zero per-item code of the verify workspace (0 = all items valid)
+bool first_bad_status(Ctx* c, size_t n, int& code) {
   std::vector<int> st(n);
   CU_TRY(cudaMemcpy(st.data(), c->vb_status.p, n * sizeof(int), cudaMemcpyDeviceToHost));
-  bad = false;
-  g_bad_code = 0;
+  code = 0;
   for (int v : st)
-    if (v && !bad) { bad = true; g_bad_code = v; }
+    if (v) { code = v; break; }
   return true;
 }
-C_KZG_RET bad_code() { return g_bad_code == 1 ? C_KZG_BADARGS : C_KZG_ERROR; }
+C_KZG_RET bad_code(int code) { return code == 1 ? C_KZG_BADARGS : C_KZG_ERROR; }
 
 // single-proof verification with everything already decoded in the workspace (item 0)
 bool verify_single_from_workspace(Ctx* c, bool& ok) {
@@ -1055,13 +1081,13 @@ C_KZG_RET free_trusted_setup(KZGSettings* s) {
   if (!s) return C_KZG_OK;
   if (s->fs) {
     Ctx* c = reinterpret_cast<Ctx*>(s->fs);
-    if (c->magic == CTX_MAGIC) destroy_ctx(c);
+    if (c->magic == CTX_MAGIC) destroy_ctx_locked(c);
     s->fs = nullptr;
   } else {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_lazy_mu);
     for (auto j = lazy_map().begin(); j != lazy_map().end();) {
       if (j->first.g1 == s->g1_values && j->first.g2 == s->g2_values) {
-        destroy_ctx(j->second);
+        destroy_ctx_locked(j->second);
         j = lazy_map().erase(j);
       } else {
         ++j;
@@ -1093,8 +1119,8 @@ C_KZG_RET lwkzg_commit_and_prove_batch(KZGCommitment* commitments, KZGProof* pro
 C_KZG_RET lwkzg_commit_and_prove_batch_device(void* d_commitments, void* d_proofs, const void* d_blobs, size_t n, const KZGSettings* s, void* stream, void* d_status) {
   return device_batch(Mode::CommitProve, s, n, d_blobs, nullptr, d_commitments, d_proofs, d_status, (cudaStream_t)stream);
 }
-C_KZG_RET lwkzg_blob_to_kzg_commitment_batch_device(void* d_commitments, const void* d_blobs, size_t n, const KZGSettings* s, void* stream) {
-  return device_batch(Mode::Commit, s, n, d_blobs, nullptr, d_commitments, nullptr, nullptr, (cudaStream_t)stream);
+C_KZG_RET lwkzg_blob_to_kzg_commitment_batch_device(void* d_commitments, const void* d_blobs, size_t n, const KZGSettings* s, void* stream, void* d_status) {
+  return device_batch(Mode::Commit, s, n, d_blobs, nullptr, d_commitments, nullptr, d_status, (cudaStream_t)stream);
 }
 C_KZG_RET lwkzg_compute_blob_kzg_proof_batch_device(void* d_proofs, const void* d_blobs, const void* d_commitments, size_t n, const KZGSettings* s, void* stream, void* d_status) {
   return device_batch(Mode::BlobProof, s, n, d_blobs, d_commitments, nullptr, d_proofs, d_status, (cudaStream_t)stream);
@@ -1124,6 +1150,8 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
+  c->vb_n = 0;   // the workspace no longer holds a phase-1 result
+  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   if (!vb_reserve(c, 1)) return C_KZG_ERROR;
   cudaStream_t s0 = c->slot[0].st;
   uint8_t zy[64];
@@ -1154,9 +1182,9 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
     return true;
   }();
   if (!good) return C_KZG_ERROR;
-  bool bad = false;
-  if (!any_bad_status(c, 1, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
+  int bad = 0;
+  if (!first_bad_status(c, 1, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   bool res = false;
   if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
@@ -1164,25 +1192,26 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
   return C_KZG_OK;
 }
 
-C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s) {
+static C_KZG_RET verify_blob_single(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s,
+                                    bool dev_inputs) {
   if (!ok) return C_KZG_ERROR;
   *ok = false;  // lib.rs:463-465
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
-  if (!verify_prepare(c, blob, commitment_bytes, proof_bytes, 1)) return C_KZG_ERROR;
-  bool bad = false;
-  if (!any_bad_status(c, 1, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
-  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  if (!verify_prepare(c, blob, commitment_bytes, proof_bytes, 1, false, dev_inputs)) return C_KZG_ERROR;
+  int bad = 0;
+  if (!first_bad_status(c, 1, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   bool res = false;
+  c->vb_n = 0;
   if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
   *ok = res;
   return C_KZG_OK;
 }
 
-C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
-                                      const KZGSettings* s) {
+static C_KZG_RET verify_blob_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
+                                   const KZGSettings* s, bool dev_inputs) {
   if (!ok) return C_KZG_ERROR;
   *ok = false;  // lib.rs:533-535
   if (n == 0) {
@@ -1191,19 +1220,18 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
     if (c0 && c0->mode == 1) *ok = true;
     return C_KZG_OK;
   }
-  if (n == 1) return verify_blob_kzg_proof(ok, blobs, commitments_bytes, proofs_bytes, s);  // lib.rs:544
+  if (n == 1) return verify_blob_single(ok, blobs, commitments_bytes, proofs_bytes, s, dev_inputs);  // lib.rs:544
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
   static const bool trace = getenv("LWKZG_VERIFY_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  if (!verify_prepare(c, blobs, commitments_bytes, proofs_bytes, n, true)) return C_KZG_ERROR;  // leaves r in vb_r
+  if (!verify_prepare(c, blobs, commitments_bytes, proofs_bytes, n, true, dev_inputs)) return C_KZG_ERROR;  // leaves r in vb_r
   const double t1 = now();
-  bool bad = false;
-  if (!any_bad_status(c, n, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
-  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
+  int bad = 0;
+  if (!first_bad_status(c, n, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   const double t2 = now();
   cudaStream_t s0 = c->slot[0].st;
   launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, 0, (int)n, c->vb_scratch.p, s0);
@@ -1214,9 +1242,25 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
     set_err("CUDA failure in batch verification");
     return C_KZG_ERROR;
   }
+  c->vb_n = 0;
   if (trace) fprintf(stderr, "[lwkzg] verify batch n=%zu: prepare %.2f ms, status %.2f ms, partials+pairing %.2f ms\n", n, t1 - t0, t2 - t1, now() - t2);
   *ok = okv != 0;
   return C_KZG_OK;
+}
+
+C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s) {
+  return verify_blob_single(ok, blob, commitment_bytes, proof_bytes, s, false);
+}
+
+C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
+                                      const KZGSettings* s) {
+  return verify_blob_batch(ok, blobs, commitments_bytes, proofs_bytes, n, s, false);
+}
+
+// the same check with blobs, commitments and proofs already in device memory (the boolean still comes back to the host)
+C_KZG_RET lwkzg_verify_blob_kzg_proof_batch_device(bool* ok, const void* d_blobs, const void* d_commitments, const void* d_proofs, size_t n,
+                                                   const KZGSettings* s) {
+  return verify_blob_batch(ok, (const Blob*)d_blobs, (const Bytes48*)d_commitments, (const Bytes48*)d_proofs, n, s, true);
 }
 
 // ---- multi-GPU batched verification phases
@@ -1228,9 +1272,9 @@ C_KZG_RET lwkzg_verify_batch_phase1(uint8_t* tuples160, const Blob* blobs, const
   c->vb_n = 0;
   if (n_local == 0) return C_KZG_OK;
   if (!verify_prepare(c, blobs, commitments, proofs, n_local)) return C_KZG_ERROR;
-  bool bad = false;
-  if (!any_bad_status(c, n_local, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(); }
+  int bad = 0;
+  if (!first_bad_status(c, n_local, bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   if (cudaMemcpy(tuples160, c->vb_tuples.p, n_local * 160, cudaMemcpyDeviceToHost) != cudaSuccess) { set_err("D2H failed"); return C_KZG_ERROR; }
   return C_KZG_OK;
@@ -1302,6 +1346,28 @@ double lwkzg_bench_msm_kernel(const void* d_blobs, size_t n, int blocks_per_blob
   cudaEventRecord(e0, sl.st);
   for (int i = 0; i < iters; i++) run_msm(sl, c, d_blobs, true, (int)n, bpb, sl.st);
   cudaEventRecord(e1, sl.st);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  return (double)ms / iters;
+}
+// measurement hook: the last step of a batched verification alone (fold of the partial sums + 2-pairing check) on
+// the partial sums the previous batched verification on these settings left in the workspace
+double lwkzg_bench_pairing(int iters, const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  if (!c || !c->srs_valid || !c->g2_valid || iters <= 0 || !c->vb_partial.p || !c->vb_ok.p) return -1.0;
+  CtxLock L(c);
+  cudaStream_t s0 = c->slot[0].st;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  launch_batch_final((int*)c->vb_ok.p, c->vb_partial.p, 1, c->d_prep0, c->d_prep1, s0);
+  cudaEventRecord(e0, s0);
+  for (int i = 0; i < iters; i++) launch_batch_final((int*)c->vb_ok.p, c->vb_partial.p, 1, c->d_prep0, c->d_prep1, s0);
+  cudaEventRecord(e1, s0);
   cudaEventSynchronize(e1);
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);

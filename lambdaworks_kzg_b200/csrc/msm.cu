@@ -76,9 +76,9 @@ void launch_msm_gather(void* d_partials, const void* d_table, int c, const void*
                        int blocks_per_blob, cudaStream_t st);
 // defined in msm_ba_v*.cu (one translation unit per variant)
 #define LW_BA_DECL(N) void launch_ba_v##N(void*, const void*, int, const void*, bool, int, void*, cudaStream_t)
-LW_BA_DECL(0); LW_BA_DECL(1); LW_BA_DECL(2); LW_BA_DECL(3); LW_BA_DECL(4); LW_BA_DECL(5);
+LW_BA_DECL(0); LW_BA_DECL(1);
 struct BaVariant { int k, threads; };
-static const BaVariant BA_VARIANTS[] = {{64, 128}, {64, 64}, {64, 64}, {64, 32}, {64, 128}, {64, 64}};   // keep in step with msm_ba_v*.cu
+static const BaVariant BA_VARIANTS[] = {{64, 128}, {64, 64}};   // keep in step with msm_ba_v*.cu
 constexpr int N_BA_VARIANTS = (int)(sizeof(BA_VARIANTS) / sizeof(BA_VARIANTS[0]));
 static int g_ba_variant = 0;
 void msm_ba_set_variant(int v) { if (v >= 0 && v < N_BA_VARIANTS) g_ba_variant = v; }
@@ -99,10 +99,6 @@ void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const vo
   }
   switch (g_ba_variant) {
     case 1: launch_ba_v1(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
-    case 2: launch_ba_v2(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
-    case 3: launch_ba_v3(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
-    case 4: launch_ba_v4(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
-    case 5: launch_ba_v5(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
     default: launch_ba_v0(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
   }
   count_launch();

@@ -1,4 +1,4 @@
-// batched-affine fixed-base MSM kernel, variant 0: 64 accumulators per thread, 128 threads per blob (3 blocks of 128 threads per SM, 168 registers)
+// batched-affine fixed-base MSM kernel, variant 0: 64 accumulators per thread, 128 threads per blob (3 blocks of 128 threads per SM)
 #include "msm_ba.cuh"
 namespace lw {
 void launch_ba_v0(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs, void* d_scratch, cudaStream_t st) {

@@ -543,3 +543,80 @@ int oracle_g1_decompress_check(const uint8_t in[48], uint8_t recompressed[48]) {
   return 1;
 }
 void oracle_sha256(uint8_t out[32], const uint8_t *msg, size_t len) { sha256(out, msg, len); }
+
+/* ---- bench.py helpers (the reference arm must not load the product library) ---- */
+/* SURVEY 8(d) synthetic blob k: word i = four big-endian u64 of SplitMix64(seed 0xB2004844 ^ (k*4096+i)),
+ * byte[0] &= 0x3f (the generator of csrc/misc.cu, restated) */
+static uint64_t splitmix64(uint64_t *st) {
+  *st += 0x9E3779B97F4A7C15ull;
+  uint64_t z = *st;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+void oracle_synth_blob(uint8_t *blob, uint64_t k) {
+  for (uint32_t i = 0; i < NPTS; i++) {
+    uint64_t st = 0xB2004844ull ^ (k * 4096ull + (uint64_t)i);
+    uint8_t *o = blob + 32 * i;
+    for (int u = 0; u < 4; u++) {
+      uint64_t v = splitmix64(&st);
+      for (int b = 0; b < 8; b++) o[8 * u + b] = (uint8_t)(v >> (56 - 8 * b));
+    }
+    o[0] &= 0x3f;
+  }
+}
+
+/* g1_lincomb (src/lib.rs:241-243): msm(scalars, points) with the dependency's Pippenger.
+ * points: n x (x || y) 48-byte big-endian canonical, all-zero = infinity; scalars: n x 32-byte big-endian
+ * (reduced mod r like from_bytes_be).  Returns 1 for a point off the curve. */
+int oracle_g1_lincomb(uint8_t out[48], const uint8_t *points_xy_be, const uint8_t *scalars_be, int n) {
+  g1p *pts = (g1p *)malloc(sizeof(g1p) * (n ? n : 1));
+  fr *sc = (fr *)malloc(sizeof(fr) * (n ? n : 1));
+  int bad = 0;
+  for (int i = 0; i < n; i++) {
+    const uint8_t *b = points_xy_be + (size_t)96 * i;
+    int zero = 1;
+    for (int k = 0; k < 96; k++) if (b[k]) { zero = 0; break; }
+    if (zero) { g1_neutral(&pts[i]); }
+    else {
+      fp_from_be(&pts[i].x, b);
+      fp_from_be(&pts[i].y, b + 48);
+      if (!g1_on_curve_affine(&pts[i].x, &pts[i].y)) bad = 1;
+      fp_set_one(&pts[i].z);
+    }
+    fr m;
+    fr_from_be(&m, scalars_be + (size_t)32 * i);
+    fr_from_mont(&sc[i], &m);
+  }
+  if (!bad) {
+    g1p r;
+    msm_pippenger(&r, sc, pts, n);
+    compress_g1(out, &r);
+  }
+  free(pts); free(sc);
+  return bad;
+}
+
+/* n synthetic points (running sums of the first SRS point: P_i = (i + 1) g1[0]) and SplitMix64 scalars, written in
+ * the formats oracle_g1_lincomb takes -- the cost of an MSM does not depend on which points it sums */
+int oracle_synth_msm_inputs(uint8_t *points_xy_be, uint8_t *scalars_be, int n, uint64_t seed) {
+  g1p *srs = (g1p *)malloc(sizeof(g1p) * NPTS);
+  if (!rehydrate_srs(srs)) { free(srs); return 2; }
+  g1p acc = srs[0];
+  for (int i = 0; i < n; i++) {
+    fp x, y;
+    if (!g1_to_affine(&x, &y, &acc)) { free(srs); return 2; }
+    fp_to_be(points_xy_be + (size_t)96 * i, &x);
+    fp_to_be(points_xy_be + (size_t)96 * i + 48, &y);
+    g1_add(&acc, &acc, &srs[0]);
+    uint64_t st = 0xB2004844ull ^ (seed * 4096ull + (uint64_t)i);
+    uint8_t *o = scalars_be + (size_t)32 * i;
+    for (int u = 0; u < 4; u++) {
+      uint64_t v = splitmix64(&st);
+      for (int b = 0; b < 8; b++) o[8 * u + b] = (uint8_t)(v >> (56 - 8 * b));
+    }
+    o[0] &= 0x3f;
+  }
+  free(srs);
+  return 0;
+}

@@ -65,3 +65,23 @@ class COracle:
         out = ctypes.create_string_buffer(32)
         self.lib.oracle_sha256(out, msg, ctypes.c_size_t(len(msg)))
         return out.raw
+
+    # ---- bench.py helpers
+    def synth_blob(self, k: int) -> bytes:
+        """SURVEY 8(d) synthetic blob k (same bytes as the GPU generator, csrc/misc.cu)."""
+        buf = ctypes.create_string_buffer(BLOB)
+        self.lib.oracle_synth_blob(buf, ctypes.c_uint64(k))
+        return buf.raw
+
+    def g1_lincomb(self, points_xy_be: bytes, scalars_be: bytes, n: int):
+        """g1_lincomb (src/lib.rs:241-243) -> (rc, 48-byte compressed sum); rc 1 = point off the curve."""
+        out = ctypes.create_string_buffer(48)
+        rc = self.lib.oracle_g1_lincomb(out, points_xy_be, scalars_be, n)
+        return rc, out.raw
+
+    def synth_msm_inputs(self, n: int, seed: int = 0):
+        pts, sc = ctypes.create_string_buffer(96 * n), ctypes.create_string_buffer(32 * n)
+        rc = self.lib.oracle_synth_msm_inputs(pts, sc, n, ctypes.c_uint64(seed))
+        if rc:
+            raise RuntimeError("oracle_synth_msm_inputs -> %d" % rc)
+        return pts.raw, sc.raw

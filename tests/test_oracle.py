@@ -225,3 +225,35 @@ def test_c_oracle_codec_and_sha(c_oracle):
         noncanon[0] |= 0x80
         ok, rec = c_oracle.g1_decompress_check(bytes(noncanon))
         assert ok and rec == bls.g1_compress(bls.g1_decompress(bytes(noncanon)))
+
+
+def test_c_oracle_bench_helpers(setup_text, py_setup):
+    """oracle_synth_blob == the SplitMix64 generator of SURVEY 8(d); oracle_g1_lincomb == the Python MSM."""
+    from oracle import c_oracle
+
+    co = c_oracle.COracle(setup_text)
+    M = (1 << 64) - 1
+
+    def word(k, i):
+        st = 0xB2004844 ^ ((k * 4096 + i) & M)
+        out = b""
+        for _ in range(4):
+            st = (st + 0x9E3779B97F4A7C15) & M
+            z = st
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+            out += (z ^ (z >> 31)).to_bytes(8, "big")
+        return bytes([out[0] & 0x3F]) + out[1:]
+
+    blob = co.synth_blob(3)
+    for i in (0, 1, 4095):
+        assert blob[32 * i: 32 * i + 32] == word(3, i)
+    n = 40
+    pts_b, sc_b = co.synth_msm_inputs(n, 7)
+    pts = [(int.from_bytes(pts_b[96 * i: 96 * i + 48], "big"), int.from_bytes(pts_b[96 * i + 48: 96 * i + 96], "big")) for i in range(n)]
+    assert pts[0] == py_setup.g1[0] and pts[2] == bls.g1_mul(py_setup.g1[0], 3)
+    sc = [int.from_bytes(sc_b[32 * i: 32 * i + 32], "big") for i in range(n)]
+    rc, got = co.g1_lincomb(pts_b, sc_b, n)
+    assert rc == 0 and got == bls.g1_compress(bls.g1_msm(pts, [v % bls.R for v in sc]))
+    rc, _ = co.g1_lincomb((1).to_bytes(48, "big") * 2, (1).to_bytes(32, "big"), 1)
+    assert rc == 1
