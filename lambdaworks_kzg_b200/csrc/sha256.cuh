@@ -63,9 +63,15 @@ LW_INL void sha256_compress(Sha256State& s, uint32_t* w) {
 // wk is laid out [64][32]: word i of the block prepared by lane b at wk[i * 32 + b].
 LW_INL void sha256_rounds_wk(Sha256State& s, const uint32_t* wk, int b) {
   uint32_t a = s.h[0], bb = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+  // all 64 schedule words are requested before the first round: left to itself ptxas issues each shared-memory
+  // load right before its use, which puts the ~30-cycle load on the dependency chain of EVERY round (measured
+  // 32 cycles per round; the arithmetic chain is three instructions deep)
+  uint32_t kw[64];
+#pragma unroll
+  for (int i = 0; i < 64; i++) kw[i] = wk[i * 32 + b];
 #pragma unroll
   for (int i = 0; i < 64; i++) {
-    const uint32_t dhk = d + h + wk[i * 32 + b];          // off the e-chain (see sha256_compress)
+    const uint32_t dhk = d + h + kw[i];                   // off the e-chain (see sha256_compress)
     const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
     const uint32_t ch = g ^ (e & (f ^ g));
     const uint32_t e_new = dhk + S1 + ch;

@@ -35,6 +35,20 @@ __global__ void __launch_bounds__(1024, 1) probe(unsigned long long* cyc, uint32
 #pragma unroll
       for (int j = 1; j < 14; j++) asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(t[2 * j]), "+r"(t[2 * j + 1]) : "r"(a[j]), "r"(b));
     }
+    if (MODE == 5) {  // immediate multiplier, the register multiplicand b reused by every MAC: the 64-bit addend is the ONLY register-file read
+      c[0] += (uint64_t)b * 0x12345679u;  c[1] += (uint64_t)b * 0x2468acf3u;  c[2] += (uint64_t)b * 0x369d0369u;  c[3] += (uint64_t)b * 0x48d159e7u;
+      c[4] += (uint64_t)b * 0x5b05b05bu;  c[5] += (uint64_t)b * 0x6d3a06d3u;  c[6] += (uint64_t)b * 0x7f6e5d4du;  c[7] += (uint64_t)b * 0x91a2b3c5u;
+      c[8] += (uint64_t)b * 0xa3d70a3du;  c[9] += (uint64_t)b * 0xb60b60b7u;  c[10] += (uint64_t)b * 0xc83fb72fu; c[11] += (uint64_t)b * 0xda740da7u;
+      c[12] += (uint64_t)b * 0xeca8641fu; c[13] += (uint64_t)b * 0xfedcba99u;
+    }
+    if (MODE == 6) {  // high halves only (what the m[0] * m_i column of the reduction needs)
+#pragma unroll
+      for (int j = 0; j < 14; j++) { uint32_t lo = (uint32_t)c[j]; lo = __umulhi(a[j], b) + lo; c[j] = (c[j] & 0xffffffff00000000ull) | lo; }
+    }
+    if (MODE == 7) {  // product without addend (first row of a CIOS product): dest fresh, a[j] distinct, b shared
+#pragma unroll
+      for (int j = 0; j < 14; j++) c[j] = (uint64_t)(a[j] ^ (uint32_t)c[j]) * b;
+    }
     b += (uint32_t)c[3];
   }
   unsigned long long t1 = clock64();
@@ -66,5 +80,8 @@ int main() {
   run<2>("IMAD.WIDE with constant-bank operand");
   run<3>("IMAD (32-bit) accumulate");
   run<4>("carry chain of 14 fused pairs");
+  run<5>("IMAD.WIDE, immediate x reused register (only the addend is read)");
+  run<6>("IMAD.HI accumulate");
+  run<7>("IMAD.WIDE without addend (+1 LOP3 each)");
   printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
 }
