@@ -236,7 +236,13 @@ int lwkzg_window_bits(const KZGSettings *s);
  * C_KZG_ERROR), 1 = MODE_CKZG_LE (the little-endian-era c-kzg-4844 semantics of
  * the YAML vectors under the reference's tests/: canonical little-endian
  * scalars, blob = evaluations, Lagrange SRS derived at load, BADARGS for invalid
- * input, empty batch verifies).  The mode is captured when a KZGSettings is
+ * input, empty batch verifies), 2 = MODE_DENEB (the final EIP-4844 / mainnet wire format, the combination
+ * the reference stopped short of -- it parses big-endian scalars, src/utils.rs:27-41, but left the Lagrange
+ * conversion of the SRS as a TODO, src/lib.rs:760-770: big-endian CANONICAL scalars (>= r is BADARGS), blob =
+ * evaluations over the bit-reversed roots of unity, Lagrange SRS derived at load, barycentric evaluation and
+ * evaluation-form quotient, Fiat-Shamir of consensus-specs deneb/polynomial-commitments.md: domain ||
+ * be128(4096) || blob || commitment, batch challenge domain || be64(4096) || be64(n) || tuples, digests read
+ * big-endian).  The mode is captured when a KZGSettings is
  * loaded / first used.  Env: LWKZG_WINDOW_BITS, LWKZG_CHUNK_BLOBS, LWKZG_MODE,
  * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS.
  * Returns 0 on success. */

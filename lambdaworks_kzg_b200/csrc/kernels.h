@@ -52,7 +52,8 @@ int msm_threads_per_block();
 
 // ---- Fiat-Shamir + polynomial (poly.cu)
 // SHA-256 midstate over domain || le64(4096) || le64(0) || blob[0 .. 131040)
-void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st, bool latency = false);
+// be_header: the 16 bytes after the domain are be128(4096) (MODE_DENEB) instead of le64(4096) || le64(0)
+void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st, bool latency = false, bool be_header = false);
 // finish with blob tail + 48 commitment bytes -> z canonical (8 u32 LE per blob)
 void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st, bool le_digest = false);
 // z from caller bytes (big-endian, reduced)
@@ -85,14 +86,16 @@ void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, 
                           const void* d_g1_0_aff, const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st);
 // tuples: compress(C)||z||y||compress(pi) (160 B each)
 void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le = false);
-// r = H(domain || le64(4096) || le64(n_total) || tuples) -> canonical r (8 u32)
-void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, bool le = false);
+// r = H(domain || le64(4096) || le64(n_total) || tuples) -> canonical r (8 u32).  wire: 0 = reference (little-endian
+// header, digest read big-endian), 1 = MODE_CKZG_LE (digest read little-endian), 2 = MODE_DENEB (be64 header fields,
+// digest read big-endian)
+void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, int wire = 0);
 // the same hash over a block range of the message, state carried in d_state (first: start from the IV; last: absorb
 // the rest of the message from blk0 on and write r).  blocks_ready(k) = full 64-byte blocks covered by the head and k tuples
 size_t batch_challenge_state_bytes();
 int batch_challenge_blocks_ready(size_t tuples_ready);
 void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples160, size_t n_total, int blk0, int blk1, bool first, bool last,
-                                 cudaStream_t st, bool le = false);
+                                 cudaStream_t st, int wire = 0);
 // partial sums over [first, first+n_local): 3 XYZZ blocks-partials then reduced to 3 affine (canonical BE 96 B each)
 void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
                            size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st);
@@ -105,9 +108,11 @@ void launch_write_generator(void* d_out, cudaStream_t st);                 // th
 void launch_le_roots(void* d_roots, cudaStream_t st);                      // 4096 Fr (Montgomery), bit-reversed order
 void launch_le_idft_rows(void* d_rows, cudaStream_t st);                   // 4096 x 4096 canonical scalars (512 MiB)
 void launch_affine_to_canon(void* d_out24, const void* d_aff, int n, cudaStream_t st);
-void launch_le_blob_check(int* d_status, const void* d_blobs, int n, cudaStream_t st);   // status 1 if a word >= r
-void launch_le_fr_parse(void* d_out, int* d_status, const void* d_in32, int n, cudaStream_t st);
-void launch_le_eval_quot(void* d_q, void* d_y, void* d_y_le32, const void* d_blobs, const void* d_z, const void* d_roots, int n, cudaStream_t st);
+// be = false: little-endian field elements (MODE_CKZG_LE); be = true: big-endian (MODE_DENEB, the mainnet wire format)
+void launch_le_blob_check(int* d_status, const void* d_blobs, int n, cudaStream_t st, bool be = false);   // status 1 if a word >= r
+void launch_le_fr_parse(void* d_out, int* d_status, const void* d_in32, int n, cudaStream_t st, bool be = false);
+void launch_le_eval_quot(void* d_q, void* d_y, void* d_y_le32, const void* d_blobs, const void* d_z, const void* d_roots, int n, cudaStream_t st,
+                         bool be = false);
 
 // ---- generic (variable-base) MSM for lwkzg_g1_lincomb (varmsm.cu)
 void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st);

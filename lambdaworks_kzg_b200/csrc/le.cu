@@ -57,27 +57,29 @@ __global__ void affine_to_canon_kernel(uint32_t* __restrict__ out24, const G1Aff
   for (int k = 0; k < 12; k++) { out24[i * 24 + k] = x.l[k]; out24[i * 24 + 12 + k] = y.l[k]; }
 }
 
-// status[b] = 1 (C_KZG_BADARGS) if any of the 4096 little-endian words is >= r
-__global__ void __launch_bounds__(128) le_blob_check_kernel(int* __restrict__ status, const uint8_t* __restrict__ blobs, int n) {
+// status[b] = 1 (C_KZG_BADARGS) if any of the 4096 words is >= r.  be = 0: little-endian words (MODE_CKZG_LE),
+// be = 1: big-endian words (MODE_DENEB, bytes_to_bls_field of the final spec)
+__global__ void __launch_bounds__(128) le_blob_check_kernel(int* __restrict__ status, const uint8_t* __restrict__ blobs, int n, int be) {
   const int b = blockIdx.x;
   const uint32_t* w = reinterpret_cast<const uint32_t*>(blobs + (size_t)b * BLOB_BYTES);
   bool bad = false;
   for (int i = threadIdx.x; i < N_POINTS; i += 128) {
     uint32_t v[8];
-    for (int k = 0; k < 8; k++) v[k] = w[i * 8 + k];
+    for (int k = 0; k < 8; k++) v[k] = be ? bswap32(w[i * 8 + 7 - k]) : w[i * 8 + k];
     if (!limbs_lt<8>(v, k::FR_MOD)) bad = true;
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) status[b] = 1;
 }
 
-// 32 little-endian bytes -> canonical limbs; status 1 (BADARGS) if >= r
-__global__ void le_fr_parse_kernel(uint32_t* __restrict__ out, int* __restrict__ status, const uint8_t* __restrict__ in, int n) {
+// 32 little-endian (be = 0) or big-endian (be = 1) bytes -> canonical limbs; status 1 (BADARGS) if >= r
+__global__ void le_fr_parse_kernel(uint32_t* __restrict__ out, int* __restrict__ status, const uint8_t* __restrict__ in, int n, int be) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t v[8];
   for (int k = 0; k < 8; k++) {
-    const uint8_t* q = in + (size_t)i * 32 + 4 * k;
-    v[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    const uint8_t* q = in + (size_t)i * 32 + 4 * (be ? 7 - k : k);
+    v[k] = be ? ((uint32_t)q[3] | ((uint32_t)q[2] << 8) | ((uint32_t)q[1] << 16) | ((uint32_t)q[0] << 24))
+              : ((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
   }
   if (!limbs_lt<8>(v, k::FR_MOD)) { if (status) status[i] = 1; for (int k = 0; k < 8; k++) v[k] = 0; }
   for (int k = 0; k < 8; k++) out[i * 8 + k] = v[k];
@@ -99,7 +101,7 @@ __device__ __forceinline__ Fr warp_sum_fr(Fr v) {
 constexpr int LE_WARPS = 4;
 __global__ void __launch_bounds__(LE_WARPS * 32) le_eval_quot_kernel(uint32_t* __restrict__ q_out, uint32_t* __restrict__ y_out,
                                                                       uint8_t* __restrict__ y_le_out, const uint8_t* __restrict__ blobs,
-                                                                      const uint32_t* __restrict__ zs, const Fr* __restrict__ roots, int n) {
+                                                                      const uint32_t* __restrict__ zs, const Fr* __restrict__ roots, int n, int be) {
   const int lane = threadIdx.x & 31;
   const int blob = blockIdx.x * LE_WARPS + (threadIdx.x >> 5);
   if (blob >= n) return;
@@ -109,8 +111,12 @@ __global__ void __launch_bounds__(LE_WARPS * 32) le_eval_quot_kernel(uint32_t* _
   for (int i = 0; i < 8; i++) zc.l[i] = zs[blob * 8 + i];
   const Fr z = fr_to_mont(zc);
 
+  // blob words are canonical by contract (le_blob_check flags the blobs where they are not; their outputs are discarded)
   auto load_b = [&](int i) { Fr b; const uint4* p = reinterpret_cast<const uint4*>(bw + i * 8); uint4 a = __ldg(p), c = __ldg(p + 1);
-                             b.l[0] = a.x; b.l[1] = a.y; b.l[2] = a.z; b.l[3] = a.w; b.l[4] = c.x; b.l[5] = c.y; b.l[6] = c.z; b.l[7] = c.w; return b; };
+                             if (be) { b.l[7] = bswap32(a.x); b.l[6] = bswap32(a.y); b.l[5] = bswap32(a.z); b.l[4] = bswap32(a.w);
+                                       b.l[3] = bswap32(c.x); b.l[2] = bswap32(c.y); b.l[1] = bswap32(c.z); b.l[0] = bswap32(c.w); }
+                             else { b.l[0] = a.x; b.l[1] = a.y; b.l[2] = a.z; b.l[3] = a.w; b.l[4] = c.x; b.l[5] = c.y; b.l[6] = c.z; b.l[7] = c.w; }
+                             return b; };
 
   // ---- sweep 1: inverses of (z - w_i), barycentric sum, detect z in the domain
   Fr acc = fr_zero();
@@ -142,7 +148,8 @@ __global__ void __launch_bounds__(LE_WARPS * 32) le_eval_quot_kernel(uint32_t* _
   }
   if (lane == 0) {
     if (y_out) for (int t = 0; t < 8; t++) y_out[blob * 8 + t] = y.l[t];
-    if (y_le_out) for (int t = 0; t < 8; t++) for (int bb = 0; bb < 4; bb++) y_le_out[(size_t)blob * 32 + 4 * t + bb] = (uint8_t)(y.l[t] >> (8 * bb));
+    if (y_le_out) for (int t = 0; t < 8; t++) for (int bb = 0; bb < 4; bb++)
+      y_le_out[(size_t)blob * 32 + (be ? 31 - (4 * t + bb) : 4 * t + bb)] = (uint8_t)(y.l[t] >> (8 * bb));
   }
   if (!q_out) return;
   __syncwarp();
@@ -174,20 +181,20 @@ void launch_affine_to_canon(void* d_out24, const void* d_aff, int n, cudaStream_
   affine_to_canon_kernel<<<(n + 63) / 64, 64, 0, st>>>((uint32_t*)d_out24, (const G1Affine*)d_aff, n);
   count_launch();
 }
-void launch_le_blob_check(int* d_status, const void* d_blobs, int n, cudaStream_t st) {
+void launch_le_blob_check(int* d_status, const void* d_blobs, int n, cudaStream_t st, bool be) {
   if (n <= 0) return;
-  le_blob_check_kernel<<<n, 128, 0, st>>>(d_status, (const uint8_t*)d_blobs, n);
+  le_blob_check_kernel<<<n, 128, 0, st>>>(d_status, (const uint8_t*)d_blobs, n, be ? 1 : 0);
   count_launch();
 }
-void launch_le_fr_parse(void* d_out, int* d_status, const void* d_in32, int n, cudaStream_t st) {
+void launch_le_fr_parse(void* d_out, int* d_status, const void* d_in32, int n, cudaStream_t st, bool be) {
   if (n <= 0) return;
-  le_fr_parse_kernel<<<(n + 63) / 64, 64, 0, st>>>((uint32_t*)d_out, d_status, (const uint8_t*)d_in32, n);
+  le_fr_parse_kernel<<<(n + 63) / 64, 64, 0, st>>>((uint32_t*)d_out, d_status, (const uint8_t*)d_in32, n, be ? 1 : 0);
   count_launch();
 }
-void launch_le_eval_quot(void* d_q, void* d_y, void* d_y_le32, const void* d_blobs, const void* d_z, const void* d_roots, int n, cudaStream_t st) {
+void launch_le_eval_quot(void* d_q, void* d_y, void* d_y_le32, const void* d_blobs, const void* d_z, const void* d_roots, int n, cudaStream_t st, bool be) {
   if (n <= 0) return;
   le_eval_quot_kernel<<<(n + LE_WARPS - 1) / LE_WARPS, LE_WARPS * 32, 0, st>>>((uint32_t*)d_q, (uint32_t*)d_y, (uint8_t*)d_y_le32, (const uint8_t*)d_blobs,
-                                                                              (const uint32_t*)d_z, (const Fr*)d_roots, n);
+                                                                              (const uint32_t*)d_z, (const Fr*)d_roots, n, be ? 1 : 0);
   count_launch();
 }
 

@@ -49,9 +49,10 @@ struct Options {
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
-  long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode)
+  long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode),
+                  // 2 = MODE_DENEB (the mainnet wire format: big-endian canonical scalars over the Lagrange SRS)
   Options() {
-    if (const char* e = getenv("LWKZG_MODE")) mode = atol(e);
+    if (const char* e = getenv("LWKZG_MODE")) mode = std::min(std::max(atol(e), 0L), 2L);
     if (const char* e = getenv("LWKZG_WINDOW_BITS")) window_bits = atol(e);
     if (const char* e = getenv("LWKZG_CHUNK_BLOBS")) chunk_blobs = std::min(std::max(atol(e), 1L), 1L << 20);
     if (const char* e = getenv("LWKZG_MSM_BLOCKS_PER_BLOB")) msm_blocks_per_blob = atol(e);
@@ -103,8 +104,10 @@ struct Ctx {
   bool srs_in_g1;     // every g1 value in the r-torsion
   bool g2_valid;      // g2[0], g2[1] on the twist
   int mode;           // semantic mode captured when the context was built
-  void* d_roots;      // MODE_CKZG_LE: bit-reversed 4096th roots of unity (Montgomery)
-  void* d_gen;        // MODE_CKZG_LE: the G1 generator (c-kzg verifies against G, not against g1_values[0] = L_0)
+  bool lagrange() const { return mode != 0; }   // evaluation-form blobs over a Lagrange SRS, c-kzg error codes
+  bool be_wire() const { return mode == 2; }    // MODE_DENEB: big-endian field elements and hash headers
+  void* d_roots;      // Lagrange modes: bit-reversed 4096th roots of unity (Montgomery)
+  void* d_gen;        // Lagrange modes: the G1 generator (c-kzg verifies against G, not against g1_values[0] = L_0)
   void* d_srs;        // 4096 affine Montgomery
   void* d_table;      // fixed-base digit table
   void* d_prep0;      // prepared g2[0] / g2[1] line coefficients
@@ -262,8 +265,8 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
   }
 
   c->mode = mode;
-  if (mode == 1) {
-    // allocated before the early return below: every LE-mode kernel may assume they exist
+  if (mode != 0) {
+    // allocated before the early return below: every Lagrange-mode kernel may assume they exist
     CU_TRY(cudaMalloc(&c->d_roots, (size_t)N_POINTS * 32));
     launch_le_roots(c->d_roots, st);
     CU_TRY(cudaMalloc(&c->d_gen, AFFINE_BYTES));
@@ -458,15 +461,17 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
                    const void* d_commit_in48, const void* d_z_in_be) {
   const int bpb = auto_bpb(n);
   cudaStream_t st = s.st;
-  const bool le = c->mode == 1;
+  const bool le = c->lagrange();
   if (le) {
     // MODE_CKZG_LE: canonical little-endian scalars = the limbs as they lie in memory,
-    // Lagrange table, barycentric evaluation, evaluation-form quotient, BADARGS for invalid input
+    // Lagrange table, barycentric evaluation, evaluation-form quotient, BADARGS for invalid input.
+    // MODE_DENEB: the same over big-endian scalars (be) with the final spec's hash layout
+    const bool be = c->be_wire();
     int* stt = d_status ? d_status : (int*)s.status.p;
     CU_TRY(cudaMemsetAsync(stt, 0, (size_t)n * sizeof(int), st));
-    launch_le_blob_check(stt, d_blobs, n, st);
+    launch_le_blob_check(stt, d_blobs, n, st, be);
     if (mode == Mode::Commit) {
-      run_msm(s, c, d_blobs, false, n, bpb, st);
+      run_msm(s, c, d_blobs, be, n, bpb, st);
       launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
       return true;
     }
@@ -474,11 +479,11 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
     if (mode == Mode::CommitProve || mode == Mode::BlobProof) {
       CU_TRY(cudaEventRecord(s.ev_fork, st));
       CU_TRY(cudaStreamWaitEvent(s.aux, s.ev_fork, 0));
-      launch_challenge_midstate(s.states.p, d_blobs, n, s.aux, mode == Mode::BlobProof);
+      launch_challenge_midstate(s.states.p, d_blobs, n, s.aux, mode == Mode::BlobProof, be);
       CU_TRY(cudaEventRecord(s.ev_aux, s.aux));
     }
     if (mode == Mode::CommitProve) {
-      run_msm(s, c, d_blobs, false, n, bpb, st);
+      run_msm(s, c, d_blobs, be, n, bpb, st);
       launch_msm_finalize(d_c48, nullptr, s.partials.p, bpb, n, st);
       commit_for_hash = d_c48;
     } else if (mode == Mode::BlobProof) {
@@ -488,13 +493,13 @@ bool enqueue_chunk(Ctx* c, Slot& s, Mode mode, const void* d_blobs, int n, void*
     }
     if (mode == Mode::PointProof) {
       CU_TRY(cudaMemsetAsync(s.status2.p, 0, (size_t)n * sizeof(int), st));
-      launch_le_fr_parse(s.z.p, (int*)s.status2.p, d_z_in_be, n, st);
+      launch_le_fr_parse(s.z.p, (int*)s.status2.p, d_z_in_be, n, st, be);
       launch_status_or(stt, (const int*)s.status2.p, n, st);
     } else {
       CU_TRY(cudaStreamWaitEvent(st, s.ev_aux, 0));
-      launch_challenge_finish(s.z.p, s.states.p, d_blobs, commit_for_hash, n, st, true);
+      launch_challenge_finish(s.z.p, s.states.p, d_blobs, commit_for_hash, n, st, !be);
     }
-    launch_le_eval_quot(s.q.p, nullptr, d_ybe, d_blobs, s.z.p, c->d_roots, n, st);
+    launch_le_eval_quot(s.q.p, nullptr, d_ybe, d_blobs, s.z.p, c->d_roots, n, st, be);
     run_msm(s, c, s.q.p, false, n, bpb, st);
     launch_msm_finalize(d_p48, nullptr, s.partials.p, bpb, n, st);
     return true;
@@ -677,7 +682,7 @@ C_KZG_RET device_batch(Mode mode, const KZGSettings* s, size_t n, const void* d_
     const void* ci = d_commit_in ? (const uint8_t*)d_commit_in + off * 48 : nullptr;
     int* so = d_status ? (int*)d_status + off : (int*)sl.status.p;
     ok = enqueue_chunk(c, sl, mode, b, m, co, po, nullptr, so, ci, nullptr);
-    if (ok && (mode == Mode::BlobProof || c->mode == 1)) {   // the only ways an item can fail: bad commitment / non-canonical blob
+    if (ok && (mode == Mode::BlobProof || c->lagrange())) {   // the only ways an item can fail: bad commitment / non-canonical blob
       if (co && d_c_out) launch_zero_failed(co, 48, so, m, sl.st);
       if (po) launch_zero_failed(po, 48, so, m, sl.st);
     }
@@ -778,7 +783,7 @@ C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, si
     if (st[n1 + i] == 0) g2[i].z.fp[0].l[5] = 1;  // affine z = 1 + 0u ; infinity keeps z = 0
   }
   const int mode = (int)current_mode();
-  if (mode == 1 && n1 == N_POINTS) {
+  if (mode != 0 && n1 == N_POINTS) {
     // c-kzg's load_trusted_setup stores the SRS in Lagrange form, bit-reversed
     // (the step the reference left as a TODO, lib.rs:760-770): L_i = sum_j (1/n) w_i^-j [tau^j]G,
     // computed as 4096 fixed-base MSMs over a temporary 8-bit table of the monomial points.
@@ -854,7 +859,8 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     chunk = std::max(1L, opts().chunk_blobs);
   }
   cudaStream_t s0 = c->slot[0].st;
-  const bool le = c->mode == 1;
+  const bool le = c->lagrange(), be = c->be_wire();
+  const int wire = c->mode;
   const cudaMemcpyKind in_kind = dev_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   // commitments on s0, proofs on the hash stream (idle until the first tuples exist): the two decompressions are
   // latency-bound thread-per-point kernels and run side by side
@@ -916,22 +922,22 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
       // (small batches use the warp-per-blob hash, which does not show this, and want the overlap)
       if (n > 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
       if (trace) { for (auto& e : tc) cudaEventCreate(&e); cudaEventRecord(tc[0], st); }
-      launch_challenge_midstate(d_states, d_blobs, m, st, true);
+      launch_challenge_midstate(d_states, d_blobs, m, st, true, be);
       if (trace) cudaEventRecord(tc[1], st);
       if (n <= 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
       if (le) {
         int* st2 = (int*)c->vb_status2.p + off;
         CU_TRY(cudaMemsetAsync(st2, 0, (size_t)m * sizeof(int), st));
-        launch_le_blob_check(st2, d_blobs, m, st);
+        launch_le_blob_check(st2, d_blobs, m, st, be);
         launch_status_or((int*)c->vb_status.p + off, st2, m, st);
-        launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, d_states, d_blobs, (const uint8_t*)c->vb_cin.p + off * 48, m, st, true);
-        launch_le_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, d_blobs, (const uint8_t*)c->vb_z.p + off * 32, c->d_roots, m, st);
+        launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, d_states, d_blobs, (const uint8_t*)c->vb_cin.p + off * 48, m, st, !be);
+        launch_le_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, d_blobs, (const uint8_t*)c->vb_z.p + off * 32, c->d_roots, m, st, be);
       } else {
         launch_challenge_finish((uint8_t*)c->vb_z.p + off * 32, d_states, d_blobs, (const uint8_t*)c->vb_c48r.p + off * 48, m, st);
         launch_poly_eval_quot(nullptr, (uint8_t*)c->vb_y.p + off * 32, nullptr, d_blobs, (const uint8_t*)c->vb_z.p + off * 32, m, st);
       }
       launch_make_tuples((uint8_t*)c->vb_tuples.p + off * 160, (const uint8_t*)c->vb_c48r.p + off * 48, (const uint8_t*)c->vb_z.p + off * 32,
-                         (const uint8_t*)c->vb_y.p + off * 32, (const uint8_t*)c->vb_p48r.p + off * 48, m, st, le);
+                         (const uint8_t*)c->vb_y.p + off * 32, (const uint8_t*)c->vb_p48r.p + off * 48, m, st, le && !be);
       if (trace) { cudaEventRecord(tc[2], st); for (auto e : tc) trace_chunks.push_back(e); }
       if (hash_r) {
         // chunks reach the hash stream in order; each launch absorbs the blocks its chunk completed
@@ -939,7 +945,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
         CU_TRY(cudaStreamWaitEvent(c->hash_st, ev_tuples, 0));
         const bool last = off + (size_t)m >= n;
         const int ready = batch_challenge_blocks_ready(off + (size_t)m);
-        launch_batch_challenge_part(c->vb_r.p, c->vb_hstate.p, c->vb_tuples.p, n, hashed_blocks, ready, k == 0, last, c->hash_st, le);
+        launch_batch_challenge_part(c->vb_r.p, c->vb_hstate.p, c->vb_tuples.p, n, hashed_blocks, ready, k == 0, last, c->hash_st, wire);
         hashed_blocks = ready;
       }
     }
@@ -985,7 +991,7 @@ C_KZG_RET bad_code(int code) { return code == 1 ? C_KZG_BADARGS : C_KZG_ERROR; }
 bool verify_single_from_workspace(Ctx* c, bool& ok) {
   cudaStream_t s0 = c->slot[0].st;
   // reference: KZG::verify subtracts y * srs[0] (= G for a monomial setup); c-kzg uses the generator itself
-  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->mode == 1 ? c->d_gen : c->d_srs, c->d_prep0, c->d_prep1, c->mode == 1 || c->srs_in_g1, s0);
+  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->lagrange() ? c->d_gen : c->d_srs, c->d_prep0, c->d_prep1, c->lagrange() || c->srs_in_g1, s0);
   int okv = 0;
   CU_TRY(cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
   CU_TRY(cudaStreamSynchronize(s0));
@@ -1016,7 +1022,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "window_bits") { if (value < 4 || value > 16) return 1; opts().window_bits = value; return 0; }
   if (n == "msm_blocks_per_blob") { if (value < 0 || value > 256 || (value > 64 && (value & (value - 1)))) return 1; opts().msm_blocks_per_blob = value; return 0; }
   if (n == "chunk_blobs") { if (value < 1 || value > (1 << 20)) return 1; opts().chunk_blobs = value; return 0; }
-  if (n == "mode") { if (value != 0 && value != 1) return 1; opts().mode = value; return 0; }
+  if (n == "mode") { if (value < 0 || value > 2) return 1; opts().mode = value; return 0; }
   if (n == "msm_algo") { if (value != 0 && value != 1) return 1; opts().msm_algo = value; return 0; }
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
   if (n == "verify_super_blobs") { if (value < 1) return 1; opts().verify_super_blobs = value; return 0; }
@@ -1161,7 +1167,7 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
     CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitment_bytes, 48, cudaMemcpyHostToDevice, s0));
     CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proof_bytes, 48, cudaMemcpyHostToDevice, c->hash_st));
     CU_TRY(cudaMemcpyAsync(c->vb_zy_in.p, zy, 64, cudaMemcpyHostToDevice, s0));
-    const bool le = c->mode == 1;
+    const bool le = c->lagrange(), be = c->be_wire();
     // the two point decompressions (sqrt + subgroup check, ~2 ms each on one thread) run side by side
     launch_g1_decompress(c->vb_caff.p, nullptr, (int*)c->vb_status.p, c->vb_cin.p, 1, s0, le);
     launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, c->hash_st, le);
@@ -1170,8 +1176,8 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
     launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, 1, s0);
     if (le) {
       CU_TRY(cudaMemsetAsync(c->vb_tuples.p, 0, 2 * sizeof(int), s0));
-      launch_le_fr_parse(c->vb_z.p, (int*)c->vb_tuples.p, c->vb_zy_in.p, 1, s0);
-      launch_le_fr_parse(c->vb_y.p, (int*)c->vb_tuples.p + 1, (const uint8_t*)c->vb_zy_in.p + 32, 1, s0);
+      launch_le_fr_parse(c->vb_z.p, (int*)c->vb_tuples.p, c->vb_zy_in.p, 1, s0, be);
+      launch_le_fr_parse(c->vb_y.p, (int*)c->vb_tuples.p + 1, (const uint8_t*)c->vb_zy_in.p + 32, 1, s0, be);
       launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, 1, s0);
       launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p + 1, 1, s0);
     } else {
@@ -1217,7 +1223,7 @@ static C_KZG_RET verify_blob_batch(bool* ok, const Blob* blobs, const Bytes48* c
   if (n == 0) {
     // lib.rs:538-543: the reference rejects an empty batch; c-kzg (MODE_CKZG_LE) accepts it
     Ctx* c0 = ctx_of(s);
-    if (c0 && c0->mode == 1) *ok = true;
+    if (c0 && c0->lagrange()) *ok = true;
     return C_KZG_OK;
   }
   if (n == 1) return verify_blob_single(ok, blobs, commitments_bytes, proofs_bytes, s, dev_inputs);  // lib.rs:544
@@ -1292,7 +1298,7 @@ C_KZG_RET lwkzg_verify_batch_phase2(uint8_t* partial288, const uint8_t* all_tupl
   bool good = [&]() -> bool {
     CU_TRY(cudaMemcpyAsync(d_all, all_tuples160, n_total * 160, cudaMemcpyHostToDevice, s0));
     if (!c->vb_r.ensure(32) || !c->vb_partial.ensure(288) || !c->vb_scratch.ensure(batch_partials_scratch_bytes((int)std::max<size_t>(n_local, 1)))) return false;
-    launch_batch_challenge(c->vb_r.p, d_all, n_total, s0, c->mode == 1);
+    launch_batch_challenge(c->vb_r.p, d_all, n_total, s0, c->mode);
     launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, first, (int)n_local, c->vb_scratch.p, s0);
     CU_TRY(cudaMemcpyAsync(partial288, c->vb_partial.p, 288, cudaMemcpyDeviceToHost, s0));
     CU_TRY(cudaStreamSynchronize(s0));

@@ -17,12 +17,21 @@ __device__ __forceinline__ void load_block_words(uint32_t* w, const uint8_t* p16
   }
 }
 
+// words 4..7 of block 0: the 16 "degree" bytes after the domain.  le64(4096) || le64(0) in the reference and in
+// MODE_CKZG_LE; int.to_bytes(4096, 16, 'big') in MODE_DENEB (consensus-specs deneb compute_challenge)
+__device__ __forceinline__ void challenge_header_words(uint32_t* w, int be_header) {
+  w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;  // "FSBL" "OBVE" "RIFY" "_V1_"
+  w[4] = be_header ? 0u : 0x00100000u;   // 4096 little-endian: 00 10 00 00 00 00 00 00
+  w[5] = 0u; w[6] = 0u;
+  w[7] = be_header ? 0x00001000u : 0u;
+}
+
 // The hashed message is  "FSBLOBVERIFY_V1_" || le64(4096) || le64(0) || blob || compress(C)
 // = 131152 bytes = 2049 full blocks + 16 bytes.  Everything up to byte 131072
 // (2048 blocks: 32-byte header + blob[0..131040)) does not depend on the
 // commitment, so this midstate runs concurrently with the commitment MSM.
 // SHA-256 is inherently sequential per message: one thread per blob.
-__global__ void __launch_bounds__(32) challenge_midstate_kernel(Sha256State* __restrict__ states, const uint8_t* __restrict__ blobs, int n) {
+__global__ void __launch_bounds__(32) challenge_midstate_kernel(Sha256State* __restrict__ states, const uint8_t* __restrict__ blobs, int n, int be_header) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   const uint8_t* blob = blobs + (size_t)b * BLOB_BYTES;
@@ -30,9 +39,7 @@ __global__ void __launch_bounds__(32) challenge_midstate_kernel(Sha256State* __r
   sha256_init(s);
   uint32_t w[16];
   // block 0: domain (16) + le64(4096) + le64(0) + blob[0..32)
-  w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;  // "FSBL" "OBVE" "RIFY" "_V1_"
-  w[4] = 0x00100000u; w[5] = 0u;   // 4096 little-endian: 00 10 00 00 00 00 00 00
-  w[6] = 0u; w[7] = 0u;
+  challenge_header_words(w, be_header);
   {
     const uint4* q = reinterpret_cast<const uint4*>(blob);
     uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
@@ -50,7 +57,7 @@ __global__ void __launch_bounds__(32) challenge_midstate_kernel(Sha256State* __r
 // Latency variant for small batches: one WARP per blob, message schedules expanded by
 // all lanes (sha256_warp_blocks).  Same result, ~2x lower latency per blob; not used for
 // large batches where a thread per blob keeps the issue slots free for the MSM.
-__global__ void __launch_bounds__(32) challenge_midstate_warp_kernel(Sha256State* __restrict__ states, const uint8_t* __restrict__ blobs, int n) {
+__global__ void __launch_bounds__(32) challenge_midstate_warp_kernel(Sha256State* __restrict__ states, const uint8_t* __restrict__ blobs, int n, int be_header) {
   __shared__ uint32_t wk[64 * 32];
   const int b = blockIdx.x;
   const uint8_t* blob = blobs + (size_t)b * BLOB_BYTES;
@@ -58,8 +65,7 @@ __global__ void __launch_bounds__(32) challenge_midstate_warp_kernel(Sha256State
   sha256_init(s);
   sha256_warp_blocks(s, 2048, [&](int blk, uint32_t* w) {
     if (blk == 0) {
-      w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;
-      w[4] = 0x00100000u; w[5] = 0u; w[6] = 0u; w[7] = 0u;
+      challenge_header_words(w, be_header);
       const uint4* q = reinterpret_cast<const uint4*>(blob);
       uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
       w[8] = bswap32(v0.x); w[9] = bswap32(v0.y); w[10] = bswap32(v0.z); w[11] = bswap32(v0.w);
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(32) challenge_midstate_warp_kernel(Sha256State
 // issues G times fewer warp instructions: 4096 warp-per-blob hashes saturate the issue slots of the whole GPU
 // (measured: a 4096-blob verification spent 17 ms there), 512 warps of this kernel do not.
 template <int G>
-__global__ void __launch_bounds__(32) challenge_midstate_group_kernel(Sha256State* __restrict__ states, const uint8_t* __restrict__ blobs, int n) {
+__global__ void __launch_bounds__(32) challenge_midstate_group_kernel(Sha256State* __restrict__ states, const uint8_t* __restrict__ blobs, int n, int be_header) {
   __shared__ uint32_t wk[64 * 32];
   constexpr int PER = 32 / G;   // blocks per blob and iteration; 2048 % PER == 0
   const int lane = threadIdx.x;
@@ -93,8 +99,7 @@ __global__ void __launch_bounds__(32) challenge_midstate_group_kernel(Sha256Stat
       const int blk = base + j;
       uint32_t w[16];
       if (blk == 0) {
-        w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;
-        w[4] = 0x00100000u; w[5] = 0u; w[6] = 0u; w[7] = 0u;
+        challenge_header_words(w, be_header);
         const uint4* q = reinterpret_cast<const uint4*>(blob);
         uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
         w[8] = bswap32(v0.x); w[9] = bswap32(v0.y); w[10] = bswap32(v0.z); w[11] = bswap32(v0.w);
@@ -219,14 +224,15 @@ __global__ void __launch_bounds__(POLY_WARPS * 32) poly_eval_quot_kernel(uint32_
 // latency = true: nothing else runs beside the hash (blob proofs for given commitments, verification), so the
 // warp-per-blob kernel's ~2x shorter critical path is what counts; false: the hash hides under a commitment MSM and
 // the thread-per-blob kernel leaves the issue slots to it.
-void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st, bool latency) {
+void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st, bool latency, bool be_header) {
   if (n <= 0) return;
+  const int bh = be_header ? 1 : 0;
   if (n <= 64)
-    challenge_midstate_warp_kernel<<<n, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n);
+    challenge_midstate_warp_kernel<<<n, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n, bh);
   else if (latency)
-    challenge_midstate_group_kernel<8><<<(n + 7) / 8, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n);
+    challenge_midstate_group_kernel<8><<<(n + 7) / 8, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n, bh);
   else
-    challenge_midstate_kernel<<<(n + 31) / 32, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n);
+    challenge_midstate_kernel<<<(n + 31) / 32, 32, 0, st>>>((Sha256State*)d_states, (const uint8_t*)d_blobs, n, bh);
   count_launch();
 }
 void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st, bool le_digest) {

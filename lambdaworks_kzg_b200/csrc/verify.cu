@@ -142,7 +142,7 @@ __global__ void make_tuples_kernel(uint8_t* __restrict__ tuples, const uint8_t* 
 // (FLAG_INIT: start from the SHA-256 IV; FLAG_FINAL: also absorb everything after blk1 -- the remaining
 // full blocks and the padded tail -- and write r).  One launch with both flags and blk0 = blk1 = 0 is
 // the monolithic hash.
-constexpr int BCH_INIT = 1, BCH_FINAL = 2, BCH_LE = 4;
+constexpr int BCH_INIT = 1, BCH_FINAL = 2, BCH_LE = 4, BCH_BE_HDR = 8;
 __global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restrict__ r_out, Sha256State* __restrict__ state, const uint8_t* __restrict__ tuples,
                                                               unsigned long long n_total, int blk0, int blk1, int flags) {
   __shared__ uint32_t wk[64 * 32];
@@ -152,8 +152,13 @@ __global__ void __launch_bounds__(32) batch_challenge_kernel(uint32_t* __restric
     const char dom[17] = "RCKZGBATCH___V1_";
     for (int i = 0; i < 16; i++) head[i] = (uint8_t)dom[i];
     for (int i = 0; i < 8; i++) head[16 + i] = 0;
-    head[17] = 0x10;  // le64(4096)
-    for (int i = 0; i < 8; i++) head[24 + i] = (uint8_t)(n_total >> (8 * i));
+    if (flags & BCH_BE_HDR) {   // MODE_DENEB: be64(4096) || be64(n)
+      head[22] = 0x10;
+      for (int i = 0; i < 8; i++) head[24 + i] = (uint8_t)(n_total >> (8 * (7 - i)));
+    } else {
+      head[17] = 0x10;  // le64(4096)
+      for (int i = 0; i < 8; i++) head[24 + i] = (uint8_t)(n_total >> (8 * i));
+    }
   }
   __syncwarp();
   const unsigned long long total = 32ull + 160ull * n_total;
@@ -444,18 +449,19 @@ void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, c
                                                   le ? 1 : 0);
   count_launch();
 }
-void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, bool le) {
+static int bch_wire_flags(int wire) { return wire == 1 ? BCH_LE : wire == 2 ? BCH_BE_HDR : 0; }
+void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, int wire) {
   batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, nullptr, (const uint8_t*)d_tuples160, (unsigned long long)n_total, 0, 0,
-                                           BCH_INIT | BCH_FINAL | (le ? BCH_LE : 0));
+                                           BCH_INIT | BCH_FINAL | bch_wire_flags(wire));
   count_launch();
 }
 size_t batch_challenge_state_bytes() { return sizeof(Sha256State); }
 int batch_challenge_blocks_ready(size_t tuples_ready) { return (int)((32 + 160 * tuples_ready) / 64); }
 void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples160, size_t n_total, int blk0, int blk1, bool first, bool last,
-                                 cudaStream_t st, bool le) {
+                                 cudaStream_t st, int wire) {
   if (!last && blk1 <= blk0 && !first) return;
   batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (Sha256State*)d_state, (const uint8_t*)d_tuples160, (unsigned long long)n_total, blk0, blk1,
-                                           (first ? BCH_INIT : 0) | (last ? BCH_FINAL : 0) | (le ? BCH_LE : 0));
+                                           (first ? BCH_INIT : 0) | (last ? BCH_FINAL : 0) | bch_wire_flags(wire));
   count_launch();
 }
 size_t batch_partials_scratch_bytes(int n_local) {

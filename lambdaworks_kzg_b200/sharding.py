@@ -88,7 +88,7 @@ def verify_blob_kzg_proof_batch_distributed(blobs_local: bytes, commitments_loca
 
     if n_total == 0:
         # lib.rs:538-543: the reference rejects an empty batch; c-kzg (MODE_CKZG_LE) accepts it
-        return api.get_option("mode") == 1 if phases is None else False
+        return api.get_option("mode") != 0 if phases is None else False
     err = 0
     tuples = b""
     result = False

@@ -91,6 +91,57 @@ def test_yaml_vectors_le_mode(le, vectors):
                       "verify_kzg_proof": 93, "verify_blob_kzg_proof": 24, "verify_blob_kzg_proof_batch": 23}
 
 
+def test_yaml_vectors_deneb_mode_hash_free(py_setup, vectors):
+    """MODE_DENEB oracle (mainnet wire format): the 149 hash-free YAML cases with their field elements
+    byte-reversed must give the reference-held answers."""
+    from tests._deneb import HASH_FREE_SUITES, to_big_endian
+
+    dn = kzg.DenebMode(py_setup)
+    ran = 0
+    for case in vectors:
+        if case["suite"] not in HASH_FREE_SUITES:
+            continue
+        inp, want = to_big_endian(case)
+        try:
+            got = _run_le(dn, case["suite"], inp)
+        except kzg.KzgError as e:
+            assert e.code == kzg.C_KZG_BADARGS
+            got = None
+        assert got == want, case["name"]
+        ran += 1
+    assert ran == 10 + 46 + 93
+
+
+def test_deneb_mode_hash_layout_and_round_trip(py_setup):
+    """The hash-dependent half of MODE_DENEB is pinned by the spec text only: spell the byte layouts out here,
+    independently of the oracle's code, and check the proof / verify round trip incl. the batched path."""
+    import hashlib
+
+    dn = kzg.DenebMode(py_setup)
+    rnd = random.Random(4844)
+    blobs = [b"".join(rnd.randrange(R).to_bytes(32, "big") for _ in range(4096)) for _ in range(3)]
+    coms = [dn.blob_to_kzg_commitment(b) for b in blobs]
+    z = dn.compute_challenge(blobs[0], coms[0])
+    msg = b"FSBLOBVERIFY_V1_" + bytes(14) + b"\x10\x00" + blobs[0] + coms[0]
+    assert len(msg) == 131152 and z == int.from_bytes(hashlib.sha256(msg).digest(), "big") % R
+    proofs = [dn.compute_blob_kzg_proof(b, c) for b, c in zip(blobs, coms)]
+    assert all(dn.verify_blob_kzg_proof(b, c, p) for b, c, p in zip(blobs, coms, proofs))
+    assert dn.verify_blob_kzg_proof_batch(blobs, coms, proofs) is True
+    assert dn.verify_blob_kzg_proof_batch(blobs, coms, [proofs[1], proofs[0], proofs[2]]) is False
+    assert dn.verify_blob_kzg_proof_batch([], [], []) is True
+    r = dn.batch_challenge(coms[:2], [5, 6], [7, 8], proofs[:2])
+    msg = b"RCKZGBATCH___V1_" + (4096).to_bytes(8, "big") + (2).to_bytes(8, "big")
+    msg += coms[0] + (5).to_bytes(32, "big") + (7).to_bytes(32, "big") + proofs[0]
+    msg += coms[1] + (6).to_bytes(32, "big") + (8).to_bytes(32, "big") + proofs[1]
+    assert r == int.from_bytes(hashlib.sha256(msg).digest(), "big") % R
+    with pytest.raises(kzg.KzgError):
+        dn.blob_to_kzg_commitment(R.to_bytes(32, "big") + blobs[0][32:])   # non-canonical word
+    # same polynomial, little-endian era: the commitment is the same point
+    le = kzg.LeMode(py_setup)
+    from tests._deneb import rev_fields
+    assert le.blob_to_kzg_commitment(rev_fields(blobs[0])) == coms[0]
+
+
 def test_reference_semantics_differ_from_yaml(ref, vectors):
     """SURVEY finding 4: with the reference's semantics (BE, monomial) only the
     all-zero blob matches its YAML commitment."""
