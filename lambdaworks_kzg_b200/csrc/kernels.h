@@ -115,9 +115,14 @@ void launch_le_eval_quot(void* d_q, void* d_y, void* d_y_le32, const void* d_blo
                          bool be = false);
 
 // ---- generic (variable-base) MSM for lwkzg_g1_lincomb (varmsm.cu)
-void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st);
+// points_in_g1: the caller vouches that every point is in the r-torsion (enables the GLV split for n <= 2^18)
+void launch_var_msm(void* d_out48, const void* d_points_xy_be, const void* d_scalars_be, size_t n, void* d_scratch, cudaStream_t st,
+                    bool points_in_g1 = false);
+// the same pipeline on device-format inputs: Montgomery affine points known to be in G1, canonical 8 x u32 scalars;
+// writes canonical big-endian affine x || y (96 bytes, all-zero = infinity)
+void launch_var_msm_mont(void* d_out_affine_be96, const void* d_points_mont, const void* d_scalars_canon8, size_t n, void* d_scratch, cudaStream_t st);
 size_t var_msm_scratch_bytes(size_t n);
-size_t var_msm_bad_flag_offset(size_t n);
+size_t var_msm_bad_flag_offset(size_t n, bool points_in_g1 = false);
 int var_msm_window_bits(size_t n);
 void launch_var_msm_synth(void* d_pts_be, void* d_sc_be, const void* d_table, unsigned long long n_entries, unsigned long long seed, size_t n,
                           cudaStream_t st);  // int flag inside the scratch: 1 = some point was not on the curve

@@ -49,6 +49,7 @@ struct Options {
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
+  long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
   long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode),
                   // 2 = MODE_DENEB (the mainnet wire format: big-endian canonical scalars over the Lagrange SRS)
   Options() {
@@ -1026,6 +1027,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "msm_algo") { if (value != 0 && value != 1) return 1; opts().msm_algo = value; return 0; }
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
   if (n == "verify_super_blobs") { if (value < 1) return 1; opts().verify_super_blobs = value; return 0; }
+  if (n == "lincomb_points_in_g1") { if (value != 0 && value != 1) return 1; opts().lincomb_points_in_g1 = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
   return 1;
 }
@@ -1039,6 +1041,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "msm_algo") return opts().msm_algo;
   if (n == "msm_ba_min_blobs") return opts().msm_ba_min_blobs;
   if (n == "verify_super_blobs") return opts().verify_super_blobs;
+  if (n == "lincomb_points_in_g1") return opts().lincomb_points_in_g1;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel
   if (n == "msm_ba_slots") return msm_ba_slots();       // read-only: affine accumulators per thread
   return -1;
@@ -1414,12 +1417,13 @@ double lwkzg_bench_var_msm(Bytes48* out, size_t n, int iters, uint64_t seed, con
     CU_TRY(cudaMalloc(&d_out, 48));
     unsigned long long entries = table_entries(c->c, N_POINTS);
     launch_var_msm_synth(d_pts, d_sc, c->d_table, entries, seed, n, st);
-    launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, st);  // warm-up
+    // the synthetic points are entries of the fixed-base table, i.e. multiples of validated SRS points: in G1
+    launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, st, true);  // warm-up
     cudaEvent_t e0, e1;
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
     CU_TRY(cudaEventRecord(e0, st));
-    for (int i = 0; i < iters; i++) launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, st);
+    for (int i = 0; i < iters; i++) launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, st, true);
     CU_TRY(cudaEventRecord(e1, st));
     CU_TRY(cudaEventSynchronize(e1));
     float ms = 0;
@@ -1436,30 +1440,54 @@ double lwkzg_bench_var_msm(Bytes48* out, size_t n, int iters, uint64_t seed, con
 }
 
 // ---- generic linear combination (g1_lincomb, lib.rs:241-243)
+// The call has no KZGSettings to hang a context on: the device buffers (inputs, MSM scratch, result) and the stream
+// live in a per-device workspace that grows to the largest n seen and is reused -- no cudaMalloc / cudaFree and no
+// device-wide synchronisation per call.
+namespace {
+struct LincombWs {
+  DevBuf pts, sc, scratch, out;
+  cudaStream_t st = nullptr;
+  void* h_out = nullptr;   // pinned: 48 result bytes + the bad-point flag
+};
+std::mutex g_lincomb_mu;
+std::map<int, LincombWs>& lincomb_ws() {
+  static std::map<int, LincombWs> m;
+  return m;
+}
+}  // namespace
+
 C_KZG_RET lwkzg_g1_lincomb(Bytes48* out, const uint8_t* points_xy_be, const uint8_t* scalars_be, size_t n) {
-  if (!out) return C_KZG_ERROR;
-  void *d_pts = nullptr, *d_sc = nullptr, *d_scratch = nullptr, *d_out = nullptr;
+  if (!out || (n && (!points_xy_be || !scalars_be))) return C_KZG_ERROR;
+  bool in_g1;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    in_g1 = opts().lincomb_points_in_g1 != 0;
+  }
+  std::lock_guard<std::mutex> lk(g_lincomb_mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_err("no CUDA device"); return C_KZG_ERROR; }
+  LincombWs& w = lincomb_ws()[dev];
   int bad = 0;
   bool good = [&]() -> bool {
-    size_t nn = std::max<size_t>(n, 1);
-    CU_TRY(cudaMalloc(&d_pts, nn * 96));
-    CU_TRY(cudaMalloc(&d_sc, nn * 32));
-    CU_TRY(cudaMalloc(&d_scratch, var_msm_scratch_bytes(nn)));
-    CU_TRY(cudaMalloc(&d_out, 48));
+    const size_t nn = std::max<size_t>(n, 1);
+    if (!w.st) CU_TRY(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
+    if (!w.h_out) CU_TRY(cudaMallocHost(&w.h_out, 64));
+    if (!w.pts.ensure(nn * 96) || !w.sc.ensure(nn * 32) || !w.scratch.ensure(var_msm_scratch_bytes(nn)) || !w.out.ensure(48)) return false;
     if (n) {
-      CU_TRY(cudaMemcpy(d_pts, points_xy_be, n * 96, cudaMemcpyHostToDevice));
-      CU_TRY(cudaMemcpy(d_sc, scalars_be, n * 32, cudaMemcpyHostToDevice));
+      CU_TRY(cudaMemcpyAsync(w.pts.p, points_xy_be, n * 96, cudaMemcpyHostToDevice, w.st));
+      CU_TRY(cudaMemcpyAsync(w.sc.p, scalars_be, n * 32, cudaMemcpyHostToDevice, w.st));
     }
-    launch_var_msm(d_out, d_pts, d_sc, n, d_scratch, 0);
-    CU_TRY(cudaDeviceSynchronize());
+    launch_var_msm(w.out.p, w.pts.p, w.sc.p, n, w.scratch.p, w.st, in_g1);
+    CU_TRY(cudaMemcpyAsync(w.h_out, w.out.p, 48, cudaMemcpyDeviceToHost, w.st));
+    CU_TRY(cudaMemcpyAsync((uint8_t*)w.h_out + 48, (uint8_t*)w.scratch.p + var_msm_bad_flag_offset(nn, in_g1), sizeof(int), cudaMemcpyDeviceToHost, w.st));
+    CU_TRY(cudaStreamSynchronize(w.st));
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpy(out, d_out, 48, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(&bad, (uint8_t*)d_scratch + var_msm_bad_flag_offset(nn), sizeof(int), cudaMemcpyDeviceToHost));
+    memcpy(&bad, (uint8_t*)w.h_out + 48, sizeof(int));
     return true;
   }();
-  cudaFree(d_pts); cudaFree(d_sc); cudaFree(d_scratch); cudaFree(d_out);
   if (!good) return C_KZG_ERROR;
   if (bad) { set_err("point not on the curve"); return C_KZG_BADARGS; }
+  memcpy(out, w.h_out, 48);
   return C_KZG_OK;
 }
 
