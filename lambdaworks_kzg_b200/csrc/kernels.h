@@ -96,9 +96,11 @@ size_t batch_challenge_state_bytes();
 int batch_challenge_blocks_ready(size_t tuples_ready);
 void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples160, size_t n_total, int blk0, int blk1, bool first, bool last,
                                  cudaStream_t st, int wire = 0);
-// partial sums over [first, first+n_local): 3 XYZZ blocks-partials then reduced to 3 affine (canonical BE 96 B each)
+// partial sums over [first, first+n_local) as two bucket MSMs (varmsm.cu): 3 affine points, canonical BE 96 B each --
+// sum r^i pi_i | infinity | sum r^i z_i pi_i + sum r^i C_i - (sum r^i y_i) G.  The smaller MSM runs on st2 between
+// ev_fork and ev_join; everything is ordered after earlier work on st and finished for later work on st.
 void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
-                           size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st);
+                           size_t first, int n_local, void* d_scratch, cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 size_t batch_partials_scratch_bytes(int n_local);
 // sum n_ranks partial triples, then e(rhs, g2_0) * e(-proof_lincomb, g2_1) == 1
 void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const void* d_prep0, const void* d_prep1, cudaStream_t st);

@@ -1243,7 +1243,8 @@ static C_KZG_RET verify_blob_batch(bool* ok, const Blob* blobs, const Bytes48* c
   if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   const double t2 = now();
   cudaStream_t s0 = c->slot[0].st;
-  launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, 0, (int)n, c->vb_scratch.p, s0);
+  launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, 0, (int)n, c->vb_scratch.p, s0, c->slot[0].aux,
+                        c->slot[0].ev_fork, c->slot[0].ev_aux);
   launch_batch_final((int*)c->vb_ok.p, c->vb_partial.p, 1, c->d_prep0, c->d_prep1, s0);
   int okv = 0;
   if (cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0) != cudaSuccess || cudaStreamSynchronize(s0) != cudaSuccess ||
@@ -1302,7 +1303,8 @@ C_KZG_RET lwkzg_verify_batch_phase2(uint8_t* partial288, const uint8_t* all_tupl
     CU_TRY(cudaMemcpyAsync(d_all, all_tuples160, n_total * 160, cudaMemcpyHostToDevice, s0));
     if (!c->vb_r.ensure(32) || !c->vb_partial.ensure(288) || !c->vb_scratch.ensure(batch_partials_scratch_bytes((int)std::max<size_t>(n_local, 1)))) return false;
     launch_batch_challenge(c->vb_r.p, d_all, n_total, s0, c->mode);
-    launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, first, (int)n_local, c->vb_scratch.p, s0);
+    launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, first, (int)n_local, c->vb_scratch.p, s0,
+                          c->slot[0].aux, c->slot[0].ev_fork, c->slot[0].ev_aux);
     CU_TRY(cudaMemcpyAsync(partial288, c->vb_partial.p, 288, cudaMemcpyDeviceToHost, s0));
     CU_TRY(cudaStreamSynchronize(s0));
     CU_TRY(cudaGetLastError());

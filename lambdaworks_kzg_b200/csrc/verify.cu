@@ -9,6 +9,8 @@
 //        e(C - y g1[0] + z pi, g2[0]) * e(-pi, g2[1]) == 1
 // so that both G2 arguments are the FIXED setup points whose Miller-loop lines
 // were precomputed at load time (pairing.cuh): no G2 arithmetic at verify time.
+#include <algorithm>
+
 #include "kernels.h"
 #include "pairing_warp.cuh"
 #include "sha256.cuh"
@@ -229,167 +231,76 @@ __device__ __forceinline__ void block_reduce_xyzz(G1Xyzz& acc, uint32_t* red) {
   }
 }
 
-constexpr int BV_THREADS = 64;
-
-// grid = (blocks, 6).  which = blockIdx.y % 3:
-//   0: sum r^i pi_i      1: sum (r^i z_i) pi_i      2: sum r^i C_i - (sum r^i y_i) G
-// half = blockIdx.y / 3: the GLV split k = q x^2 + m turns every scalar multiplication into two independent
-// 128-bit ones ([m]P and [q](beta x, -y)); the kernel is bound by the latency of one thread's double-and-add
-// chain, so the halves go to different threads (192 instead of 256 sequential group operations each).
-// Block tree, one XYZZ partial per block into scratch[blockIdx.y][block].
-__global__ void __launch_bounds__(BV_THREADS) batch_partials_kernel(G1Xyzz* __restrict__ scratch, const uint32_t* __restrict__ r_in,
-                                                                     const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
-                                                                     const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
-                                                                     unsigned long long first, int n_local) {
-  __shared__ uint32_t red[48 * (BV_THREADS / 2)];
-  __shared__ uint32_t ysum[BV_THREADS][8];
-  const int which = blockIdx.y % 3, half = blockIdx.y / 3;
-  const int i = blockIdx.x * BV_THREADS + threadIdx.x;
-  G1Xyzz acc = xyzz_inf();
-  Fr ys = fr_zero();  // canonical
-  if (i < n_local) {
+// ---- the random linear combination of a batched verification (verify_kzg_proof_batch, lib.rs:639-692) as two
+// bucket MSMs over the batch -- the reference computes it with three `msm` calls (lib.rs:679-685):
+//   proof_lincomb                        = sum r^i pi_i                                   (n points)
+//   proof_z_lincomb + c_minus_y_lincomb  = sum (r^i z_i) pi_i + sum r^i C_i - (sum r^i y_i) G   (2n + 1 points)
+// (the pairing check only ever uses the SUM of the last two).  This kernel derives the scalars and lays the
+// points of the second MSM out contiguously: [C_0 .. C_{n-1} | pi_0 .. pi_{n-1} | G].
+constexpr int RLC_THREADS = 128;
+__global__ void __launch_bounds__(RLC_THREADS) rlc_scalars_kernel(uint32_t* __restrict__ sc_a, uint32_t* __restrict__ sc_b, G1Affine* __restrict__ pts_b,
+                                                                   uint32_t* __restrict__ ypart, uint32_t* __restrict__ ticket,
+                                                                   const uint32_t* __restrict__ r_in, const G1Affine* __restrict__ c_aff,
+                                                                   const G1Affine* __restrict__ pi_aff, const uint32_t* __restrict__ z,
+                                                                   const uint32_t* __restrict__ y, unsigned long long first, int n) {
+  __shared__ uint32_t ysum[RLC_THREADS][8];
+  __shared__ bool is_last;
+  const int i = blockIdx.x * RLC_THREADS + threadIdx.x;
+  Fr ys = fr_zero();   // canonical r^(first + i) y_i
+  if (i < n) {
     Fr rc;
     for (int k = 0; k < 8; k++) rc.l[k] = r_in[k];
-    Fr rm = fr_to_mont(rc);
-    // r^(first + i), Montgomery
-    unsigned long long e = first + (unsigned long long)i;
-    Fr pw = fr_one();
+    const Fr rm = fr_to_mont(rc);
+    const unsigned long long e = first + (unsigned long long)i;
+    Fr pw = fr_one();   // r^e, Montgomery
     bool started = false;
     for (int bit = 63; bit >= 0; bit--) {
       if (started) pw = fr_sqr(pw);
       if ((e >> bit) & 1ull) { pw = fr_mul(pw, rm); started = true; }
     }
-    Fr sc;  // canonical scalar
-    G1Affine base;
-    if (which == 0) {
-      sc = fr_from_mont(pw);
-      base = pi_aff[i];
-    } else if (which == 1) {
-      Fr zc;
-      for (int k = 0; k < 8; k++) zc.l[k] = z[i * 8 + k];
-      sc = fr_mul(pw, zc);  // mont(r^i) * canonical z = canonical r^i z
-      base = pi_aff[i];
-    } else {
-      sc = fr_from_mont(pw);
-      base = c_aff[i];
-      Fr yc;
-      for (int k = 0; k < 8; k++) yc.l[k] = y[i * 8 + k];
-      if (half == 0) ys = fr_mul(pw, yc);  // canonical r^i y_i
+    Fr zc, yc;
+    for (int k = 0; k < 8; k++) { zc.l[k] = z[i * 8 + k]; yc.l[k] = y[i * 8 + k]; }
+    const Fr p1 = fr_from_mont(pw);
+    const Fr pz = fr_mul(pw, zc);   // mont(r^e) * canonical z = canonical r^e z
+    ys = fr_mul(pw, yc);
+    for (int k = 0; k < 8; k++) {
+      sc_a[(size_t)i * 8 + k] = p1.l[k];
+      sc_b[(size_t)i * 8 + k] = p1.l[k];
+      sc_b[((size_t)n + i) * 8 + k] = pz.l[k];
     }
-    // sc is canonical (< r): [sc]P = [m]P + [q](beta x, -y), 128 doublings each
-    if (!g1a_is_inf(base)) {
-      uint32_t q4[4], m4[4];
-      glv_split(q4, m4, sc.l);
-      if (half == 0) {
-        acc = g1_mul_scalar(base, m4, 4);
-      } else {
-        Fp beta;
-        for (int k = 0; k < 12; k++) beta.l[k] = k::FP_BETA[k];
-        G1Affine p2;
-        p2.x = fp_mul(base.x, beta);
-        p2.y = fp_neg(base.y);
-        acc = g1_mul_scalar(p2, q4, 4);
-      }
+    pts_b[i] = c_aff[i];
+    pts_b[(size_t)n + i] = pi_aff[i];
+  }
+  for (int k = 0; k < 8; k++) ysum[threadIdx.x][k] = ys.l[k];
+  __syncthreads();
+  for (int s = RLC_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      Fr a, b;
+      for (int k = 0; k < 8; k++) { a.l[k] = ysum[threadIdx.x][k]; b.l[k] = ysum[threadIdx.x + s][k]; }
+      a = fr_add(a, b);
+      for (int k = 0; k < 8; k++) ysum[threadIdx.x][k] = a.l[k];
     }
+    __syncthreads();
   }
-  if (which == 2 && half == 0) {
-    for (int k = 0; k < 8; k++) ysum[threadIdx.x][k] = ys.l[k];
-  }
-  block_reduce_xyzz<BV_THREADS>(acc, red);
   if (threadIdx.x == 0) {
-    if (which == 2 && half == 0) {
-      Fr tot = fr_zero();
-      for (int t = 0; t < BV_THREADS; t++) {
-        Fr v;
-        for (int k = 0; k < 8; k++) v.l[k] = ysum[t][k];
-        tot = fr_add(tot, v);
-      }
-      uint32_t* ys_out = reinterpret_cast<uint32_t*>(scratch + (size_t)6 * gridDim.x) + (size_t)blockIdx.x * 8;
-      for (int k = 0; k < 8; k++) ys_out[k] = tot.l[k];
-    }
-    scratch[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+    for (int k = 0; k < 8; k++) ypart[(size_t)blockIdx.x * 8 + k] = ysum[0][k];
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
-}
-
-// One warp: threads 0..2 sum the block partials of the three sums; then ALL 32 threads share the one scalar
-// multiplication (sum r^i y_i) G -- thread t multiplies the precomputed 2^(8t) G (constants.cuh) by byte t of the
-// scalar and a shared-memory tree adds the 32 pieces (3.6 ms of single-thread double-and-add -> ~0.3 ms);
-// threads 0..2 normalise and emit canonical big-endian affine (96 B each).
-__global__ void __launch_bounds__(32) batch_partials_finish_kernel(uint8_t* __restrict__ out288, const G1Xyzz* __restrict__ scratch, int blocks) {
-  __shared__ uint32_t red[48 * 16];
-  __shared__ uint32_t tot_s[8];
-  __shared__ G1Xyzz part_s[30];
-  const int which = threadIdx.x, lane = threadIdx.x;
-  G1Xyzz acc = xyzz_inf();
-  // sum w has 2 * blocks partials (both GLV halves): rows w and w + 3 of scratch.  Lanes 10 w .. 10 w + 9 take
-  // every tenth of them, lane w (< 3) then adds the ten pieces.
-  if (lane < 30) {
-    const int w = lane / 10, j = lane % 10;
-    G1Xyzz part = xyzz_inf();
-    for (int b = j; b < 2 * blocks; b += 10) {
-      G1Xyzz o = scratch[(size_t)(b < blocks ? w : w + 3) * blocks + (b < blocks ? b : b - blocks)];
-      xyzz_add_ni(part, o);
-    }
-    part_s[lane] = part;
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  // last block: - (sum r^i y_i) times the generator G (lib.rs:661-668 uses the curve generator)
+  __threadfence();
+  Fr tot = fr_zero();
+  for (unsigned b = 0; b < gridDim.x; b++) {
+    Fr v;
+    for (int k = 0; k < 8; k++) v.l[k] = __ldcg(ypart + (size_t)b * 8 + k);
+    tot = fr_add(tot, v);
   }
-  __syncwarp();
-  if (which < 3) {
-    for (int j = 0; j < 10; j++) {
-      G1Xyzz o = part_s[which * 10 + j];
-      xyzz_add_ni(acc, o);
-    }
-  }
-  if (which == 2) {
-    const uint32_t* ys = reinterpret_cast<const uint32_t*>(scratch + (size_t)6 * blocks);
-    Fr tot = fr_zero();
-    for (int b = 0; b < blocks; b++) {
-      Fr v;
-      for (int k = 0; k < 8; k++) v.l[k] = ys[(size_t)b * 8 + k];
-      tot = fr_add(tot, v);
-    }
-    for (int k = 0; k < 8; k++) tot_s[k] = tot.l[k];
-  }
-  __syncwarp();
-  // (sum r^i y_i) G, G = the curve generator (lib.rs:661-668)
-  G1Affine base;
-  for (int k = 0; k < 12; k++) { base.x.l[k] = k::G1_GEN_POW256[lane][k]; base.y.l[k] = k::G1_GEN_POW256[lane][12 + k]; }
-  uint32_t byte = (tot_s[lane >> 2] >> (8 * (lane & 3))) & 0xffu;
-  G1Xyzz piece = g1_mul_scalar(base, &byte, 1);
-  for (int s = 16; s > 0; s >>= 1) {
-    if (lane >= s && lane < 2 * s) {
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&piece);
-      for (int i = 0; i < 48; i++) red[i * 16 + (lane - s)] = w[i];
-    }
-    __syncwarp();
-    if (lane < s) {
-      G1Xyzz o;
-      uint32_t* w = reinterpret_cast<uint32_t*>(&o);
-      for (int i = 0; i < 48; i++) w[i] = red[i * 16 + lane];
-      xyzz_add_ni(piece, o);
-    }
-    __syncwarp();
-  }
-  if (lane == 0) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&piece);
-    for (int i = 0; i < 48; i++) red[i * 16] = w[i];
-  }
-  __syncwarp();
-  if (which == 2) {
-    G1Xyzz yg;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&yg);
-    for (int i = 0; i < 48; i++) w[i] = red[i * 16];
-    xyzz_add_ni(acc, xyzz_neg(yg));
-  }
-  if (which < 3) {
-    G1Affine a = xyzz_to_affine(acc);
-    uint8_t* o = out288 + 96 * which;
-    if (g1a_is_inf(a)) {
-      for (int k = 0; k < 96; k++) o[k] = 0;
-    } else {
-      fp_canon_to_be48(o, fp_from_mont(a.x));
-      fp_canon_to_be48(o + 48, fp_from_mont(a.y));
-    }
-  }
+  tot = fr_neg(tot);
+  for (int k = 0; k < 8; k++) sc_b[(size_t)2 * n * 8 + k] = tot.l[k];
+  pts_b[(size_t)2 * n] = g1a_generator();
+  *ticket = 0;
 }
 
 __device__ __forceinline__ G1Affine affine_from_be96(const uint8_t* b) {
@@ -464,20 +375,48 @@ void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples1
                                            (first ? BCH_INIT : 0) | (last ? BCH_FINAL : 0) | bch_wire_flags(wire));
   count_launch();
 }
-size_t batch_partials_scratch_bytes(int n_local) {
-  size_t blocks = (size_t)((n_local + BV_THREADS - 1) / BV_THREADS);
-  if (blocks < 1) blocks = 1;
-  return blocks * (6 * sizeof(G1Xyzz) + 32);
+struct RlcLayout { size_t sc_a, sc_b, pts_b, ypart, ticket, msm_a, msm_b, total; };
+static RlcLayout rlc_layout(size_t n) {
+  RlcLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  const size_t blocks = (n + RLC_THREADS - 1) / RLC_THREADS + 1;
+  L.sc_a = take(n * 32);
+  L.sc_b = take((2 * n + 1) * 32);
+  L.pts_b = take((2 * n + 1) * sizeof(G1Affine));
+  L.ypart = take(blocks * 32);
+  L.ticket = take(4);
+  L.msm_a = take(var_msm_scratch_bytes(n));
+  L.msm_b = take(var_msm_scratch_bytes(2 * n + 1));
+  L.total = off;
+  return L;
 }
+size_t batch_partials_scratch_bytes(int n_local) { return rlc_layout((size_t)std::max(n_local, 1)).total; }
+// st2 / ev_fork / ev_join: the two MSMs run side by side (the small one on st2)
 void launch_batch_partials(void* d_partial288, const void* d_r, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
-                           size_t first, int n_local, void* d_scratch_xyzz, cudaStream_t st) {
-  int blocks = (n_local + BV_THREADS - 1) / BV_THREADS;
-  if (blocks < 1) blocks = 1;
-  dim3 grid(blocks, 6);
-  batch_partials_kernel<<<grid, BV_THREADS, 0, st>>>((G1Xyzz*)d_scratch_xyzz, (const uint32_t*)d_r, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff,
-                                                    (const uint32_t*)d_z, (const uint32_t*)d_y, (unsigned long long)first, n_local);
-  batch_partials_finish_kernel<<<1, 32, 0, st>>>((uint8_t*)d_partial288, (const G1Xyzz*)d_scratch_xyzz, blocks);
-  count_launch(2);
+                           size_t first, int n_local, void* d_scratch, cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+  const size_t n = (size_t)std::max(n_local, 0);
+  const RlcLayout L = rlc_layout(std::max<size_t>(n, 1));
+  uint8_t* base = (uint8_t*)d_scratch;
+  uint8_t* out = (uint8_t*)d_partial288;
+  cudaMemsetAsync(base + L.ticket, 0, 4, st);
+  cudaMemsetAsync(out + 96, 0, 96, st);   // proof_z_lincomb travels inside the third point
+  if (n == 0) {
+    cudaMemsetAsync(out, 0, 288, st);
+    return;
+  }
+  const int blocks = (int)((n + RLC_THREADS - 1) / RLC_THREADS);
+  rlc_scalars_kernel<<<blocks, RLC_THREADS, 0, st>>>((uint32_t*)(base + L.sc_a), (uint32_t*)(base + L.sc_b), (G1Affine*)(base + L.pts_b),
+                                                     (uint32_t*)(base + L.ypart), (uint32_t*)(base + L.ticket), (const uint32_t*)d_r,
+                                                     (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
+                                                     (unsigned long long)first, (int)n);
+  count_launch();
+  cudaEventRecord(ev_fork, st);
+  cudaStreamWaitEvent(st2, ev_fork, 0);
+  launch_var_msm_mont(out, d_pi_aff, base + L.sc_a, n, base + L.msm_a, st2);
+  cudaEventRecord(ev_join, st2);
+  launch_var_msm_mont(out + 192, base + L.pts_b, base + L.sc_b, 2 * n + 1, base + L.msm_b, st);
+  cudaStreamWaitEvent(st, ev_join, 0);
 }
 void launch_batch_final(int* d_ok, const void* d_partials288, int n_ranks, const void* d_prep0, const void* d_prep1, cudaStream_t st) {
   batch_final_kernel<<<1, LW_PAIR_LANES, 0, st>>>(d_ok, (const uint8_t*)d_partials288, n_ranks, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1);
