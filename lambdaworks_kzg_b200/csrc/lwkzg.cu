@@ -881,12 +881,18 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   // challenge -> evaluation -> tuple) start on one of 2 * NSLOT compute streams as soon as its copy has landed.
   // The copy engine is the only thing that runs the whole time.
   const size_t super = dev_inputs ? n : std::min<size_t>(n, vb_super_blobs());   // device blobs are read in place
-  const size_t chunks_per_super = (super + (size_t)chunk - 1) / (size_t)chunk;
-  while (c->ev_pool.size() < 2 * chunks_per_super) {
-    cudaEvent_t e;
-    CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->ev_pool.push_back(e);
-  }
+  // (measured and not kept: small first chunks, so that the batch-challenge hash -- one sequential SHA-256 over
+  // all tuples, ~1 us per 64-byte block, as long as the blob copies -- starts absorbing 1.5 ms earlier: the hash
+  // then runs slower beside the extra kernels and the batch ends 0.4 ms later, profiles/r02_verify_notes.md)
+  auto chunk_len = [&](size_t, size_t left) -> size_t { return std::min((size_t)chunk, left); };
+  auto need_events = [&](size_t count) -> bool {
+    while (c->ev_pool.size() < count) {
+      cudaEvent_t e;
+      CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->ev_pool.push_back(e);
+    }
+    return true;
+  };
   cudaStream_t cs[2 * NSLOT];
   for (int i = 0; i < NSLOT; i++) { cs[2 * i] = c->slot[i].st; cs[2 * i + 1] = c->slot[i].aux; }
   auto sync_all = [&]() -> bool {
@@ -908,8 +914,10 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     if (base > 0 && !sync_all()) return false;   // the staging area is about to be overwritten
     const size_t top = std::min(n, base + super);
     size_t j = 0;
-    for (size_t off = base; off < top; off += chunk, k++, j++) {
-      const int m = (int)std::min<size_t>(chunk, top - off);
+    for (size_t off = base, m_sz = 0; off < top; off += m_sz, k++, j++) {
+      m_sz = chunk_len(off, top - off);
+      const int m = (int)m_sz;
+      if (!need_events(2 * j + 2)) return false;
       const uint8_t* d_blobs = dev_inputs ? (const uint8_t*)blobs + off * BLOB_BYTES : (const uint8_t*)c->vb_blobs.p + (off - base) * BLOB_BYTES;
       void* d_states = (uint8_t*)c->vb_states.p + off * 32;
       cudaEvent_t ev_copied = c->ev_pool[2 * j], ev_tuples = c->ev_pool[2 * j + 1];

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(32) challenge_midstate_group_kernel(Sha256Stat
   const uint8_t* blob = blobs + (size_t)(blob_e < n ? blob_e : 0) * BLOB_BYTES;
   Sha256State s;
   sha256_init(s);
+  const uint32_t one = sha_runtime_one();
   for (int base = 0; base < 2048; base += PER) {
     if (blob_e < n) {
       const int blk = base + j;
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(32) challenge_midstate_group_kernel(Sha256Stat
     }
     __syncwarp();
     if (lane < G && blob_r < n) {
-      for (int t = 0; t < PER; t++) sha256_rounds_wk(s, wk, lane * PER + t);
+      for (int t = 0; t < PER; t++) sha256_rounds_wk(s, wk, lane * PER + t, one);
     }
     __syncwarp();
   }

@@ -61,27 +61,40 @@ LW_INL void sha256_compress(Sha256State& s, uint32_t* w) {
 
 // Rounds only, with W[i] + K[i] precomputed (warp-cooperative path below).
 // wk is laid out [64][32]: word i of the block prepared by lane b at wk[i * 32 + b].
-LW_INL void sha256_rounds_wk(Sha256State& s, const uint32_t* wk, int b) {
+//
+// One lane runs the rounds, so the warp's issue rate is the bound: a round is 6 funnel shifts + 4 three-input
+// logic ops + 7 additions, and on the ALU pipe (one warp instruction every two cycles) that is the measured 32
+// cycles per round.  The additions are therefore written as multiply-adds by a run-time 1 (`one`: a value ptxas
+// cannot fold), which issue on the FMA pipe beside the shifts and logic ops.
+#if defined(LWKZG_HOST_EMUL)
+LW_INL uint32_t sha_add(uint32_t a, uint32_t b, uint32_t) { return a + b; }
+LW_INL uint32_t sha_runtime_one() { return 1u; }
+#else
+static __device__ uint32_t g_sha_one = 1u;
+LW_INL uint32_t sha_add(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
+LW_INL uint32_t sha_runtime_one() { return *(volatile uint32_t*)&g_sha_one; }
+#endif
+LW_INL void sha256_rounds_wk(Sha256State& s, const uint32_t* wk, int b, uint32_t one) {
   uint32_t a = s.h[0], bb = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
   // all 64 schedule words are requested before the first round: left to itself ptxas issues each shared-memory
-  // load right before its use, which puts the ~30-cycle load on the dependency chain of EVERY round (measured
-  // 32 cycles per round; the arithmetic chain is three instructions deep)
+  // load right before its use, which puts the ~30-cycle load on the dependency chain of EVERY round
   uint32_t kw[64];
 #pragma unroll
   for (int i = 0; i < 64; i++) kw[i] = wk[i * 32 + b];
 #pragma unroll
   for (int i = 0; i < 64; i++) {
-    const uint32_t dhk = d + h + kw[i];                   // off the e-chain (see sha256_compress)
+    const uint32_t dhk = sha_add(sha_add(d, h, one), kw[i], one);   // off the e-chain (see sha256_compress)
     const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
     const uint32_t ch = g ^ (e & (f ^ g));
-    const uint32_t e_new = dhk + S1 + ch;
+    const uint32_t e_new = sha_add(S1, sha_add(dhk, ch, one), one);
     const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
     const uint32_t mj = (a & bb) | (c & (a | bb));
-    const uint32_t t2md = S0 + mj - d;
-    h = g; g = f; f = e; d = c; c = bb; bb = a; a = e_new + t2md; e = e_new;
+    const uint32_t t2md = sha_add(S0, mj - d, one);
+    h = g; g = f; f = e; d = c; c = bb; bb = a; a = sha_add(e_new, t2md, one); e = e_new;
   }
   s.h[0] += a; s.h[1] += bb; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
+LW_INL void sha256_rounds_wk(Sha256State& s, const uint32_t* wk, int b) { sha256_rounds_wk(s, wk, b, sha_runtime_one()); }
 // Message-schedule expansion of one block into wk (adds the round constants).
 LW_INL void sha256_expand_wk(uint32_t* wk, int b, uint32_t* w /* 16 words in, 64 used */) {
 #pragma unroll
@@ -104,6 +117,7 @@ LW_INL void sha256_expand_wk(uint32_t* wk, int b, uint32_t* w /* 16 words in, 64
 template <class Load>
 __device__ __forceinline__ void sha256_warp_blocks(Sha256State& s, int nblocks, Load load, uint32_t* wk) {
   const int lane = threadIdx.x & 31;
+  const uint32_t one = sha_runtime_one();
   for (int base = 0; base < nblocks; base += 32) {
     const int blk = base + lane;
     if (blk < nblocks) {
@@ -114,7 +128,7 @@ __device__ __forceinline__ void sha256_warp_blocks(Sha256State& s, int nblocks, 
     __syncwarp();
     if (lane == 0) {
       const int cnt = (nblocks - base < 32) ? (nblocks - base) : 32;
-      for (int b = 0; b < cnt; b++) sha256_rounds_wk(s, wk, b);
+      for (int b = 0; b < cnt; b++) sha256_rounds_wk(s, wk, b, one);
     }
     __syncwarp();
   }
