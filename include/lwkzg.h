@@ -187,6 +187,31 @@ C_KZG_RET lwkzg_verify_batch_phase2(uint8_t *partial288, const uint8_t *all_tupl
 C_KZG_RET lwkzg_verify_batch_phase3(bool *ok, const uint8_t *partials288, size_t n_ranks,
                                     const KZGSettings *s);
 
+/* The same phases with the exchanged data in DEVICE memory, so that the all-gathers can run on it directly
+ * (ncclAllGather / torch.distributed on CUDA tensors): phase 1 writes n_local tuples to d_tuples160 (blobs,
+ * commitments and proofs are host pointers, or device pointers when inputs_on_device != 0); phase 2 reads all
+ * n_total tuples from d_all_tuples160 and writes 288 bytes to d_partial288; phase 3 reads n_ranks x 288 bytes.
+ * Each call returns when its results are complete in memory. */
+C_KZG_RET lwkzg_verify_batch_phase1_device(void *d_tuples160, const void *blobs, const void *commitments,
+                                           const void *proofs, size_t n_local, int inputs_on_device,
+                                           const KZGSettings *s);
+C_KZG_RET lwkzg_verify_batch_phase2_device(void *d_partial288, const void *d_all_tuples160,
+                                           size_t n_total, size_t first, size_t n_local,
+                                           const KZGSettings *s);
+C_KZG_RET lwkzg_verify_batch_phase3_device(bool *ok, const void *d_partials288, size_t n_ranks,
+                                           const KZGSettings *s);
+
+/* Multi-GPU from ONE process: after lwkzg_set_devices(ids, n) every host-buffer batch call
+ * -- lwkzg_blob_to_kzg_commitment_batch, lwkzg_compute_blob_kzg_proof_batch, lwkzg_compute_kzg_proof_batch,
+ * lwkzg_commit_and_prove_batch, verify_blob_kzg_proof_batch -- splits its items into contiguous shards over the
+ * listed CUDA devices: one host thread and one stream set per device, the SRS and its digit table replicated on
+ * each (built on the first such call).  Commit / proof shards need no exchange; batched verification exchanges
+ * the 160-byte tuples and 288 bytes of partial sums per device (the reference's per-blob loop, src/lib.rs:562-596,
+ * and its linear combination, :639-692).  Results are byte-identical to the single-device call.  n = 0 restores
+ * the default (the device the settings were loaded on).  Returns 0 on success, 1 for an unknown or repeated id. */
+int lwkzg_set_devices(const int *ids, int n);
+int lwkzg_get_devices(int *ids, int cap);
+
 /* Synthetic blobs: word i of blob k = four big-endian u64 from
  * SplitMix64 seeded with 0xB2004844 ^ (k*4096+i), byte[0] &= 0x3f.  Written
  * straight into device memory so large batches never cross PCIe. */

@@ -48,6 +48,11 @@ from .api import (  # noqa: F401
     verify_batch_phase1,
     verify_batch_phase2,
     verify_batch_phase3,
+    verify_batch_phase1_device,
+    verify_batch_phase2_device,
+    verify_batch_phase3_device,
+    set_devices,
+    get_devices,
     verify_blob_kzg_proof,
     verify_blob_kzg_proof_batch,
     verify_blob_kzg_proof_batch_device,
@@ -56,4 +61,4 @@ from .api import (  # noqa: F401
     compute_blob_kzg_proof_batch_device,
     verify_kzg_proof,
 )
-from .sharding import shard_range, verify_blob_kzg_proof_batch_distributed  # noqa: F401
+from .sharding import shard_range, verify_blob_kzg_proof_batch_distributed, verify_blob_kzg_proof_batch_distributed_device  # noqa: F401

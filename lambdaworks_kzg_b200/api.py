@@ -69,6 +69,11 @@ def load_library() -> ctypes.CDLL:
         "lwkzg_verify_batch_phase1": [vp, vp, vp, vp, sz, sp],
         "lwkzg_verify_batch_phase2": [vp, vp, sz, sz, sz, sp],
         "lwkzg_verify_batch_phase3": [bp, vp, sz, sp],
+        "lwkzg_verify_batch_phase1_device": [vp, vp, vp, vp, sz, ctypes.c_int, sp],
+        "lwkzg_verify_batch_phase2_device": [vp, vp, sz, sz, sz, sp],
+        "lwkzg_verify_batch_phase3_device": [bp, vp, sz, sp],
+        "lwkzg_set_devices": [ip, ctypes.c_int],
+        "lwkzg_get_devices": [ip, ctypes.c_int],
         "lwkzg_debug_batch_challenge": [vp, sp],
         "lwkzg_synth_blobs_device": [vp, ctypes.c_uint64, sz, vp],
         "lwkzg_synth_blob_host": [vp, ctypes.c_uint64],
@@ -412,6 +417,35 @@ def verify_batch_phase2(all_tuples: bytes, n_total: int, first: int, n_local: in
     out = ctypes.create_string_buffer(288)
     _check(load_library().lwkzg_verify_batch_phase2(out, all_tuples, n_total, first, n_local, _sp(s)), "lwkzg_verify_batch_phase2")
     return out.raw
+
+
+def verify_batch_phase1_device(d_tuples: int, blobs_ptr: int, commitments_ptr: int, proofs_ptr: int, n_local: int, s, inputs_on_device: bool):
+    """phase 1 with the tuples written to device memory (d_tuples: n_local x 160 bytes); inputs are raw host or device addresses."""
+    _check(load_library().lwkzg_verify_batch_phase1_device(d_tuples, blobs_ptr, commitments_ptr, proofs_ptr, n_local, 1 if inputs_on_device else 0, _sp(s)),
+           "lwkzg_verify_batch_phase1_device")
+
+
+def verify_batch_phase2_device(d_partial: int, d_all_tuples: int, n_total: int, first: int, n_local: int, s):
+    _check(load_library().lwkzg_verify_batch_phase2_device(d_partial, d_all_tuples, n_total, first, n_local, _sp(s)), "lwkzg_verify_batch_phase2_device")
+
+
+def verify_batch_phase3_device(d_partials: int, n_ranks: int, s) -> bool:
+    ok = ctypes.c_bool(False)
+    _check(load_library().lwkzg_verify_batch_phase3_device(ctypes.byref(ok), d_partials, n_ranks, _sp(s)), "lwkzg_verify_batch_phase3_device")
+    return bool(ok.value)
+
+
+def set_devices(ids: Sequence[int]):
+    """lwkzg_set_devices: shard the host-buffer batch calls of THIS process over the listed GPUs ([] = default)."""
+    arr = (ctypes.c_int * max(len(ids), 1))(*ids)
+    if load_library().lwkzg_set_devices(arr, len(ids)) != 0:
+        raise ValueError("lwkzg_set_devices(%r) rejected" % (list(ids),))
+
+
+def get_devices() -> List[int]:
+    arr = (ctypes.c_int * 64)()
+    n = load_library().lwkzg_get_devices(arr, 64)
+    return [arr[i] for i in range(min(n, 64))]
 
 
 def verify_batch_phase3(partials: bytes, n_ranks: int, s) -> bool:

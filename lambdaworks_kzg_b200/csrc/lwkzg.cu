@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lwkzg.h"
@@ -128,6 +129,12 @@ struct Ctx {
   void* h_stage = nullptr;
   size_t h_stage_cap = 0;
   std::mutex mu;
+  // lwkzg_set_devices: contexts of the same settings on the other GPUs (built on the first multi-device call; owned
+  // by this, the primary, context) and the host arrays they were built from
+  const g1_t* g1_host = nullptr;
+  const g2_t* g2_host = nullptr;
+  std::vector<Ctx*> replicas;
+  std::mutex replicas_mu;
 };
 
 struct DeviceGuard {
@@ -158,6 +165,8 @@ void blst_fp_to_canon(uint32_t* le12, const blst_fp* in) {
 // ------------------------------------------------------------------ context
 void destroy_ctx(Ctx* c) {
   if (!c) return;
+  for (Ctx* r : c->replicas) destroy_ctx(r);
+  c->replicas.clear();
   DeviceGuard g(c->device);
   for (auto& s : c->slot) {
     if (s.st) cudaStreamSynchronize(s.st);
@@ -322,6 +331,8 @@ Ctx* build_ctx(const g1_t* g1, const g2_t* g2, int mode = -1, long window_overri
   c->mode = mode;
   c->c = c->nwin = 0;
   c->srs_valid = c->srs_in_g1 = c->g2_valid = false;
+  c->g1_host = g1;
+  c->g2_host = g2;
   if (!build_ctx_inner(c, g1, g2, mode, window_override)) {
     std::string e = tl_err;
     destroy_ctx(c);
@@ -553,18 +564,61 @@ C_KZG_RET first_bad(const std::vector<int>& st) {
   return C_KZG_OK;
 }
 
-// Host-buffer batch driver: chunked, double-buffered over two stream slots so
-// the H2D copy of chunk k+1 overlaps the kernels of chunk k.
-C_KZG_RET host_batch(Mode mode, const KZGSettings* s, size_t n, const Blob* blobs, const Bytes48* commit_in, const Bytes32* z_in,
-                     Bytes48* c_out, Bytes48* p_out, Bytes32* y_out, int* status) {
-  if (n == 0) return C_KZG_OK;
-  Ctx* c = ctx_of(s);
-  if (!c) return C_KZG_ERROR;
-  if (!c->srs_valid) {
-    set_err("SRS re-hydration failed: g1_values holds a point that is not on the curve");
-    if (status) for (size_t i = 0; i < n; i++) status[i] = C_KZG_ERROR;
-    return C_KZG_ERROR;
+// ------------------------------------------------------------------ devices (lwkzg_set_devices)
+std::vector<int>& device_list() {   // guarded by g_mu; empty = whatever device the settings were loaded on
+  static std::vector<int> d;
+  return d;
+}
+
+// The contexts a multi-device call runs on: the primary one plus a replica per other device of lwkzg_set_devices
+// (same SRS, same window, same mode), built side by side on first use.
+std::vector<Ctx*> ctxs_for(Ctx* c) {
+  std::vector<int> devs;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    devs = device_list();
   }
+  std::vector<Ctx*> out{c};
+  if (devs.size() <= 1 || !c->srs_valid) return out;
+  std::lock_guard<std::mutex> lk(c->replicas_mu);
+  std::vector<int> missing;
+  for (int d : devs) {
+    if (d == c->device) continue;
+    bool have = false;
+    for (Ctx* r : c->replicas) have = have || r->device == d;
+    if (!have) missing.push_back(d);
+  }
+  if (!missing.empty()) {
+    std::vector<Ctx*> built(missing.size(), nullptr);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < missing.size(); k++)
+      th.emplace_back([&, k]() {
+        if (cudaSetDevice(missing[k]) != cudaSuccess) return;
+        built[k] = build_ctx(c->g1_host, c->g2_host, c->mode, c->c);
+      });
+    for (auto& t : th) t.join();
+    for (Ctx* b : built)
+      if (b) c->replicas.push_back(b);
+  }
+  for (int d : devs) {
+    if (d == c->device) continue;
+    for (Ctx* r : c->replicas)
+      if (r->device == d && r->srs_valid) { out.push_back(r); break; }
+  }
+  return out;
+}
+
+// contiguous shard k of n items over g workers
+void shard_of(size_t n, size_t g, size_t k, size_t& first, size_t& count) {
+  const size_t base = n / g, rem = n % g;
+  count = base + (k < rem ? 1 : 0);
+  first = k * base + std::min(k, rem);
+}
+
+// Host-buffer batch driver on ONE device: chunked, double-buffered over the stream slots so
+// the H2D copy of chunk k+1 overlaps the kernels of chunk k.  `status` receives one code per item.
+C_KZG_RET host_batch_on(Ctx* c, Mode mode, size_t n, const Blob* blobs, const Bytes48* commit_in, const Bytes32* z_in,
+                        Bytes48* c_out, Bytes48* p_out, Bytes32* y_out, int* status) {
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard dg(c->device);
   long chunk;
@@ -622,11 +676,53 @@ C_KZG_RET host_batch(Mode mode, const KZGSettings* s, size_t n, const Blob* blob
       if (p_out) p_out[i] = p_tmp[i];
       if (y_out) y_out[i] = y_tmp[i];
     }
-    if (status) status[i] = st_host[i];
+    status[i] = st_host[i];
   }
+  return C_KZG_OK;
+}
+
+// Host-buffer batch driver: one device, or -- after lwkzg_set_devices -- contiguous shards of the batch on every
+// listed GPU, one host thread and stream set per device, no exchange between them (commit / proof
+// batches are independent units).
+C_KZG_RET host_batch(Mode mode, const KZGSettings* s, size_t n, const Blob* blobs, const Bytes48* commit_in, const Bytes32* z_in,
+                     Bytes48* c_out, Bytes48* p_out, Bytes32* y_out, int* status) {
+  if (n == 0) return C_KZG_OK;
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  if (!c->srs_valid) {
+    set_err("SRS re-hydration failed: g1_values holds a point that is not on the curve");
+    if (status) for (size_t i = 0; i < n; i++) status[i] = C_KZG_ERROR;
+    return C_KZG_ERROR;
+  }
+  std::vector<int> st_own;
+  int* st = status;
+  if (!st) { st_own.assign(n, 0); st = st_own.data(); }
+  C_KZG_RET rc = C_KZG_OK;
+  std::vector<Ctx*> ctxs = n >= 2 ? ctxs_for(c) : std::vector<Ctx*>{c};
+  if (ctxs.size() <= 1 || n < 2 * ctxs.size()) {
+    rc = host_batch_on(c, mode, n, blobs, commit_in, z_in, c_out, p_out, y_out, st);
+  } else {
+    const size_t g = ctxs.size();
+    std::vector<C_KZG_RET> rcs(g, C_KZG_OK);
+    std::vector<std::string> errs(g);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < g; k++)
+      th.emplace_back([&, k]() {
+        size_t first, cnt;
+        shard_of(n, g, k, first, cnt);
+        if (!cnt) return;
+        rcs[k] = host_batch_on(ctxs[k], mode, cnt, blobs + first, commit_in ? commit_in + first : nullptr, z_in ? z_in + first : nullptr,
+                               c_out ? c_out + first : nullptr, p_out ? p_out + first : nullptr, y_out ? y_out + first : nullptr, st + first);
+        if (rcs[k] != C_KZG_OK) errs[k] = tl_err;
+      });
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < g; k++)
+      if (rcs[k] != C_KZG_OK && rc == C_KZG_OK) { rc = rcs[k]; set_err(errs[k]); }
+  }
+  if (rc != C_KZG_OK) return rc;
   if (!status) {
     for (size_t i = 0; i < n; i++)
-      if (st_host[i]) { set_err("invalid input item"); return (C_KZG_RET)st_host[i]; }
+      if (st[i]) { set_err("invalid input item"); return (C_KZG_RET)st[i]; }
   }
   return C_KZG_OK;
 }
@@ -1227,6 +1323,94 @@ static C_KZG_RET verify_blob_single(bool* ok, const Blob* blob, const Bytes48* c
   return C_KZG_OK;
 }
 
+// verify_blob_kzg_proof_batch over the GPUs of lwkzg_set_devices: contiguous shards, one host thread
+// per device.  Phase 1 is local (decode, challenge, evaluation -> 160-byte tuples); exchange A brings the tuples
+// to the primary device, which derives r (one sequential hash over ALL tuples, utils.rs:166-206); phase 2 is local
+// again (the two MSMs of the shard with r^(first + i)); exchange B brings 288 bytes per device back; the primary
+// device adds them and runs the 2-pairing check.  Both exchanges are a few hundred KB at most and go through
+// pinned host memory of this one process.  Group addition is exact: the boolean does not depend on the sharding.
+static C_KZG_RET verify_blob_batch_multi(bool* ok, const Blob* blobs, const Bytes48* cs, const Bytes48* ps, size_t n, std::vector<Ctx*>& ctxs) {
+  const size_t g = ctxs.size();
+  Ctx* c0 = ctxs[0];
+  std::vector<std::unique_lock<std::mutex>> locks;
+  for (Ctx* c : ctxs) locks.emplace_back(c->mu);
+  std::vector<uint8_t> tuples(n * 160), partials(g * 288);
+  std::vector<int> rc(g, 0), bad(g, 0);
+  std::vector<std::string> errs(g);
+  auto run_all = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < g; k++)
+      th.emplace_back([&, k]() {
+        size_t first, cnt;
+        shard_of(n, g, k, first, cnt);
+        DeviceGuard dg(ctxs[k]->device);
+        if (!fn(k, ctxs[k], first, cnt)) { rc[k] = 1; errs[k] = tl_err; }
+      });
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < g; k++)
+      if (rc[k]) { set_err(errs[k]); return false; }
+    return true;
+  };
+  // phase 1 + exchange A
+  if (!run_all([&](size_t k, Ctx* c, size_t first, size_t cnt) -> bool {
+        if (!verify_prepare(c, blobs + first, cs + first, ps + first, cnt)) return false;
+        if (!first_bad_status(c, cnt, bad[k])) return false;
+        CU_TRY(cudaMemcpy(tuples.data() + first * 160, c->vb_tuples.p, cnt * 160, cudaMemcpyDeviceToHost));
+        return true;
+      }))
+    return C_KZG_ERROR;
+  for (size_t k = 0; k < g; k++)
+    if (bad[k]) { for (Ctx* c : ctxs) c->vb_n = 0; set_err("invalid commitment, proof or field element bytes"); return bad_code(bad[k]); }
+  // r on the primary device
+  uint32_t r_host[8];
+  {
+    DeviceGuard dg(c0->device);
+    cudaStream_t s0 = c0->slot[0].st;
+    void* d_all = nullptr;
+    if (cudaMalloc(&d_all, n * 160) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
+    bool good = [&]() -> bool {
+      CU_TRY(cudaMemcpyAsync(d_all, tuples.data(), n * 160, cudaMemcpyHostToDevice, s0));
+      launch_batch_challenge(c0->vb_r.p, d_all, n, s0, c0->mode);
+      CU_TRY(cudaMemcpyAsync(r_host, c0->vb_r.p, 32, cudaMemcpyDeviceToHost, s0));
+      CU_TRY(cudaStreamSynchronize(s0));
+      return true;
+    }();
+    cudaFree(d_all);
+    if (!good) return C_KZG_ERROR;
+  }
+  // phase 2 + exchange B
+  if (!run_all([&](size_t k, Ctx* c, size_t first, size_t cnt) -> bool {
+        cudaStream_t s0 = c->slot[0].st;
+        CU_TRY(cudaMemcpyAsync(c->vb_r.p, r_host, 32, cudaMemcpyHostToDevice, s0));
+        launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, first, (int)cnt, c->vb_scratch.p, s0,
+                              c->slot[0].aux, c->slot[0].ev_fork, c->slot[0].ev_aux);
+        CU_TRY(cudaMemcpyAsync(partials.data() + k * 288, c->vb_partial.p, 288, cudaMemcpyDeviceToHost, s0));
+        CU_TRY(cudaStreamSynchronize(s0));
+        CU_TRY(cudaGetLastError());
+        c->vb_n = 0;
+        return true;
+      }))
+    return C_KZG_ERROR;
+  // phase 3
+  DeviceGuard dg(c0->device);
+  cudaStream_t s0 = c0->slot[0].st;
+  void* d_p = nullptr;
+  if (cudaMalloc(&d_p, g * 288) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
+  int okv = 0;
+  bool good = [&]() -> bool {
+    CU_TRY(cudaMemcpyAsync(d_p, partials.data(), g * 288, cudaMemcpyHostToDevice, s0));
+    launch_batch_final((int*)c0->vb_ok.p, d_p, (int)g, c0->d_prep0, c0->d_prep1, s0);
+    CU_TRY(cudaMemcpyAsync(&okv, c0->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CU_TRY(cudaStreamSynchronize(s0));
+    CU_TRY(cudaGetLastError());
+    return true;
+  }();
+  cudaFree(d_p);
+  if (!good) return C_KZG_ERROR;
+  *ok = okv != 0;
+  return C_KZG_OK;
+}
+
 static C_KZG_RET verify_blob_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
                                    const KZGSettings* s, bool dev_inputs) {
   if (!ok) return C_KZG_ERROR;
@@ -1240,6 +1424,10 @@ static C_KZG_RET verify_blob_batch(bool* ok, const Blob* blobs, const Bytes48* c
   if (n == 1) return verify_blob_single(ok, blobs, commitments_bytes, proofs_bytes, s, dev_inputs);  // lib.rs:544
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
+  if (!dev_inputs) {
+    std::vector<Ctx*> ctxs = ctxs_for(c);
+    if (ctxs.size() > 1 && n >= 2 * ctxs.size()) return verify_blob_batch_multi(ok, blobs, commitments_bytes, proofs_bytes, n, ctxs);
+  }
   CtxLock L(c);
   static const bool trace = getenv("LWKZG_VERIFY_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1281,48 +1469,68 @@ C_KZG_RET lwkzg_verify_blob_kzg_proof_batch_device(bool* ok, const void* d_blobs
   return verify_blob_batch(ok, (const Blob*)d_blobs, (const Bytes48*)d_commitments, (const Bytes48*)d_proofs, n, s, true);
 }
 
-// ---- multi-GPU batched verification phases
-C_KZG_RET lwkzg_verify_batch_phase1(uint8_t* tuples160, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n_local,
-                                    const KZGSettings* s) {
+// ---- multi-GPU batched verification phases (one process per GPU; the caller runs the two all-gathers)
+static C_KZG_RET phase1_impl(uint8_t* tuples_out, bool out_on_device, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs,
+                             size_t n_local, bool inputs_on_device, const KZGSettings* s) {
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
   c->vb_n = 0;
   if (n_local == 0) return C_KZG_OK;
-  if (!verify_prepare(c, blobs, commitments, proofs, n_local)) return C_KZG_ERROR;
+  if (!verify_prepare(c, blobs, commitments, proofs, n_local, false, inputs_on_device)) return C_KZG_ERROR;
   int bad = 0;
   if (!first_bad_status(c, n_local, bad)) return C_KZG_ERROR;
   if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
-  if (cudaMemcpy(tuples160, c->vb_tuples.p, n_local * 160, cudaMemcpyDeviceToHost) != cudaSuccess) { set_err("D2H failed"); return C_KZG_ERROR; }
+  if (cudaMemcpy(tuples_out, c->vb_tuples.p, n_local * 160, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_err("tuple copy failed");
+    return C_KZG_ERROR;
+  }
   return C_KZG_OK;
 }
-
-C_KZG_RET lwkzg_verify_batch_phase2(uint8_t* partial288, const uint8_t* all_tuples160, size_t n_total, size_t first, size_t n_local,
+C_KZG_RET lwkzg_verify_batch_phase1(uint8_t* tuples160, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n_local,
                                     const KZGSettings* s) {
+  return phase1_impl(tuples160, false, blobs, commitments, proofs, n_local, false, s);
+}
+C_KZG_RET lwkzg_verify_batch_phase1_device(void* d_tuples160, const void* blobs, const void* commitments, const void* proofs, size_t n_local,
+                                           int inputs_on_device, const KZGSettings* s) {
+  return phase1_impl((uint8_t*)d_tuples160, true, (const Blob*)blobs, (const Bytes48*)commitments, (const Bytes48*)proofs, n_local,
+                     inputs_on_device != 0, s);
+}
+
+static C_KZG_RET phase2_impl(uint8_t* partial288, const uint8_t* all_tuples160, bool on_device, size_t n_total, size_t first, size_t n_local,
+                             const KZGSettings* s) {
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
   if (c->vb_n != n_local || first + n_local > n_total) { set_err("phase2 does not match the preceding phase1"); return C_KZG_BADARGS; }
   cudaStream_t s0 = c->slot[0].st;
   void* d_all = nullptr;
-  if (cudaMalloc(&d_all, std::max<size_t>(n_total, 1) * 160) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
+  if (!on_device && cudaMalloc(&d_all, std::max<size_t>(n_total, 1) * 160) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
   bool good = [&]() -> bool {
-    CU_TRY(cudaMemcpyAsync(d_all, all_tuples160, n_total * 160, cudaMemcpyHostToDevice, s0));
+    if (!on_device) CU_TRY(cudaMemcpyAsync(d_all, all_tuples160, n_total * 160, cudaMemcpyHostToDevice, s0));
     if (!c->vb_r.ensure(32) || !c->vb_partial.ensure(288) || !c->vb_scratch.ensure(batch_partials_scratch_bytes((int)std::max<size_t>(n_local, 1)))) return false;
-    launch_batch_challenge(c->vb_r.p, d_all, n_total, s0, c->mode);
+    launch_batch_challenge(c->vb_r.p, on_device ? (const void*)all_tuples160 : d_all, n_total, s0, c->mode);
     launch_batch_partials(c->vb_partial.p, c->vb_r.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, first, (int)n_local, c->vb_scratch.p, s0,
                           c->slot[0].aux, c->slot[0].ev_fork, c->slot[0].ev_aux);
-    CU_TRY(cudaMemcpyAsync(partial288, c->vb_partial.p, 288, cudaMemcpyDeviceToHost, s0));
+    CU_TRY(cudaMemcpyAsync(partial288, c->vb_partial.p, 288, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s0));
     CU_TRY(cudaStreamSynchronize(s0));
     CU_TRY(cudaGetLastError());
     return true;
   }();
-  cudaFree(d_all);
+  if (d_all) cudaFree(d_all);
   return good ? C_KZG_OK : C_KZG_ERROR;
 }
+C_KZG_RET lwkzg_verify_batch_phase2(uint8_t* partial288, const uint8_t* all_tuples160, size_t n_total, size_t first, size_t n_local,
+                                    const KZGSettings* s) {
+  return phase2_impl(partial288, all_tuples160, false, n_total, first, n_local, s);
+}
+C_KZG_RET lwkzg_verify_batch_phase2_device(void* d_partial288, const void* d_all_tuples160, size_t n_total, size_t first, size_t n_local,
+                                           const KZGSettings* s) {
+  return phase2_impl((uint8_t*)d_partial288, (const uint8_t*)d_all_tuples160, true, n_total, first, n_local, s);
+}
 
-C_KZG_RET lwkzg_verify_batch_phase3(bool* ok, const uint8_t* partials288, size_t n_ranks, const KZGSettings* s) {
+static C_KZG_RET phase3_impl(bool* ok, const uint8_t* partials288, bool on_device, size_t n_ranks, const KZGSettings* s) {
   if (!ok) return C_KZG_ERROR;
   *ok = false;
   Ctx* c = ctx_of(s);
@@ -1331,21 +1539,50 @@ C_KZG_RET lwkzg_verify_batch_phase3(bool* ok, const uint8_t* partials288, size_t
   if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   cudaStream_t s0 = c->slot[0].st;
   void* d_p = nullptr;
-  if (cudaMalloc(&d_p, std::max<size_t>(n_ranks, 1) * 288) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
+  if (!on_device && cudaMalloc(&d_p, std::max<size_t>(n_ranks, 1) * 288) != cudaSuccess) { set_err("cudaMalloc failed"); return C_KZG_MALLOC; }
   int okv = 0;
   bool good = [&]() -> bool {
     if (!c->vb_ok.ensure(sizeof(int))) return false;
-    CU_TRY(cudaMemcpyAsync(d_p, partials288, n_ranks * 288, cudaMemcpyHostToDevice, s0));
-    launch_batch_final((int*)c->vb_ok.p, d_p, (int)n_ranks, c->d_prep0, c->d_prep1, s0);
+    if (!on_device) CU_TRY(cudaMemcpyAsync(d_p, partials288, n_ranks * 288, cudaMemcpyHostToDevice, s0));
+    launch_batch_final((int*)c->vb_ok.p, on_device ? (const void*)partials288 : d_p, (int)n_ranks, c->d_prep0, c->d_prep1, s0);
     CU_TRY(cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
     CU_TRY(cudaStreamSynchronize(s0));
     CU_TRY(cudaGetLastError());
     return true;
   }();
-  cudaFree(d_p);
+  if (d_p) cudaFree(d_p);
   if (!good) return C_KZG_ERROR;
   *ok = okv != 0;
   return C_KZG_OK;
+}
+C_KZG_RET lwkzg_verify_batch_phase3(bool* ok, const uint8_t* partials288, size_t n_ranks, const KZGSettings* s) {
+  return phase3_impl(ok, partials288, false, n_ranks, s);
+}
+C_KZG_RET lwkzg_verify_batch_phase3_device(bool* ok, const void* d_partials288, size_t n_ranks, const KZGSettings* s) {
+  return phase3_impl(ok, (const uint8_t*)d_partials288, true, n_ranks, s);
+}
+
+// ---- devices: after lwkzg_set_devices(ids, n) the host-buffer batch calls (commit / proof / commit+proof batches,
+// verify_blob_kzg_proof_batch) shard their items over the listed GPUs from this one process
+int lwkzg_set_devices(const int* ids, int n) {
+  int have = 0;
+  if (n < 0 || (n > 0 && !ids) || cudaGetDeviceCount(&have) != cudaSuccess) return 1;
+  std::vector<int> v;
+  for (int i = 0; i < n; i++) {
+    if (ids[i] < 0 || ids[i] >= have) return 1;
+    for (int d : v)
+      if (d == ids[i]) return 1;
+    v.push_back(ids[i]);
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  device_list() = v;
+  return 0;
+}
+int lwkzg_get_devices(int* ids, int cap) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int n = (int)device_list().size();
+  for (int i = 0; i < n && i < cap; i++) ids[i] = device_list()[i];
+  return n;
 }
 
 // ---- measurement hook: the dominant kernel alone, timed with CUDA events on

@@ -14,7 +14,13 @@ utils.rs:166-206):
 
 Group addition is exact, so the boolean is independent of the number of ranks.
 The collectives go through torch.distributed (NCCL over NVLink on the GPU box,
-gloo in the CPU tests).
+gloo in the CPU tests).  On the GPU box the exchanged data never leaves device
+memory: verify_blob_kzg_proof_batch_distributed_device has phase 1 write its
+tuples straight into the all-gather's input tensor (lwkzg_verify_batch_phase*_device).
+
+What bounds one batch spread over many GPUs is not the exchange but r itself: a
+single sequential SHA-256 over all n x 160 tuple bytes (~1 us per 64-byte block on
+one GPU lane).  Independent batches per GPU scale linearly; one batch does not.
 """
 from __future__ import annotations
 
@@ -118,3 +124,45 @@ def verify_blob_kzg_proof_batch_distributed(blobs_local: bytes, commitments_loca
     partial = ph.phase2(all_tuples, n_total, first, n_local) if n_local else bytes(288)
     partials = b"".join(_all_gather_bytes(dist, partial, device))  # exchange B
     return ph.phase3(partials, world)
+
+
+def verify_blob_kzg_proof_batch_distributed_device(blobs_ptr: int, commitments_ptr: int, proofs_ptr: int, n_total: int, settings, *,
+                                                   inputs_on_device: bool, dist=None) -> bool:
+    """The same protocol over NCCL with every exchanged byte in device memory.  blobs / commitments / proofs are raw
+    addresses of THIS rank's contiguous shard (shard_range), in host memory or -- inputs_on_device -- on this rank's GPU.
+    Needs n_total >= 2 (the single-blob path has nothing to shard)."""
+    import torch
+
+    if dist is None:
+        import torch.distributed as dist  # type: ignore
+    assert n_total >= 2
+    world, rank = dist.get_world_size(), dist.get_rank()
+    device = torch.device("cuda", torch.cuda.current_device())
+    first, n_local = shard_range(n_total, world, rank)
+    n_max = shard_range(n_total, world, 0)[1]   # rank 0 holds a largest shard
+    mine = torch.zeros(n_max * 160, dtype=torch.uint8, device=device)
+    err = 0
+    try:
+        if n_local:
+            api.verify_batch_phase1_device(mine.data_ptr(), blobs_ptr, commitments_ptr, proofs_ptr, n_local, settings, inputs_on_device)
+    except api.KzgError as e:
+        err = e.code
+    flag = torch.tensor([err], dtype=torch.int64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag[0]):
+        raise api.KzgError(int(flag[0]), "verify_blob_kzg_proof_batch_distributed_device", "invalid item on some rank")
+    gathered = torch.empty(world * n_max * 160, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, mine)                       # exchange A
+    torch.cuda.current_stream().synchronize()                         # the library's streams do not order after torch's
+    if n_total == world * n_max:
+        all_tuples = gathered
+    else:                                                             # uneven shards: drop the padding
+        parts = [gathered[r * n_max * 160: r * n_max * 160 + shard_range(n_total, world, r)[1] * 160] for r in range(world)]
+        all_tuples = torch.cat(parts)
+    partial = torch.zeros(288, dtype=torch.uint8, device=device)
+    if n_local:
+        api.verify_batch_phase2_device(partial.data_ptr(), all_tuples.data_ptr(), n_total, first, n_local, settings)
+    partials = torch.empty(world * 288, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(partials, partial)                    # exchange B
+    torch.cuda.current_stream().synchronize()
+    return api.verify_batch_phase3_device(partials.data_ptr(), world, settings)
