@@ -335,9 +335,10 @@ def main():
                                    "(burst; best of carry-chain and carry-less variants; profiles/r01_pipe_probe.md). "
                                    "MEASURED_PEAKS.json carries no integer peak; the nominal figure is in peak_nominal",
                     "peak_nominal": IMAD_NOMINAL / 1e12,
-                    "peak_note": "nominal = 148 SM x 64 INT32 lanes x 1.965 GHz (SURVEY 8d) assumes one IMAD.WIDE per lane per clock; the probe "
-                                 "issues IMAD.WIDE at 0.94-1.0 per clock per SM with distinct operands (a 32x32+64 MAC occupies the 16-lane "
-                                 "fmaheavy pipe for four cycles per warp) and 1.99 only when every chain re-uses the same operand registers",
+                    "peak_note": "nominal = 148 SM x 64 INT32 lanes x 1.965 GHz (SURVEY 8d) assumes one IMAD.WIDE per lane per clock; a 32x32+64 MAC "
+                                 "occupies the 16-lane fmaheavy pipe of an SM sub-partition for four cycles per warp whatever feeds it: 0.98 "
+                                 "IMAD.WIDE per clock per SM even with an immediate multiplier and the multiplicand in the operand-reuse cache "
+                                 "(round 1's 1.99 reading was ptxas hoisting the product out of the probe loop: profiles/r02_pipe_probe_imad_wide.md)",
                     "note": "achieved = SURVEY 8(d)'s ALGORITHMIC work (2.80e8 MAC32 per MSM-4096: bucket method, c = 13, XYZZ) / kernel time; "
                             "the kernel needs fewer multiplications than that model (full digit table, GLV, batched-affine additions), so frac may "
                             "exceed 1 -- frac_executed is the pipe-utilisation figure and frac_floor the distance to this algorithm's own minimum",
@@ -374,7 +375,25 @@ def main():
         if world == 1:
             for lg in (12, 14):
                 cpu_pts["2^%d" % lg] = cpu_msm_points_per_s(oracle, lg)
+        # lwkzg_g1_lincomb itself (host buffers in, 48 bytes out): 4096 SRS points x random scalars
+        g1v = settings.g1_values_bytes()
+        be = lambda o: b"".join(g1v[o + 8 * q: o + 8 * q + 8][::-1] for q in range(6))  # noqa: E731  (6 x u64, most significant limb first)
+        pts_be = b"".join(be(144 * i) + be(144 * i + 48) for i in range(4096))
+        sc_be = bytes(blobs[:BLOB_BYTES].cpu().numpy().tobytes())
+        lincomb_ms = {}
+        for key, flag in (("any_curve_points", 0), ("points_in_g1", 1)):
+            lw.set_option("lincomb_points_in_g1", flag)
+            ref_out = lw.g1_lincomb(pts_be, sc_be, 4096)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                assert lw.g1_lincomb(pts_be, sc_be, 4096) == ref_out
+            lincomb_ms[key] = (time.perf_counter() - t0) / 5 * 1e3
+        lw.set_option("lincomb_points_in_g1", 0)
+        assert ref_out == dev_coms[:48], "g1_lincomb(SRS, blob words) must be the blob's commitment"
         msm_sweep = {"sizes": rows, "cpu_g1_lincomb_points_per_s": cpu_pts,
+                     "g1_lincomb_2^12_ms_per_call": lincomb_ms,
+                     "g1_lincomb_note": "lwkzg_g1_lincomb from host buffers, H2D and D2H included; points_in_g1 = the caller vouches for subgroup "
+                                        "membership (GLV split); the sweep itself runs on G1 points (table entries) with the split",
                      "cpu_note": "C restatement of g1_lincomb (unsigned Pippenger, homogeneous projective), one thread, as the reference runs it",
                      "work_model": "SURVEY 8d: min_c ceil(256/c) (10 N + 14 2^c) + 256*9 Fp products of 300 MAC32"}
         # ---- single-call latencies of the c-kzg entry points
@@ -454,11 +473,16 @@ def verify_block(lw, torch, dev, settings, rank, world, dist, barrier, max_over_
     t_pin = timed(lambda: lw.verify_blob_kzg_proof_batch_ptr(pb.data_ptr(), pc.data_ptr(), pp.data_ptr(), nv, settings))
     out["pinned"] = {"ms": t_pin * 1e3, "value": world * nv / t_pin, "h2d_bytes": nv * (BLOB_BYTES + 96)}
     out["corrupted_batch_rejected"] = True
+    out["scaling_note"] = "device_resident / pinned / pageable: every rank verifies its OWN batch of %d blobs (independent batches, weak scaling)" % nv
     out["pairing_ms"] = lw.bench_pairing(settings, 5)   # partial-sum fold + 2-pairing check alone (CUDA events)
     if dist is not None and hasattr(lw, "verify_blob_kzg_proof_batch_distributed_device"):
-        t_dist = timed(lambda: lw.verify_blob_kzg_proof_batch_distributed_device(d_blobs, d_c, d_p, world * nv, settings))
+        t_dist = timed(lambda: lw.verify_blob_kzg_proof_batch_distributed_device(d_blobs.data_ptr(), d_c.data_ptr(), d_p.data_ptr(), world * nv, settings,
+                                                                                 inputs_on_device=True))
         out["distributed"] = {"ms": t_dist * 1e3, "value": world * nv / t_dist, "global_blobs": world * nv,
-                              "note": "ONE batch of world x %d blobs sharded over the ranks; two exchanges (tuples, partial sums) over NCCL" % nv}
+                              "note": "ONE batch of world x %d device-resident blobs sharded over the ranks; two all-gathers (160 B per blob, 288 B per "
+                                      "rank) over NCCL on device tensors.  Bounded by the batch challenge r: one sequential SHA-256 over all "
+                                      "world x %d tuples (~2.5 us per blob on one GPU lane), which no number of GPUs shortens -- the per-GPU "
+                                      "batches above are what scales" % (nv, nv)}
     return out
 
 
