@@ -22,12 +22,15 @@ The JSON line (rank 0):
   msm_sweep     BASELINE config 5: variable-base G1 MSM 2^12 .. 2^22, points/s and roofline fraction per size, next to
                 the CPU restatement's g1_lincomb
   latency       single-call latency of every c-kzg entry point, GPU vs the CPU restatement
+  cells         PeerDAS / EIP-7594 in the mainnet wire format: cells + FK20 cell proofs of 256 blobs (device-resident and
+                through the host API), verify / recover latencies, checked against committed known answers
   cpu_baseline  the C restatement of the reference's CPU path (oracle/c) on a bounded sample of the same workload
 
 --impl reference times that CPU restatement alone (the reference's own Rust code cannot be built here: no cargo,
 un-vendored git dependencies); it never loads the product library.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -48,6 +51,7 @@ IMAD_NOMINAL = 148 * 64 * 1.965e9  # SURVEY §8d sanity ceiling: one IMAD.WIDE p
 METRIC = "blobs/sec commit+proof"
 UNIT = "blobs/s"
 VERIFY_BLOBS = 4096
+CELL_BLOBS = 256          # PeerDAS block: blobs per compute_cells_and_kzg_proofs batch (256 x 128 = 32768 cell proofs)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE 1024-blob launch of msm_gather_ba_kernel from the ncu --set full
 # capture committed as profiles/r02_ncu_ba_staged_1024blob_raw.csv
 NCU_DRAM_BYTES_PER_BLOB = (35.42e9 + 9.33e9) / 1024
@@ -413,6 +417,9 @@ def main():
             gpu_lat[name] = (time.perf_counter() - t0) / 5 * 1e3
         latency = {"unit": "ms per call", "gpu": gpu_lat, "cpu_restatement": cpu_latencies(oracle) if world == 1 else None,
                    "cpu_note": "oracle/c restates commit / proof only (no pairing), one thread: the reference is single-threaded inside a call"}
+    cells = None
+    if rank == 0 and not args.no_extras:
+        cells = cells_block(lw, torch, dev)
     if rank == 0 and world == 1:
         cpu_base, _ = cpu_reference_run(1, 1)
 
@@ -427,11 +434,113 @@ def main():
                         "api": "lwkzg_commit_and_prove_batch (host buffers, pinned)", "pageable_value": e2e_pageable,
                         "pageable_note": "same call from ordinary (pageable) host memory, what a c-kzg caller passes"},
                 "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "roofline": roofline, "verify": verify, "msm_sweep": msm_sweep,
-                "latency": latency, "cpu_baseline": cpu_base}
+                "latency": latency, "cells": cells, "cpu_baseline": cpu_base}
         emit(line)
     settings.free()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def cells_block(lw, torch, dev, n=CELL_BLOBS):
+    """PeerDAS / EIP-7594 (include/lwkzg.h part 3) in the mainnet wire format (MODE_DENEB): cells + FK20 cell
+    proofs of n device-resident blobs, the same through the host API, and the single-call latencies.  Checked against
+    the committed known answers (tests/golden/cell_kats.json, made by the oracle without FK20) and by verifying a
+    sample of the timed outputs with verify_cell_kzg_proof_batch."""
+    import hashlib
+    import random
+
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    lw.set_option("mode", 2)
+    lw.set_option("window_bits", 8)    # the commitment table of these second settings stays small; the FK20 table is the one that matters
+    t0 = time.perf_counter()
+    s = lw.load_trusted_setup_file(SETUP)
+    lw.set_option("mode", 0)
+    try:
+        kat = json.load(open(os.path.join(ROOT, "tests", "golden", "cell_kats.json")))[0]
+        rng = random.Random(kat["seed"])
+        blob = b"".join(rng.randrange(R).to_bytes(32, "big") for _ in range(4096))
+        t1 = time.perf_counter()
+        cs, ps = lw.compute_cells_and_kzg_proofs(blob, s)     # first call: builds the FK20 points and their digit table
+        t_first = time.perf_counter() - t1
+        assert hashlib.sha256(b"".join(cs)).hexdigest() == kat["cells_sha256"], "cells differ from the known answer"
+        assert [ps[i].hex() for i in kat["proof_cells"]] == kat["proofs"], "cell proofs differ from the known answer"
+        com = lw.blob_to_kzg_commitment(blob, s)
+        stream = torch.cuda.current_stream().cuda_stream
+        d_blobs = torch.empty(n * BLOB_BYTES, dtype=torch.uint8, device=dev)
+        lw.synth_blobs_device(d_blobs.data_ptr(), 3 << 20, n, stream)
+        d_cells = torch.zeros(n * 128 * 2048, dtype=torch.uint8, device=dev)
+        d_proofs = torch.zeros(n * 128 * 48, dtype=torch.uint8, device=dev)
+        d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+
+        def dev_ms(cells_ptr, proofs_ptr, reps=3):
+            lw.compute_cells_and_kzg_proofs_batch_device(cells_ptr, proofs_ptr, d_blobs.data_ptr(), n, s, stream, d_st.data_ptr())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                lw.compute_cells_and_kzg_proofs_batch_device(cells_ptr, proofs_ptr, d_blobs.data_ptr(), n, s, stream, d_st.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms_both = dev_ms(d_cells.data_ptr(), d_proofs.data_ptr())
+        ms_cells = dev_ms(d_cells.data_ptr(), 0)
+        assert int(d_st.abs().sum()) == 0
+        # host API, pinned buffers
+        hb = d_blobs.cpu().pin_memory()
+        hc = torch.zeros(n * 128 * 2048, dtype=torch.uint8).pin_memory()
+        hp = torch.zeros(n * 128 * 48, dtype=torch.uint8).pin_memory()
+        lib = lw.load_library()
+        st = (ctypes.c_int * n)()
+        host_call = lambda: lib.lwkzg_compute_cells_and_kzg_proofs_batch(hc.data_ptr(), hp.data_ptr(), hb.data_ptr(), n, s.ptr, st)  # noqa: E731
+        assert host_call() == 0
+        t2 = time.perf_counter()
+        assert host_call() == 0
+        ms_host = (time.perf_counter() - t2) * 1e3
+        assert bytes(hp.numpy()) == bytes(d_proofs.cpu().numpy()) and bytes(hc.numpy()) == bytes(d_cells.cpu().numpy())
+        # a sample of the timed outputs verifies in one batched check over n commitments; a swapped proof does not
+        d_c = torch.zeros(n * 48, dtype=torch.uint8, device=dev)
+        lw.blob_to_kzg_commitment_batch_device(d_c.data_ptr(), d_blobs.data_ptr(), n, s, stream, d_st.data_ptr())
+        torch.cuda.synchronize()
+        coms = bytes(d_c.cpu().numpy())
+        cells_b, proofs_b = bytes(hc.numpy()), bytes(hp.numpy())
+        rng = random.Random(1)
+        pick = [(b, rng.randrange(128)) for b in range(n) for _ in range(2)]
+        v_args = ([coms[48 * b: 48 * b + 48] for b, _ in pick], [i for _, i in pick],
+                  [cells_b[(b * 128 + i) * 2048: (b * 128 + i + 1) * 2048] for b, i in pick],
+                  [proofs_b[(b * 128 + i) * 48: (b * 128 + i + 1) * 48] for b, i in pick])
+        assert lw.verify_cell_kzg_proof_batch(*v_args, s) is True
+        swapped = list(v_args[3])
+        swapped[0], swapped[1] = swapped[1], swapped[0]
+        assert lw.verify_cell_kzg_proof_batch(v_args[0], v_args[1], v_args[2], swapped, s) is False
+
+        def lat(fn, reps=3):
+            fn()
+            t = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t) / reps * 1e3
+
+        keep = list(range(0, 128, 2))
+        latency = {
+            "compute_cells_and_kzg_proofs": lat(lambda: lw.compute_cells_and_kzg_proofs(blob, s)),
+            "compute_cells_only": lat(lambda: lw.compute_cells_and_kzg_proofs(blob, s, want_proofs=False)),
+            "recover_cells_and_kzg_proofs_64_of_128": lat(lambda: lw.recover_cells_and_kzg_proofs(keep, [cs[i] for i in keep], s)),
+            "verify_cell_kzg_proof_batch_128_cells_1_blob": lat(lambda: lw.verify_cell_kzg_proof_batch([com] * 128, list(range(128)), cs, ps, s)),
+            "verify_cell_kzg_proof_batch_%d_cells_%d_blobs" % (len(pick), n): lat(lambda: lw.verify_cell_kzg_proof_batch(*v_args, s), reps=2),
+        }
+        return {"mode": "MODE_DENEB (mainnet wire format)", "blobs": n, "fk20_window_bits": lw.cell_window_bits(s),
+                "setup_s": {"load_trusted_setup (Lagrange SRS + 8-bit commitment table)": t1 - t0, "first cell call (FK20 points + digit table)": t_first},
+                "device_resident": {"cells_and_proofs_ms": ms_both, "cells_only_ms": ms_cells, "blobs_per_s": n / (ms_both * 1e-3),
+                                    "cell_proofs_per_s": n * 128 / (ms_both * 1e-3)},
+                "host_pinned": {"ms": ms_host, "blobs_per_s": n / (ms_host * 1e-3), "h2d_bytes": n * BLOB_BYTES, "d2h_bytes": n * 128 * (2048 + 48)},
+                "latency_ms": latency,
+                "parity": "known answers of tests/golden/cell_kats.json (oracle/py/cells.py, proofs computed without FK20); %d sampled cells of the timed "
+                          "batch verify together and fail with two proofs swapped; host API bytes == device API bytes" % len(pick),
+                "cpu_note": "no CPU figure: the reference implements no cell path (src/srs.rs:274 reads 2 of its 65 G2 points)"}
+    finally:
+        s.free()
+        lw.set_option("window_bits", 16)
 
 
 def verify_block(lw, torch, dev, settings, rank, world, dist, barrier, max_over_ranks):

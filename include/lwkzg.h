@@ -212,6 +212,49 @@ C_KZG_RET lwkzg_verify_batch_phase3_device(bool *ok, const void *d_partials288, 
 int lwkzg_set_devices(const int *ids, int n);
 int lwkzg_get_devices(int *ids, int cap);
 
+/* ------------------------------------------------------------------ Part 3 */
+/* PeerDAS / EIP-7594 cells and cell proofs.  The reference stops before this: it loads the 65 G2
+ * points such a path needs but only ever reads two (src/srs.rs:274; constants at src/lib.rs:60-92), and it has no
+ * G1 FFT.  Names, argument order and error behaviour are c-kzg-4844's eip7594 API (the header the reference's
+ * src/c_kzg_4844.h:85-231 grew into); semantics are consensus-specs fulu/polynomial-commitments-sampling.md, restated
+ * in oracle/py/cells.py.  The calls follow the mode of the settings: in the Lagrange modes (1, 2) a blob is the
+ * evaluation form and cells 0..63 of its extension are the blob itself; in MODE_REFERENCE a blob is 4096 big-endian
+ * coefficients reduced mod r (src/utils.rs:27-41) and all 128 cells are computed.  Field elements inside a Cell use
+ * the mode's byte order (big-endian except in MODE_CKZG_LE).  The settings must come from load_trusted_setup[_file]
+ * (the Lagrange modes keep the monomial points the loader saw); hand-built Lagrange settings get C_KZG_ERROR. */
+#define FIELD_ELEMENTS_PER_EXT_BLOB (2 * FIELD_ELEMENTS_PER_BLOB)
+#define FIELD_ELEMENTS_PER_CELL 64
+#define BYTES_PER_CELL (FIELD_ELEMENTS_PER_CELL * BYTES_PER_FIELD_ELEMENT)
+#define CELLS_PER_EXT_BLOB (FIELD_ELEMENTS_PER_EXT_BLOB / FIELD_ELEMENTS_PER_CELL)
+typedef struct { uint8_t bytes[BYTES_PER_CELL]; } Cell;
+
+/* cells: CELLS_PER_EXT_BLOB cells or NULL; proofs: CELLS_PER_EXT_BLOB proofs or NULL (not both NULL).
+ * Proofs are FK20 multiproofs: 128 fixed-base MSMs of 64 points over a digit table of the 8192 transformed SRS
+ * points (built on the first call; "cell_window_bits"), one inverse and one forward G1 FFT of size 128. */
+C_KZG_RET compute_cells_and_kzg_proofs(Cell *cells, KZGProof *proofs, const Blob *blob, const KZGSettings *s);
+/* num_cells in [64, 128], cell_indices strictly ascending and < 128; either output may be NULL */
+C_KZG_RET recover_cells_and_kzg_proofs(Cell *recovered_cells, KZGProof *recovered_proofs, const uint64_t *cell_indices,
+                                       const Cell *cells, size_t num_cells, const KZGSettings *s);
+/* one commitment per cell (repeats allowed, deduplicated as the spec does); num_cells = 0 verifies */
+C_KZG_RET verify_cell_kzg_proof_batch(bool *ok, const Bytes48 *commitments_bytes, const uint64_t *cell_indices,
+                                      const Cell *cells, const Bytes48 *proofs_bytes, size_t num_cells,
+                                      const KZGSettings *s);
+/* additive: n blobs per call (cells: n x 128, proofs: n x 128, either may be NULL); status[n] per blob, may be NULL */
+C_KZG_RET lwkzg_compute_cells_and_kzg_proofs_batch(Cell *cells, KZGProof *proofs, const Blob *blobs, size_t n,
+                                                   const KZGSettings *s, int *status);
+/* the same on device buffers (16-byte aligned), ordered after / before work on `stream`; outputs of failed items
+ * are zeroed; d_status (n ints) may be NULL */
+C_KZG_RET lwkzg_compute_cells_and_kzg_proofs_batch_device(void *d_cells, void *d_proofs, const void *d_blobs, size_t n,
+                                                          const KZGSettings *s, void *stream, void *d_status);
+/* Test hook: intermediate values of the FK20 pipeline for one blob, so a parity test can name the stage that deviates:
+ * scalars = the 8192 MSM scalars DFT_128(circulant column b)_j / 128 as 32-byte little-endian integers, index j * 64 + b;
+ * hhat48 = the 128 MSM results (compressed, natural j); h48 = after the inverse G1 FFT (compressed; position p holds
+ * H_brp7(p), odd positions infinity); fk20_xy96 = the 8192 FK20 points X[j * 64 + b] as canonical little-endian x || y. */
+C_KZG_RET lwkzg_debug_cell_stages(uint8_t *scalars, uint8_t *hhat48, uint8_t *h48, uint8_t *fk20_xy96, const Blob *blob,
+                                  const KZGSettings *s);
+/* window of the FK20 digit table in use (-1 before the first cell call) */
+int lwkzg_cell_window_bits(const KZGSettings *s);
+
 /* Synthetic blobs: word i of blob k = four big-endian u64 from
  * SplitMix64 seeded with 0xB2004844 ^ (k*4096+i), byte[0] &= 0x3f.  Written
  * straight into device memory so large batches never cross PCIe. */
@@ -269,7 +312,9 @@ int lwkzg_window_bits(const KZGSettings *s);
  * be128(4096) || blob || commitment, batch challenge domain || be64(4096) || be64(n) || tuples, digests read
  * big-endian).  The mode is captured when a KZGSettings is
  * loaded / first used.  Env: LWKZG_WINDOW_BITS, LWKZG_CHUNK_BLOBS, LWKZG_MODE,
- * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS.
+ * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS.  Cells: "cell_window_bits" (window of the FK20 digit table over 8192
+ * points, 4..14, default 13 = 29 GiB, shrunk to what free device memory allows), "cell_chunk_blobs" (blobs per
+ * pass of a cell batch, default 1024).
  * Returns 0 on success. */
 int lwkzg_set_option(const char *name, long value);
 long lwkzg_get_option(const char *name);

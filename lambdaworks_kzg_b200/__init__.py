@@ -60,5 +60,12 @@ from .api import (  # noqa: F401
     blob_to_kzg_commitment_batch_device,
     compute_blob_kzg_proof_batch_device,
     verify_kzg_proof,
+    compute_cells_and_kzg_proofs,
+    compute_cells_and_kzg_proofs_batch,
+    compute_cells_and_kzg_proofs_batch_device,
+    recover_cells_and_kzg_proofs,
+    verify_cell_kzg_proof_batch,
+    cell_window_bits,
+    debug_cell_stages,
 )
 from .sharding import shard_range, verify_blob_kzg_proof_batch_distributed, verify_blob_kzg_proof_batch_distributed_device  # noqa: F401

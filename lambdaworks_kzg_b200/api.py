@@ -77,6 +77,13 @@ def load_library() -> ctypes.CDLL:
         "lwkzg_debug_batch_challenge": [vp, sp],
         "lwkzg_synth_blobs_device": [vp, ctypes.c_uint64, sz, vp],
         "lwkzg_synth_blob_host": [vp, ctypes.c_uint64],
+        "compute_cells_and_kzg_proofs": [vp, vp, vp, sp],
+        "recover_cells_and_kzg_proofs": [vp, vp, vp, vp, sz, sp],
+        "verify_cell_kzg_proof_batch": [bp, vp, vp, vp, vp, sz, sp],
+        "lwkzg_compute_cells_and_kzg_proofs_batch": [vp, vp, vp, sz, sp, ip],
+        "lwkzg_compute_cells_and_kzg_proofs_batch_device": [vp, vp, vp, sz, sp, vp, vp],
+        "lwkzg_cell_window_bits": [sp],
+        "lwkzg_debug_cell_stages": [vp, vp, vp, vp, vp, sp],
         "lwkzg_set_option": [ctypes.c_char_p, ctypes.c_long],
         "lwkzg_get_option": [ctypes.c_char_p],
     }
@@ -452,3 +459,77 @@ def verify_batch_phase3(partials: bytes, n_ranks: int, s) -> bool:
     ok = ctypes.c_bool(False)
     _check(load_library().lwkzg_verify_batch_phase3(ctypes.byref(ok), partials, n_ranks, _sp(s)), "lwkzg_verify_batch_phase3")
     return bool(ok.value)
+
+
+# ------------------------------------------------------------------ PeerDAS / EIP-7594 cells (include/lwkzg.h part 3)
+CELLS_PER_EXT_BLOB = 128
+BYTES_PER_CELL = 2048
+
+
+def compute_cells_and_kzg_proofs(blob: bytes, s, want_cells: bool = True, want_proofs: bool = True) -> Tuple[List[bytes], List[bytes]]:
+    """compute_cells_and_kzg_proofs of c-kzg-4844's eip7594 API: 128 cells and / or 128 proofs of one blob."""
+    assert len(blob) == BYTES_PER_BLOB
+    cells = ctypes.create_string_buffer(CELLS_PER_EXT_BLOB * BYTES_PER_CELL) if want_cells else None
+    proofs = ctypes.create_string_buffer(CELLS_PER_EXT_BLOB * 48) if want_proofs else None
+    _check(load_library().compute_cells_and_kzg_proofs(cells, proofs, blob, _sp(s)), "compute_cells_and_kzg_proofs")
+    cl = [cells.raw[i * BYTES_PER_CELL: (i + 1) * BYTES_PER_CELL] for i in range(CELLS_PER_EXT_BLOB)] if want_cells else []
+    pl = [proofs.raw[i * 48: (i + 1) * 48] for i in range(CELLS_PER_EXT_BLOB)] if want_proofs else []
+    return cl, pl
+
+
+def compute_cells_and_kzg_proofs_batch(blobs: bytes, n: int, s, want_cells: bool = True, want_proofs: bool = True):
+    """-> (cells bytes n x 128 x 2048 or b"", proofs bytes n x 128 x 48 or b"", status list)."""
+    assert len(blobs) == n * BYTES_PER_BLOB
+    cells = ctypes.create_string_buffer(max(1, n * CELLS_PER_EXT_BLOB * BYTES_PER_CELL)) if want_cells else None
+    proofs = ctypes.create_string_buffer(max(1, n * CELLS_PER_EXT_BLOB * 48)) if want_proofs else None
+    st = (ctypes.c_int * max(1, n))()
+    _check(load_library().lwkzg_compute_cells_and_kzg_proofs_batch(cells, proofs, blobs, n, _sp(s), st), "lwkzg_compute_cells_and_kzg_proofs_batch")
+    return (cells.raw[: n * CELLS_PER_EXT_BLOB * BYTES_PER_CELL] if want_cells else b"", proofs.raw[: n * CELLS_PER_EXT_BLOB * 48] if want_proofs else b"",
+            list(st)[:n])
+
+
+def compute_cells_and_kzg_proofs_batch_device(d_cells: int, d_proofs: int, d_blobs: int, n: int, s, stream: int = 0, d_status: int = 0):
+    """Device-pointer variant: raw device addresses (0 = not wanted), asynchronous with respect to the host."""
+    _check(load_library().lwkzg_compute_cells_and_kzg_proofs_batch_device(d_cells or None, d_proofs or None, d_blobs, n, _sp(s), stream or None,
+                                                                          d_status or None), "lwkzg_compute_cells_and_kzg_proofs_batch_device")
+
+
+def recover_cells_and_kzg_proofs(cell_indices: Sequence[int], cells: Sequence[bytes], s, want_cells: bool = True, want_proofs: bool = True):
+    n = len(cell_indices)
+    idx = (ctypes.c_uint64 * max(1, n))(*cell_indices)
+    rc = ctypes.create_string_buffer(CELLS_PER_EXT_BLOB * BYTES_PER_CELL) if want_cells else None
+    rp = ctypes.create_string_buffer(CELLS_PER_EXT_BLOB * 48) if want_proofs else None
+    _check(load_library().recover_cells_and_kzg_proofs(rc, rp, idx, _cat(cells, BYTES_PER_CELL), n, _sp(s)), "recover_cells_and_kzg_proofs")
+    cl = [rc.raw[i * BYTES_PER_CELL: (i + 1) * BYTES_PER_CELL] for i in range(CELLS_PER_EXT_BLOB)] if want_cells else []
+    pl = [rp.raw[i * 48: (i + 1) * 48] for i in range(CELLS_PER_EXT_BLOB)] if want_proofs else []
+    return cl, pl
+
+
+def verify_cell_kzg_proof_batch(commitments: Sequence[bytes], cell_indices: Sequence[int], cells: Sequence[bytes], proofs: Sequence[bytes], s) -> bool:
+    n = len(cell_indices)
+    assert len(commitments) == len(cells) == len(proofs) == n
+    idx = (ctypes.c_uint64 * max(1, n))(*cell_indices)
+    ok = ctypes.c_bool(False)
+    _check(load_library().verify_cell_kzg_proof_batch(ctypes.byref(ok), _cat(commitments, 48) or b"\0", idx, _cat(cells, BYTES_PER_CELL) or b"\0",
+                                                      _cat(proofs, 48) or b"\0", n, _sp(s)), "verify_cell_kzg_proof_batch")
+    return bool(ok.value)
+
+
+def cell_window_bits(s) -> int:
+    return int(load_library().lwkzg_cell_window_bits(_sp(s)))
+
+
+def debug_cell_stages(blob: bytes, s):
+    """-> (scalars [j][b] as ints, Hhat_j compressed, H positions compressed, FK20 points as (x, y) ints or None)."""
+    sc = ctypes.create_string_buffer(8192 * 32)
+    hh = ctypes.create_string_buffer(128 * 48)
+    h = ctypes.create_string_buffer(128 * 48)
+    fk = ctypes.create_string_buffer(8192 * 96)
+    _check(load_library().lwkzg_debug_cell_stages(sc, hh, h, fk, blob, _sp(s)), "lwkzg_debug_cell_stages")
+    scalars = [int.from_bytes(sc.raw[32 * i: 32 * i + 32], "little") for i in range(8192)]
+    pts = []
+    for i in range(8192):
+        x = int.from_bytes(fk.raw[96 * i: 96 * i + 48], "little")
+        y = int.from_bytes(fk.raw[96 * i + 48: 96 * i + 96], "little")
+        pts.append(None if x == 0 and y == 0 else (x, y))
+    return scalars, [hh.raw[48 * i: 48 * i + 48] for i in range(128)], [h.raw[48 * i: 48 * i + 48] for i in range(128)], pts

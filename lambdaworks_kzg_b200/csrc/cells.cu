@@ -1,0 +1,427 @@
+// PeerDAS / EIP-7594 cells and FK20 cell proofs.
+//
+// The reference stops before this: it loads all 65 G2 points of the trusted setup but only ever reads two
+// (/root/reference/src/srs.rs:274; constants at src/lib.rs:60-92) and has no G1 FFT.  What is computed here follows
+// consensus-specs `specs/fulu/polynomial-commitments-sampling.md`, restated in oracle/py/cells.py:
+//
+//   cells   : p in coefficient form (inverse FFT of the blob), evaluated on the 8192-point domain; cell i = the 64
+//             evaluations on the coset h_i <w64>, h_i = w8192^brp7(i).  The even half of the domain IS the blob, so
+//             only the odd half -- one 4096-point FFT of f_n w8192^n -- is computed.
+//   proofs  : pi_i = [ (p - I_i)(tau) / (tau^64 - h_i^64) ] G for all 128 cosets at once (Feist-Khovratovich):
+//             with l = 64, H_t = sum_k f_(k + 64 (t + 1)) [tau^k]G (t < 63) and  pi = DFT_128(H, 0 ...)  in
+//             natural order of the coset shifts w8192^m.  The H_t are 64 upper-triangular Toeplitz products (one per
+//             offset b = k mod 64), each embedded in a circulant of size 128:
+//                 Hhat_j = sum_b DFT_128(c^b)_j * X^b_j ,   X^b = DFT_128(s_(64 (62 - v) + b))_v   (fixed, set-up time)
+//             i.e. per blob 64 scalar FFTs of size 128, ONE fixed-base MSM per frequency j over 64 points (128 MSMs,
+//             8192 points in all, served by a GLV digit table exactly like the commitment MSM's), one inverse and one
+//             forward G1 FFT of size 128.
+//
+// B200 mapping: the scalar FFTs run out of shared memory (a blob's 4096 coefficients = 128 KB, limb-major so that a
+// warp's accesses are conflict-free); the MSM is one warp per (blob, frequency) gathering table entries; the G1 FFTs
+// are batched ACROSS blobs -- a warp holds the same butterfly of 32 different blobs, so the twiddle (a fixed 128th
+// root of unity, recoded once into signed digits of its two GLV halves) drives a warp-uniform double-and-add ladder.
+#include "kernels_cells.h"
+#include "msm_common.cuh"
+
+namespace lw {
+
+namespace {
+
+__device__ __forceinline__ Fr fr_const(const uint32_t* c) { Fr r; for (int i = 0; i < 8; i++) r.l[i] = c[i]; return r; }
+__device__ __forceinline__ Fp fp_beta() { Fp b; for (int i = 0; i < 12; i++) b.l[i] = k::FP_BETA[i]; return b; }
+__device__ __forceinline__ uint32_t brp7(uint32_t i) { return __brev(i) >> 25; }
+__device__ __forceinline__ Fr fr_pow_small(Fr base, uint32_t e) {
+  Fr acc = fr_one();
+  for (int bit = 31; bit >= 0; bit--) {
+    acc = fr_sqr(acc);
+    if ((e >> bit) & 1u) acc = fr_mul(acc, base);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------ setup
+__global__ void cell_twiddles_kernel(Fr* __restrict__ tw) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < EXT_POINTS) tw[i] = fr_pow_small(fr_const(k::FR_ROOT_8192), i);
+}
+
+// Signed-digit (non-adjacent form) recoding of the GLV halves of the 128th roots of unity nu^e, nu = w8192^64:
+// [nu^e]P = [m]P + [q](beta x, -y).  Layout per e: m+ | m- | q+ | q-, 5 words (160 bits) each.
+__global__ void cell_twiddle_naf_kernel(uint32_t* __restrict__ naf) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 128) return;
+  Fr w = fr_from_mont(fr_pow_small(fr_const(k::FR_ROOT_8192), 64u * e));
+  uint32_t q[4], m[4];
+  glv_split(q, m, w.l);
+  for (int half = 0; half < 2; half++) {
+    uint32_t kk[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) kk[i] = half ? q[i] : m[i];
+    uint32_t pos[5] = {0, 0, 0, 0, 0}, neg[5] = {0, 0, 0, 0, 0};
+    for (int bit = 0; bit < 160; bit++) {
+      if (kk[0] & 1u) {
+        if ((kk[0] & 3u) == 1u) {            // digit +1: k -= 1
+          pos[bit >> 5] |= 1u << (bit & 31);
+          kk[0] &= ~1u;
+        } else {                             // digit -1: k += 1
+          neg[bit >> 5] |= 1u << (bit & 31);
+          uint32_t carry = 1;
+          for (int i = 0; i < 5 && carry; i++) { kk[i] += carry; carry = kk[i] == 0 ? 1u : 0u; }
+        }
+      }
+      for (int i = 0; i < 4; i++) kk[i] = (kk[i] >> 1) | (kk[i + 1] << 31);
+      kk[4] >>= 1;
+    }
+    uint32_t* out = naf + (size_t)e * CELL_NAF_WORDS + half * 10;
+    for (int i = 0; i < 5; i++) { out[i] = pos[i]; out[5 + i] = neg[i]; }
+  }
+}
+
+__global__ void cell_srs_columns_kernel(G1Xyzz* __restrict__ pts, const G1Affine* __restrict__ srs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= EXT_POINTS) return;
+  const int v = t / 64, b = t % 64;
+  pts[t] = v <= 62 ? xyzz_from_affine(srs[64 * (62 - v) + b]) : xyzz_inf();
+}
+
+__global__ void cell_fk20_points_kernel(G1Affine* __restrict__ out, const G1Xyzz* __restrict__ pts) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= EXT_POINTS) return;
+  const int j = t / 64, b = t % 64;
+  out[t] = xyzz_to_affine(pts[brp7(j) * 64 + b]);
+}
+
+// ------------------------------------------------------------------ G1 FFT stage
+// [nu^e] T by the recoded digits (warp-uniform: every lane of a warp has the same e)
+LW_COLD G1Xyzz g1_mul_root(const G1Xyzz& t, const uint32_t* __restrict__ naf_e) {
+  G1Xyzz acc = xyzz_inf();
+  if (!xyzz_is_inf(t)) {
+    const G1Affine a = xyzz_to_affine(t);
+    G1Affine a2;
+    a2.x = fp_mul(a.x, fp_beta());
+    a2.y = fp_neg(a.y);
+    const G1Affine an = g1a_neg(a), a2n = g1a_neg(a2);
+    int top = 159;
+    while (top > 0) {
+      const int w = top >> 5, s = top & 31;
+      if (((naf_e[w] | naf_e[5 + w] | naf_e[10 + w] | naf_e[15 + w]) >> s) & 1u) break;
+      top--;
+    }
+    for (int bit = top; bit >= 0; bit--) {
+      const int w = bit >> 5, s = bit & 31;
+      xyzz_dbl_ni(acc);
+      if ((naf_e[w] >> s) & 1u) xyzz_madd_ni(acc, a);
+      if ((naf_e[5 + w] >> s) & 1u) xyzz_madd_ni(acc, an);
+      if ((naf_e[10 + w] >> s) & 1u) xyzz_madd_ni(acc, a2);
+      if ((naf_e[15 + w] >> s) & 1u) xyzz_madd_ni(acc, a2n);
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(64) cell_g1_fft_stage_kernel(G1Xyzz* __restrict__ pts, int batch, int batch_pad, int half, int dif, int inverse,
+                                                              int upper_half_zero, const uint32_t* __restrict__ naf) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = (int)(gt % batch_pad), bf = (int)(gt / batch_pad);
+  if (bf >= 64 || item >= batch) return;
+  const int j = bf & (half - 1);
+  const int i0 = ((bf - j) << 1) + j, i1 = i0 + half;
+  int e = j * (64 / half);
+  if (inverse) e = (128 - e) & 127;
+  G1Xyzz* p0 = pts + (size_t)i0 * batch + item;
+  G1Xyzz* p1 = pts + (size_t)i1 * batch + item;
+  if (dif) {
+    // (P, Q) -> (P + Q, [w](P - Q)).  upper_half_zero on the last stage: the odd outputs are H_t, t >= 64, which the
+    // caller discards -- they are written as infinity instead of being computed
+    G1Xyzz P = *p0, Q = *p1;
+    G1Xyzz s = P;
+    xyzz_add_ni(s, Q);
+    *p0 = s;
+    if (upper_half_zero && half == 1) {
+      *p1 = xyzz_inf();
+    } else {
+      G1Xyzz d = P;
+      xyzz_add_ni(d, xyzz_neg(Q));
+      *p1 = e ? g1_mul_root(d, naf + (size_t)e * CELL_NAF_WORDS) : d;
+    }
+  } else {
+    // (P, Q) -> (P + [w]Q, P - [w]Q)
+    G1Xyzz P = *p0, Q = *p1;
+    G1Xyzz t = e ? g1_mul_root(Q, naf + (size_t)e * CELL_NAF_WORDS) : Q;
+    G1Xyzz s = P;
+    xyzz_add_ni(s, t);
+    *p0 = s;
+    G1Xyzz d = P;
+    xyzz_add_ni(d, xyzz_neg(t));
+    *p1 = d;
+  }
+}
+
+// ------------------------------------------------------------------ scalar FFTs in shared memory
+// limb-major: limb l of element i at sm[l * N + i]
+template <int N>
+__device__ __forceinline__ Fr sm_load(const uint32_t* sm, int i) {
+  Fr r;
+#pragma unroll
+  for (int l = 0; l < 8; l++) r.l[l] = sm[l * N + i];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ void sm_store(uint32_t* sm, int i, const Fr& v) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) sm[l * N + i] = v.l[l];
+}
+
+// bit-reversed in -> natural out, inverse twiddles, unscaled.  tw = powers of w8192; the N-th root is w8192^(8192/N)
+template <int N>
+__device__ void sm_dit_inverse(uint32_t* sm, const Fr* __restrict__ tw) {
+  for (int half = 1; half < N; half <<= 1) {
+    const int step = (EXT_POINTS / 2) / half;   // exponent of w8192 per unit j: 8192 / (2 half)
+    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+      const int j = t & (half - 1);
+      const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+      Fr u = sm_load<N>(sm, i0), v = sm_load<N>(sm, i1);
+      if (j) v = fr_mul(v, tw[(EXT_POINTS - step * j) & (EXT_POINTS - 1)]);
+      sm_store<N>(sm, i0, fr_add(u, v));
+      sm_store<N>(sm, i1, fr_sub(u, v));
+    }
+    __syncthreads();
+  }
+}
+// natural in -> bit-reversed out, forward twiddles
+template <int N>
+__device__ void sm_dif_forward(uint32_t* sm, const Fr* __restrict__ tw) {
+  for (int half = N / 2; half >= 1; half >>= 1) {
+    const int step = (EXT_POINTS / 2) / half;
+    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+      const int j = t & (half - 1);
+      const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+      Fr u = sm_load<N>(sm, i0), v = sm_load<N>(sm, i1);
+      sm_store<N>(sm, i0, fr_add(u, v));
+      Fr d = fr_sub(u, v);
+      if (j) d = fr_mul(d, tw[step * j]);
+      sm_store<N>(sm, i1, d);
+    }
+    __syncthreads();
+  }
+}
+
+// 32 bytes of a blob / cell <-> canonical field element in the mode's byte order (mode 1: little-endian)
+__device__ __forceinline__ Fr fr_from_wire(const uint8_t* p, int mode) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  Fr r;
+  if (mode == 1) {
+    for (int i = 0; i < 8; i++) r.l[i] = w[i];
+    mod_reduce_small<FrCfg, 2>(r.l);
+  } else {
+    r = fr_canon_from_be_words(w);
+  }
+  return r;
+}
+__device__ __forceinline__ void fr_to_wire(uint8_t* p, const Fr& canon, int mode) {
+  uint4 a, b;
+  if (mode == 1) {
+    a = make_uint4(canon.l[0], canon.l[1], canon.l[2], canon.l[3]);
+    b = make_uint4(canon.l[4], canon.l[5], canon.l[6], canon.l[7]);
+  } else {
+    a = make_uint4(bswap32(canon.l[7]), bswap32(canon.l[6]), bswap32(canon.l[5]), bswap32(canon.l[4]));
+    b = make_uint4(bswap32(canon.l[3]), bswap32(canon.l[2]), bswap32(canon.l[1]), bswap32(canon.l[0]));
+  }
+  reinterpret_cast<uint4*>(p)[0] = a;
+  reinterpret_cast<uint4*>(p)[1] = b;
+}
+
+constexpr int POLY_THREADS = 512;
+constexpr int POLY_SMEM = N_POINTS * 32;
+
+// One block per blob.  from_blob: parse the blob (and turn evaluations into coefficients in the Lagrange modes),
+// write the coefficient form; else read it from d_coef.  Then, if cells are wanted, the extended evaluations.
+__global__ void __launch_bounds__(POLY_THREADS) cell_poly_kernel(Fr* __restrict__ coef, uint8_t* __restrict__ cells, const uint8_t* __restrict__ blobs,
+                                                               int mode, int from_blob, const Fr* __restrict__ tw) {
+  extern __shared__ uint32_t sm[];
+  const int blob = blockIdx.x;
+  Fr* cf = coef + (size_t)blob * N_POINTS;
+  uint8_t* out = cells ? cells + (size_t)blob * N_CELLS * CELL_BYTES : nullptr;
+  const bool evals_in = from_blob && mode != 0;
+  if (from_blob) {
+    const uint8_t* src = blobs + (size_t)blob * BLOB_BYTES;
+    for (int i = threadIdx.x; i < N_POINTS; i += blockDim.x) sm_store<N_POINTS>(sm, i, fr_to_mont(fr_from_wire(src + (size_t)i * 32, mode)));
+    __syncthreads();
+    if (evals_in) {
+      sm_dit_inverse<N_POINTS>(sm, tw);
+      const Fr ninv = fr_const(k::FR_N_INV);
+      for (int i = threadIdx.x; i < N_POINTS; i += blockDim.x) cf[i] = fr_mul(sm_load<N_POINTS>(sm, i), ninv);
+    } else {
+      for (int i = threadIdx.x; i < N_POINTS; i += blockDim.x) cf[i] = sm_load<N_POINTS>(sm, i);
+    }
+    __syncthreads();   // cf is re-read below by other threads of this block
+  }
+  if (!out) return;
+  // first half of the extended blob: p on the 4096th roots of unity in bit-reversed order
+  if (evals_in) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(blobs + (size_t)blob * BLOB_BYTES);
+    uint4* d4 = reinterpret_cast<uint4*>(out);
+    for (int i = threadIdx.x; i < BLOB_BYTES / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = threadIdx.x; i < N_POINTS; i += blockDim.x) sm_store<N_POINTS>(sm, i, cf[i]);
+    __syncthreads();
+    sm_dif_forward<N_POINTS>(sm, tw);
+    for (int i = threadIdx.x; i < N_POINTS; i += blockDim.x) fr_to_wire(out + (size_t)i * 32, fr_from_mont(sm_load<N_POINTS>(sm, i)), mode);
+    __syncthreads();
+  }
+  // second half: p on w8192 * (the same roots)
+  for (int i = threadIdx.x; i < N_POINTS; i += blockDim.x) sm_store<N_POINTS>(sm, i, fr_mul(cf[i], tw[i]));
+  __syncthreads();
+  sm_dif_forward<N_POINTS>(sm, tw);
+  for (int i = threadIdx.x; i < N_POINTS; i += blockDim.x)
+    fr_to_wire(out + (size_t)(N_POINTS + i) * 32, fr_from_mont(sm_load<N_POINTS>(sm, i)), mode);
+}
+
+// FK20 scalars.  Block = 4 offsets b x 64 threads; grid (16, n_blobs).
+constexpr int TOEP_COLS = 4;
+__global__ void __launch_bounds__(64 * TOEP_COLS) cell_toeplitz_kernel(uint32_t* __restrict__ scalars, const Fr* __restrict__ coef, const Fr* __restrict__ tw) {
+  __shared__ uint32_t smem[TOEP_COLS][8 * 128];
+  const int col = threadIdx.x / 64, t = threadIdx.x % 64;
+  const int b = blockIdx.x * TOEP_COLS + col, blob = blockIdx.y;
+  const Fr* cf = coef + (size_t)blob * N_POINTS;
+  uint32_t* sm = smem[col];
+  // c_0 = f_(64 * 63 + b); c_u = 0 for 1 <= u <= 65; c_u = f_(64 (u - 65) + b) for 66 <= u <= 127
+  for (int u = t; u < 128; u += 64) {
+    Fr v = fr_zero();
+    if (u == 0) v = cf[64 * 63 + b];
+    else if (u >= 66) v = cf[64 * (u - 65) + b];
+    sm_store<128>(sm, u, v);
+  }
+  __syncthreads();
+  for (int half = 64; half >= 1; half >>= 1) {
+    const int step = (EXT_POINTS / 2) / half;
+    const int j = t & (half - 1);
+    const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+    Fr u = sm_load<128>(sm, i0), v = sm_load<128>(sm, i1);
+    sm_store<128>(sm, i0, fr_add(u, v));
+    Fr d = fr_sub(u, v);
+    if (j) d = fr_mul(d, tw[step * j]);
+    sm_store<128>(sm, i1, d);
+    __syncthreads();
+  }
+  const Fr inv128 = fr_const(k::FR_INV_128);
+  for (int pos = t; pos < 128; pos += 64) {
+    const Fr v = fr_from_mont(fr_mul(sm_load<128>(sm, pos), inv128));
+    const int j = brp7(pos);
+    uint4* dst = reinterpret_cast<uint4*>(scalars + (((size_t)blob * 128 + j) * 64 + b) * 8);
+    dst[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    dst[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+  }
+}
+
+// One warp per (blob, frequency): 64 points, lanes 0..15 sum the m-halves, lanes 16..31 the q-halves.
+__global__ void __launch_bounds__(32) cell_msm_kernel(G1Xyzz* __restrict__ out, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars, int c, int nwin,
+                                                     uint32_t cnt_top, int n_blobs) {
+  __shared__ uint32_t sk[4][32];
+  __shared__ uint32_t red[48 * 16];
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x % N_CELLS, blob = blockIdx.x / N_CELLS;
+  const uint8_t* sc = scalars + (size_t)blockIdx.x * 64 * 32;
+  const int half = tid / 16, pl = tid % 16;
+  auto limb = [&](int w) { return sk[w][tid]; };
+  G1Xyzz acc = xyzz_inf();
+  for (int b = pl; b < 64; b += 16) {
+    uint32_t h4[4];
+    load_scalar_half<false>(h4, sc, b, half);
+#pragma unroll
+    for (int i = 0; i < 4; i++) sk[i][tid] = h4[i];
+    const uint32_t pi = (uint32_t)j * 64 + b;
+    int carry = 0, d = 0;
+    G1Affine cur = g1a_inf();
+    for (int w = 0; w <= nwin; w++) {
+      int dn = 0;
+      G1Affine nxt = g1a_inf();
+      if (w < nwin) {
+        dn = glv_digit(limb, c, nwin, w, carry);
+        if (dn != 0) {
+          const uint32_t cnt = (w == nwin - 1) ? cnt_top : (1u << (c - 1));
+          nxt = load_entry(table, (((size_t)w * EXT_POINTS) << (c - 1)) + (size_t)pi * cnt + (uint32_t)((dn < 0 ? -dn : dn) - 1));
+        }
+      }
+      if (d != 0) {
+        cur.y = fp_cneg(cur.y, d < 0);
+        xyzz_madd_hot(acc, cur);
+      }
+      cur = nxt; d = dn;
+    }
+  }
+  block_reduce_xyzz_glv<32>(acc, red);
+  if (tid == 0) out[(size_t)j * n_blobs + blob] = acc;
+}
+
+__global__ void cell_proofs_finalize_kernel(uint8_t* __restrict__ proofs, const G1Xyzz* __restrict__ pts, int n_blobs) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)n_blobs * N_CELLS) return;
+  const int blob = (int)(t % n_blobs), i = (int)(t / n_blobs);
+  const G1Affine a = xyzz_to_affine(pts[(size_t)brp7(i) * n_blobs + blob]);
+  g1_compress(proofs + ((size_t)blob * N_CELLS + i) * 48, a);
+}
+
+}  // namespace
+
+void launch_cell_twiddles(void* d_tw, cudaStream_t st) {
+  cell_twiddles_kernel<<<EXT_POINTS / 128, 128, 0, st>>>((Fr*)d_tw);
+  count_launch();
+}
+void launch_cell_twiddle_naf(void* d_naf, cudaStream_t st) {
+  cell_twiddle_naf_kernel<<<1, 128, 0, st>>>((uint32_t*)d_naf);
+  count_launch();
+}
+void launch_cell_srs_columns(void* d_pts, const void* d_srs, cudaStream_t st) {
+  cell_srs_columns_kernel<<<EXT_POINTS / 128, 128, 0, st>>>((G1Xyzz*)d_pts, (const G1Affine*)d_srs);
+  count_launch();
+}
+void launch_cell_fk20_points(void* d_aff, const void* d_pts, cudaStream_t st) {
+  cell_fk20_points_kernel<<<EXT_POINTS / 64, 64, 0, st>>>((G1Affine*)d_aff, (const G1Xyzz*)d_pts);
+  count_launch();
+}
+void launch_cell_g1_fft_stage(void* d_pts, int batch, int half, bool dif, bool inverse, bool upper_half_zero, const void* d_naf, cudaStream_t st) {
+  if (batch <= 0) return;
+  const int pad = (batch + 31) / 32 * 32;
+  const long threads = (long)pad * 64;
+  cell_g1_fft_stage_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>((G1Xyzz*)d_pts, batch, pad, half, dif ? 1 : 0, inverse ? 1 : 0,
+                                                                          upper_half_zero ? 1 : 0, (const uint32_t*)d_naf);
+  count_launch();
+}
+static void poly_launch(void* d_coef, void* d_cells, const void* d_blobs, int n, int mode, int from_blob, const void* d_tw, cudaStream_t st) {
+  if (n <= 0) return;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaFuncSetAttribute(cell_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POLY_SMEM);
+    attr_set[dev] = true;
+  }
+  cell_poly_kernel<<<n, POLY_THREADS, POLY_SMEM, st>>>((Fr*)d_coef, (uint8_t*)d_cells, (const uint8_t*)d_blobs, mode, from_blob, (const Fr*)d_tw);
+  count_launch();
+}
+void launch_cell_poly(void* d_coef, void* d_cells, const void* d_blobs, int n, int mode, const void* d_tw, cudaStream_t st) {
+  poly_launch(d_coef, d_cells, d_blobs, n, mode, 1, d_tw, st);
+}
+void launch_cell_coef_to_cells(void* d_cells, const void* d_coef, int n, int mode, const void* d_tw, cudaStream_t st) {
+  poly_launch(const_cast<void*>(d_coef), d_cells, nullptr, n, mode, 0, d_tw, st);
+}
+void launch_cell_toeplitz(void* d_scalars, const void* d_coef, int n, const void* d_tw, cudaStream_t st) {
+  if (n <= 0) return;
+  cell_toeplitz_kernel<<<dim3(64 / TOEP_COLS, n), 64 * TOEP_COLS, 0, st>>>((uint32_t*)d_scalars, (const Fr*)d_coef, (const Fr*)d_tw);
+  count_launch();
+}
+void launch_cell_msm(void* d_pts, const void* d_table, int c, const void* d_scalars, int n, cudaStream_t st) {
+  if (n <= 0) return;
+  cell_msm_kernel<<<(unsigned)n * N_CELLS, 32, 0, st>>>((G1Xyzz*)d_pts, (const uint4*)d_table, (const uint8_t*)d_scalars, c, glv_num_windows(c),
+                                                                glv_top_max(c) + 1u, n);
+  count_launch();
+}
+void launch_cell_proofs_finalize(void* d_proofs48, const void* d_pts, int n, cudaStream_t st) {
+  if (n <= 0) return;
+  const long total = (long)n * N_CELLS;
+  cell_proofs_finalize_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>((uint8_t*)d_proofs48, (const G1Xyzz*)d_pts, n);
+  count_launch();
+}
+
+}  // namespace lw

@@ -24,6 +24,7 @@
 
 #include "../../include/lwkzg.h"
 #include "kernels.h"
+#include "kernels_cells.h"
 #include "kernels_setup.h"
 
 namespace {
@@ -51,6 +52,8 @@ struct Options {
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
+  long cell_window_bits = 13;        // window of the FK20 digit table (8192 points; 13 bits = 29 GiB), shrunk to what free HBM allows
+  long cell_chunk_blobs = 1024;      // blobs per pass of compute_cells_and_kzg_proofs batches (the G1 FFTs are batched across blobs)
   long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode),
                   // 2 = MODE_DENEB (the mainnet wire format: big-endian canonical scalars over the Lagrange SRS)
   Options() {
@@ -97,6 +100,9 @@ struct Slot {
   DevBuf blobs, q, partials, states, z, y, ybe, c48, cin48, p48, caff, status, status2, zbe;
 };
 
+struct CellCtx;                       // PeerDAS state (cells_host.inl), built on the first cell call
+void destroy_cell_ctx(CellCtx* cc);
+
 struct Ctx {
   FFTSettings fs_prefix;  // MUST be first: KZGSettings.fs points here
   uint64_t magic;
@@ -111,6 +117,9 @@ struct Ctx {
   void* d_roots;      // Lagrange modes: bit-reversed 4096th roots of unity (Montgomery)
   void* d_gen;        // Lagrange modes: the G1 generator (c-kzg verifies against G, not against g1_values[0] = L_0)
   void* d_srs;        // 4096 affine Montgomery
+  void* d_mono = nullptr;     // the MONOMIAL SRS [tau^i]G (= d_srs in MODE_REFERENCE; kept by the loader in the Lagrange modes): FK20, cell verification
+  bool mono_owned = false;
+  CellCtx* cell = nullptr;
   void* d_table;      // fixed-base digit table
   void* d_prep0;      // prepared g2[0] / g2[1] line coefficients
   void* d_prep1;
@@ -187,6 +196,9 @@ void destroy_ctx(Ctx* c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
   if (c->hash_st) cudaStreamDestroy(c->hash_st);
+  if (c->cell) destroy_cell_ctx(c->cell);
+  c->cell = nullptr;
+  if (c->d_mono && c->mono_owned) cudaFree(c->d_mono);
   if (c->d_srs) cudaFree(c->d_srs);
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_prep0) cudaFree(c->d_prep0);
@@ -275,6 +287,7 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
   }
 
   c->mode = mode;
+  if (mode == 0) c->d_mono = c->d_srs;
   if (mode != 0) {
     // allocated before the early return below: every Lagrange-mode kernel may assume they exist
     CU_TRY(cudaMalloc(&c->d_roots, (size_t)N_POINTS * 32));
@@ -914,6 +927,32 @@ C_KZG_RET settings_from_compressed(KZGSettings* out, const uint8_t* g1_bytes, si
   }
   Ctx* c = build_ctx(g1, g2, mode);
   if (!c) { free(g1); free(g2); return C_KZG_ERROR; }
+  if (mode != 0 && n1 == N_POINTS && c->srs_valid) {
+    // the Lagrange modes keep the monomial points too (c-kzg's g1_values_monomial): FK20 and cell verification need them
+    bool good = [&]() -> bool {
+      DeviceGuard dg(c->device);
+      void* d_canon = nullptr;
+      int* d_flags = nullptr;
+      CU_TRY(cudaMalloc(&d_canon, (size_t)N_POINTS * 96));
+      CU_TRY(cudaMalloc(&d_flags, 2 * N_POINTS * sizeof(int)));
+      CU_TRY(cudaMalloc(&c->d_mono, (size_t)N_POINTS * AFFINE_BYTES));
+      c->mono_owned = true;
+      // on the kernel's own stream: a plain cudaMemcpy from pageable memory may return before the DMA has landed, and
+      // a non-blocking stream does not wait for the legacy stream
+      CU_TRY(cudaMemcpyAsync(d_canon, c1.data(), (size_t)N_POINTS * 96, cudaMemcpyHostToDevice, c->slot[0].st));
+      launch_srs_import(c->d_mono, d_canon, d_flags, d_flags + N_POINTS, N_POINTS, c->slot[0].st);
+      std::vector<int> flags(N_POINTS);
+      CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, N_POINTS * sizeof(int), cudaMemcpyDeviceToHost, c->slot[0].st));
+      CU_TRY(cudaStreamSynchronize(c->slot[0].st));
+      CU_TRY(cudaGetLastError());
+      cudaFree(d_canon);
+      cudaFree(d_flags);
+      for (int f : flags)
+        if (f) { set_err("monomial SRS import failed"); return false; }
+      return true;
+    }();
+    if (!good) { destroy_ctx(c); free(g1); free(g2); return C_KZG_ERROR; }
+  }
   out->fs = reinterpret_cast<FFTSettings*>(c);
   out->g1_values = g1;
   out->g2_values = g2;
@@ -1112,6 +1151,8 @@ struct CtxLock {
   explicit CtxLock(Ctx* ctx) : c(ctx), lk(ctx->mu), dg(ctx->device) {}
 };
 
+#include "cells_host.inl"
+
 }  // namespace
 
 // =================================================================== C ABI
@@ -1132,6 +1173,8 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
   if (n == "verify_super_blobs") { if (value < 1) return 1; opts().verify_super_blobs = value; return 0; }
   if (n == "lincomb_points_in_g1") { if (value != 0 && value != 1) return 1; opts().lincomb_points_in_g1 = value; return 0; }
+  if (n == "cell_window_bits") { if (value < 4 || value > 14) return 1; opts().cell_window_bits = value; return 0; }
+  if (n == "cell_chunk_blobs") { if (value < 1 || value > 65536) return 1; opts().cell_chunk_blobs = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
   return 1;
 }
@@ -1146,6 +1189,8 @@ long lwkzg_get_option(const char* name) {
   if (n == "msm_ba_min_blobs") return opts().msm_ba_min_blobs;
   if (n == "verify_super_blobs") return opts().verify_super_blobs;
   if (n == "lincomb_points_in_g1") return opts().lincomb_points_in_g1;
+  if (n == "cell_window_bits") return opts().cell_window_bits;
+  if (n == "cell_chunk_blobs") return opts().cell_chunk_blobs;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel
   if (n == "msm_ba_slots") return msm_ba_slots();       // read-only: affine accumulators per thread
   return -1;
@@ -1737,5 +1782,7 @@ C_KZG_RET lwkzg_g1_lincomb(Bytes48* out, const uint8_t* points_xy_be, const uint
   memcpy(out, w.h_out, 48);
   return C_KZG_OK;
 }
+
+#include "cells_api.inl"
 
 }  // extern "C"
