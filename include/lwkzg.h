@@ -314,7 +314,7 @@ int lwkzg_window_bits(const KZGSettings *s);
  * loaded / first used.  Env: LWKZG_WINDOW_BITS, LWKZG_CHUNK_BLOBS, LWKZG_MODE,
  * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS.  Cells: "cell_window_bits" (window of the FK20 digit table over 8192
  * points, 4..14, default 13 = 29 GiB, shrunk to what free device memory allows), "cell_chunk_blobs" (blobs per
- * pass of a cell batch, default 1024).
+ * pass of a cell batch, default 864: one full wave of the G1 FFT stage kernel).
  * Returns 0 on success. */
 int lwkzg_set_option(const char *name, long value);
 long lwkzg_get_option(const char *name);

@@ -91,35 +91,98 @@ __global__ void cell_fk20_points_kernel(G1Affine* __restrict__ out, const G1Xyzz
 }
 
 // ------------------------------------------------------------------ G1 FFT stage
-// [nu^e] T by the recoded digits (warp-uniform: every lane of a warp has the same e)
-LW_COLD G1Xyzz g1_mul_root(const G1Xyzz& t, const uint32_t* __restrict__ naf_e) {
-  G1Xyzz acc = xyzz_inf();
+// Compact group law for the twiddle ladders: every field multiplication is a CALL to the one out-of-line multiplier
+// (fp_mul_nv / fp_sqr_nv), so a doubling or an addition is a few hundred bytes of SASS instead of ~40 KB -- a stage runs
+// only a handful of warps per SM, each at its own place in the ladder, and the force-inlined formulas thrashed the
+// instruction cache.
+__device__ __noinline__ void cell_dbl_c(G1Xyzz& p) {
+  if (!xyzz_is_inf(p)) {
+    const Fp U = fp_dbl(p.y), V = fp_sqr_nv(U), W = fp_mul_nv(U, V), S = fp_mul_nv(p.x, V), X2 = fp_sqr_nv(p.x);
+    const Fp M = fp_add(fp_dbl(X2), X2);
+    const Fp X3 = fp_sub(fp_sqr_nv(M), fp_dbl(S));
+    p.y = fp_sub(fp_mul_nv(M, fp_sub(S, X3)), fp_mul_nv(W, p.y));
+    p.x = X3;
+    p.zz = fp_mul_nv(V, p.zz);
+    p.zzz = fp_mul_nv(W, p.zzz);
+  }
+}
+// acc += (x, y), an affine point that is not infinity
+__device__ __noinline__ void cell_madd_c(G1Xyzz& acc, const Fp& x, const Fp& y) {
+  if (xyzz_is_inf(acc)) {
+    acc.x = x; acc.y = y; acc.zz = fp_one(); acc.zzz = fp_one();
+  } else {
+    const Fp Pd = fp_sub(fp_mul_nv(x, acc.zz), acc.x);
+    const Fp Rd = fp_sub(fp_mul_nv(y, acc.zzz), acc.y);
+    if (fp_is_zero(Pd)) {
+      G1Affine a;
+      a.x = x; a.y = y;
+      xyzz_madd_rare(acc, a);
+    } else {
+      const Fp PP = fp_sqr_nv(Pd), PPP = fp_mul_nv(Pd, PP), Q = fp_mul_nv(acc.x, PP);
+      const Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
+      acc.y = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(acc.y, PPP));
+      acc.x = X3;
+      acc.zz = fp_mul_nv(acc.zz, PP);
+      acc.zzz = fp_mul_nv(acc.zzz, PPP);
+    }
+  }
+}
+// a += b (both XYZZ), b negated first if neg_b
+__device__ __noinline__ void cell_add_c(G1Xyzz& a, const G1Xyzz& b, bool neg_b) {
+  if (!xyzz_is_inf(b)) {
+    const Fp by = fp_cneg(b.y, neg_b);
+    if (xyzz_is_inf(a)) {
+      a = b;
+      a.y = by;
+    } else {
+      const Fp U1 = fp_mul_nv(a.x, b.zz), S1 = fp_mul_nv(a.y, b.zzz);
+      const Fp Pd = fp_sub(fp_mul_nv(b.x, a.zz), U1), Rd = fp_sub(fp_mul_nv(by, a.zzz), S1);
+      if (fp_is_zero(Pd)) {
+        if (fp_is_zero(Rd)) cell_dbl_c(a);
+        else a = xyzz_inf();
+      } else {
+        const Fp PP = fp_sqr_nv(Pd), PPP = fp_mul_nv(Pd, PP), Q = fp_mul_nv(U1, PP);
+        const Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
+        a.y = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(S1, PPP));
+        a.x = X3;
+        a.zz = fp_mul_nv(fp_mul_nv(a.zz, b.zz), PP);
+        a.zzz = fp_mul_nv(fp_mul_nv(a.zzz, b.zzz), PPP);
+      }
+    }
+  }
+}
+
+// t <- [nu^e] t by the recoded digits (warp-uniform: every lane of a warp has the same e)
+__device__ __noinline__ void g1_mul_root(G1Xyzz& t, const uint32_t* __restrict__ naf_e) {
   if (!xyzz_is_inf(t)) {
     const G1Affine a = xyzz_to_affine(t);
-    G1Affine a2;
-    a2.x = fp_mul(a.x, fp_beta());
-    a2.y = fp_neg(a.y);
-    const G1Affine an = g1a_neg(a), a2n = g1a_neg(a2);
+    const Fp bx = fp_mul_nv(a.x, fp_beta());   // (beta x, -y) = [x^2](x, y): the base of the q-half
+    const Fp ny = fp_neg(a.y);
     int top = 159;
     while (top > 0) {
       const int w = top >> 5, s = top & 31;
       if (((naf_e[w] | naf_e[5 + w] | naf_e[10 + w] | naf_e[15 + w]) >> s) & 1u) break;
       top--;
     }
+    G1Xyzz acc = xyzz_inf();
     for (int bit = top; bit >= 0; bit--) {
       const int w = bit >> 5, s = bit & 31;
-      xyzz_dbl_ni(acc);
-      if ((naf_e[w] >> s) & 1u) xyzz_madd_ni(acc, a);
-      if ((naf_e[5 + w] >> s) & 1u) xyzz_madd_ni(acc, an);
-      if ((naf_e[10 + w] >> s) & 1u) xyzz_madd_ni(acc, a2);
-      if ((naf_e[15 + w] >> s) & 1u) xyzz_madd_ni(acc, a2n);
+      cell_dbl_c(acc);
+      if ((naf_e[w] >> s) & 1u) cell_madd_c(acc, a.x, a.y);
+      if ((naf_e[5 + w] >> s) & 1u) cell_madd_c(acc, a.x, ny);
+      if ((naf_e[10 + w] >> s) & 1u) cell_madd_c(acc, bx, ny);
+      if ((naf_e[15 + w] >> s) & 1u) cell_madd_c(acc, bx, a.y);
     }
+    t = acc;
   }
-  return acc;
 }
 
-__global__ void __launch_bounds__(64) cell_g1_fft_stage_kernel(G1Xyzz* __restrict__ pts, int batch, int batch_pad, int half, int dif, int inverse,
-                                                              int upper_half_zero, const uint32_t* __restrict__ naf) {
+#ifndef LWKZG_CELL_FFT_MIN_BLOCKS
+#define LWKZG_CELL_FFT_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(64, LWKZG_CELL_FFT_MIN_BLOCKS)
+cell_g1_fft_stage_kernel(G1Xyzz* __restrict__ pts, int batch, int batch_pad, int half, int dif, int inverse, int upper_half_zero,
+                         const uint32_t* __restrict__ naf) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int item = (int)(gt % batch_pad), bf = (int)(gt / batch_pad);
   if (bf >= 64 || item >= batch) return;
@@ -132,26 +195,29 @@ __global__ void __launch_bounds__(64) cell_g1_fft_stage_kernel(G1Xyzz* __restric
   if (dif) {
     // (P, Q) -> (P + Q, [w](P - Q)).  upper_half_zero on the last stage: the odd outputs are H_t, t >= 64, which the
     // caller discards -- they are written as infinity instead of being computed
-    G1Xyzz P = *p0, Q = *p1;
-    G1Xyzz s = P;
-    xyzz_add_ni(s, Q);
-    *p0 = s;
+    const G1Xyzz Q = *p1;
+    G1Xyzz s = *p0;
     if (upper_half_zero && half == 1) {
+      cell_add_c(s, Q, false);
+      *p0 = s;
       *p1 = xyzz_inf();
     } else {
-      G1Xyzz d = P;
-      xyzz_add_ni(d, xyzz_neg(Q));
-      *p1 = e ? g1_mul_root(d, naf + (size_t)e * CELL_NAF_WORDS) : d;
+      G1Xyzz d = s;
+      cell_add_c(s, Q, false);
+      *p0 = s;
+      cell_add_c(d, Q, true);
+      if (e) g1_mul_root(d, naf + (size_t)e * CELL_NAF_WORDS);
+      *p1 = d;
     }
   } else {
     // (P, Q) -> (P + [w]Q, P - [w]Q)
-    G1Xyzz P = *p0, Q = *p1;
-    G1Xyzz t = e ? g1_mul_root(Q, naf + (size_t)e * CELL_NAF_WORDS) : Q;
-    G1Xyzz s = P;
-    xyzz_add_ni(s, t);
+    G1Xyzz t = *p1;
+    if (e) g1_mul_root(t, naf + (size_t)e * CELL_NAF_WORDS);
+    G1Xyzz s = *p0;
+    G1Xyzz d = s;
+    cell_add_c(s, t, false);
     *p0 = s;
-    G1Xyzz d = P;
-    xyzz_add_ni(d, xyzz_neg(t));
+    cell_add_c(d, t, true);
     *p1 = d;
   }
 }

@@ -125,7 +125,7 @@ def test_batch_and_device_api_equal_single_calls(lw, s2, blob11):
     try:
         cells, proofs, st = lw.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n, s2)
     finally:
-        lw.set_option("cell_chunk_blobs", 1024)
+        lw.set_option("cell_chunk_blobs", 864)
     assert st == [0, 0, 0, lw.C_KZG_BADARGS, 0]
     for i in range(n):
         if i == 3:
@@ -264,3 +264,37 @@ def test_full_batch_properties(lw, s2):
     pr = list(args[3])
     pr[17], pr[18] = pr[18], pr[17]
     assert lw.verify_cell_kzg_proof_batch(args[0], args[1], args[2], pr, s2) is False
+
+
+def test_fk20_stages_against_the_exponent_model(lw, s2, o2):
+    """Every intermediate of the FK20 pipeline against a model in the exponent (tau known): the 8192 MSM scalars, the
+    8192 transformed SRS points, the 128 MSM results and the inverse G1 FFT -- so a failure names its stage."""
+    from oracle.py import bls, cells
+    from oracle.py.kzg import _bitrev
+
+    Rr, tau = bls.R, 1337
+    blob = make_blob(41, 2)
+    f = o2.blob_to_coeffs(blob)
+    scalars, hhat, h, fk = lw.debug_cell_stages(blob, s2)
+    nu = pow(cells.root_of_unity(8192), 64, Rr)
+    sp = [pow(tau, k, Rr) for k in range(4096)]
+    inv128 = bls.fr_inv(128)
+    X, C = [], []
+    for b in range(64):
+        X.append(cells.fft([sp[64 * (62 - v) + b] if v <= 62 else 0 for v in range(128)], nu))
+        c = [0] * 128
+        c[0] = f[64 * 63 + b]
+        for u in range(66, 128):
+            c[u] = f[64 * (u - 65) + b]
+        C.append(cells.fft(c, nu))
+    assert all(scalars[j * 64 + b] == C[b][j] * inv128 % Rr for j in range(128) for b in range(64))
+    rng = random.Random(2)
+    for j, b in [(0, 0), (64, 5), (127, 63)] + [(rng.randrange(128), rng.randrange(64)) for _ in range(40)]:
+        assert fk[j * 64 + b] == bls.g1_mul(bls.G1, X[b][j]), (j, b)
+    hh = [sum(C[b][j] * X[b][j] for b in range(64)) * inv128 % Rr for j in range(128)]
+    assert all(hhat[j] == bls.g1_compress(bls.g1_mul(bls.G1, hh[j])) for j in range(128))
+    H = cells.fft(hh, bls.fr_inv(nu))
+    assert H[63] == 0
+    for p in range(128):
+        want = bls.g1_mul(bls.G1, H[_bitrev(p, 7)]) if p % 2 == 0 else None
+        assert h[p] == bls.g1_compress(want), p
