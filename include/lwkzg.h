@@ -290,6 +290,11 @@ double lwkzg_bench_pairing(int iters, const KZGSettings *s);
  * the "window_bits" option if HBM was short), -1 on error */
 int lwkzg_window_bits(const KZGSettings *s);
 
+/* how these settings hold their digit table: 0 = private copy, 1 = built here and published ("share_table"),
+ * 2 = attached to the table another PROCESS built (CUDA IPC), 3 = shared with another settings object of this
+ * process; -1 on error */
+int lwkzg_table_share(const KZGSettings *s);
+
 /* Options: "window_bits" (fixed-base table window c, 4..16; default 16 = 100 GiB, the fastest; shrunk
  * automatically to what free device memory allows -- lwkzg_window_bits() tells; must
  * be set before the settings are first used), "msm_blocks_per_blob" (0 = auto),
@@ -312,7 +317,12 @@ int lwkzg_window_bits(const KZGSettings *s);
  * be128(4096) || blob || commitment, batch challenge domain || be64(4096) || be64(n) || tuples, digests read
  * big-endian).  The mode is captured when a KZGSettings is
  * loaded / first used.  Env: LWKZG_WINDOW_BITS, LWKZG_CHUNK_BLOBS, LWKZG_MODE,
- * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS.  Cells: "cell_window_bits" (window of the FK20 digit table over 8192
+ * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS, LWKZG_SHARE_TABLE.  "share_table" (default 0; SURVEY 8 f2's table cache): 1 = the
+ * digit table is keyed by (SRS contents, window, device) and held ONCE per GPU -- settings objects of one process share
+ * it by reference count, other processes attach to it through a CUDA IPC handle published under /dev/shm (attaching
+ * takes milliseconds instead of the 3.8 s build and no further 100 GiB); the process that built it must outlive the
+ * ones attached to it.  A disk cache is deliberately absent: the GPU rebuilds the table at 26 GiB/s, faster than any
+ * disk delivers it.  Cells: "cell_window_bits" (window of the FK20 digit table over 8192
  * points, 4..14, default 13 = 29 GiB, shrunk to what free device memory allows), "cell_chunk_blobs" (blobs per
  * pass of a cell batch, default 864: one full wave of the G1 FFT stage kernel).
  * Returns 0 on success. */

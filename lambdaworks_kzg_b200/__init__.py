@@ -66,6 +66,7 @@ from .api import (  # noqa: F401
     recover_cells_and_kzg_proofs,
     verify_cell_kzg_proof_batch,
     cell_window_bits,
+    table_share,
     debug_cell_stages,
 )
 from .sharding import shard_range, verify_blob_kzg_proof_batch_distributed, verify_blob_kzg_proof_batch_distributed_device  # noqa: F401

@@ -83,6 +83,7 @@ def load_library() -> ctypes.CDLL:
         "lwkzg_compute_cells_and_kzg_proofs_batch": [vp, vp, vp, sz, sp, ip],
         "lwkzg_compute_cells_and_kzg_proofs_batch_device": [vp, vp, vp, sz, sp, vp, vp],
         "lwkzg_cell_window_bits": [sp],
+        "lwkzg_table_share": [sp],
         "lwkzg_debug_cell_stages": [vp, vp, vp, vp, vp, sp],
         "lwkzg_set_option": [ctypes.c_char_p, ctypes.c_long],
         "lwkzg_get_option": [ctypes.c_char_p],
@@ -533,3 +534,8 @@ def debug_cell_stages(blob: bytes, s):
         y = int.from_bytes(fk.raw[96 * i + 48: 96 * i + 96], "little")
         pts.append(None if x == 0 and y == 0 else (x, y))
     return scalars, [hh.raw[48 * i: 48 * i + 48] for i in range(128)], [h.raw[48 * i: 48 * i + 48] for i in range(128)], pts
+
+
+def table_share(s) -> int:
+    """0 = private digit table, 1 = built here and published, 2 = attached to another process's, 3 = shared in-process."""
+    return int(load_library().lwkzg_table_share(_sp(s)))

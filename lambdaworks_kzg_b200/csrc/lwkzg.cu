@@ -10,6 +10,10 @@
 // There is no CPU compute path in here: the host only parses text, moves bytes
 // and launches kernels.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <signal.h>
+#include <sys/file.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -52,6 +56,7 @@ struct Options {
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
+  long share_table = 0;              // 1 = one digit table per (SRS, window, device) for every settings object and PROCESS that loads it
   long cell_window_bits = 13;        // window of the FK20 digit table (8192 points; 13 bits = 29 GiB), shrunk to what free HBM allows
   long cell_chunk_blobs = 864;       // blobs per pass of a cell batch: 27 x 32 blobs x 64 butterflies = 1728 warps per G1 FFT stage, one wave of the
                                      // 12 x 148 = 1776 warp slots the stage kernel gets
@@ -64,6 +69,7 @@ struct Options {
     if (const char* e = getenv("LWKZG_MSM_BLOCKS_PER_BLOB")) msm_blocks_per_blob = atol(e);
     if (const char* e = getenv("LWKZG_MSM_ALGO")) msm_algo = atol(e);
     if (const char* e = getenv("LWKZG_MSM_BA_MIN_BLOBS")) msm_ba_min_blobs = atol(e);
+    if (const char* e = getenv("LWKZG_SHARE_TABLE")) share_table = atol(e) != 0;
   }
 };
 Options& opts() {
@@ -122,6 +128,8 @@ struct Ctx {
   bool mono_owned = false;
   CellCtx* cell = nullptr;
   void* d_table;      // fixed-base digit table
+  int table_share = 0;        // 0 = private, 1 = built here and published ("share_table"), 2 = attached to another process's, 3 = another settings object's
+  uint64_t table_key = 0;
   void* d_prep0;      // prepared g2[0] / g2[1] line coefficients
   void* d_prep1;
   Slot slot[NSLOT];
@@ -172,6 +180,45 @@ void blst_fp_to_canon(uint32_t* le12, const blst_fp* in) {
   }
 }
 
+// ------------------------------------------------------------------ shared digit tables ("share_table")
+// SURVEY 8 f2 asks for a table cache.  On this hardware the table is REBUILT faster than any disk could deliver it
+// (100 GiB in 3.8 s = 26 GiB/s), so what is worth caching is the copy already in HBM: with "share_table" a table is
+// keyed by (SRS contents, window, device), shared by every settings object of a process (reference count) and by
+// every PROCESS on the same GPU through a CUDA IPC handle published in /dev/shm -- N verifier or fuzzer processes
+// (the reference's fuzz harness runs `-workers` processes, fuzz/Makefile:53-58) hold ONE table instead of N and attach
+// in milliseconds.  The first loader owns the memory and must outlive the others (CUDA IPC rule); a stale file left
+// by a dead owner is ignored and replaced.
+uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull);
+struct SharedTable { void* p; int refs; bool ipc_import; bool published; };
+std::mutex g_table_mu;
+std::map<uint64_t, SharedTable>& table_registry() {
+  static std::map<uint64_t, SharedTable> m;
+  return m;
+}
+struct TableFile {
+  uint64_t magic, key, entries;
+  int32_t pid, c;
+  cudaIpcMemHandle_t handle;
+};
+constexpr uint64_t TABLE_FILE_MAGIC = 0x4c574b5a5442314cull;
+std::string table_path(uint64_t key) {
+  char buf[96];
+  snprintf(buf, sizeof(buf), "/dev/shm/lwkzg_b200_%016llx.tbl", (unsigned long long)key);
+  return buf;
+}
+void release_table(Ctx* c) {
+  if (c->table_share == 0) { cudaFree(c->d_table); c->d_table = nullptr; return; }
+  std::lock_guard<std::mutex> lk(g_table_mu);
+  auto it = table_registry().find(c->table_key);
+  if (it != table_registry().end() && --it->second.refs == 0) {
+    if (it->second.ipc_import) cudaIpcCloseMemHandle(it->second.p);
+    else cudaFree(it->second.p);
+    if (it->second.published) unlink(table_path(c->table_key).c_str());
+    table_registry().erase(it);
+  }
+  c->d_table = nullptr;
+}
+
 // ------------------------------------------------------------------ context
 void destroy_ctx(Ctx* c) {
   if (!c) return;
@@ -201,7 +248,7 @@ void destroy_ctx(Ctx* c) {
   c->cell = nullptr;
   if (c->d_mono && c->mono_owned) cudaFree(c->d_mono);
   if (c->d_srs) cudaFree(c->d_srs);
-  if (c->d_table) cudaFree(c->d_table);
+  if (c->d_table) release_table(c);
   if (c->d_prep0) cudaFree(c->d_prep0);
   if (c->d_prep1) cudaFree(c->d_prep1);
   if (c->d_roots) cudaFree(c->d_roots);
@@ -311,6 +358,59 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
   if (want_c > 16) want_c = 16;
   size_t free_b = 0, total_b = 0;
   CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  bool share;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    share = opts().share_table != 0 && window_override == 0;
+  }
+  uint64_t base_key = 0;
+  int lock_fd = -1;
+  if (share) {
+    // key: SRS contents (as imported: the Lagrange points in the Lagrange modes), device identity
+    char bus[32] = {0};
+    cudaDeviceGetPCIBusId(bus, sizeof(bus), c->device);
+    base_key = fnv1a(g1, sizeof(g1_t) * N_POINTS);
+    base_key = fnv1a(bus, sizeof(bus), base_key);
+    // one loader at a time per machine: a second process waits for the first one's build and then attaches
+    lock_fd = open("/dev/shm/lwkzg_b200.lock", O_CREAT | O_RDWR, 0600);
+    if (lock_fd >= 0) flock(lock_fd, LOCK_EX);
+  }
+  auto unlock = [&]() { if (lock_fd >= 0) { flock(lock_fd, LOCK_UN); close(lock_fd); lock_fd = -1; } };
+  if (share) {
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    for (int cb = (int)want_c; cb >= 4 && !c->d_table; cb--) {
+      const uint64_t key = base_key * 31 + (uint64_t)cb;
+      auto it = table_registry().find(key);
+      if (it != table_registry().end()) {   // another settings object of this process
+        it->second.refs++;
+        c->d_table = it->second.p;
+        c->table_share = 3;
+        c->table_key = key;
+        c->c = cb;
+        break;
+      }
+      TableFile tf;
+      FILE* f = fopen(table_path(key).c_str(), "rb");
+      if (!f) continue;
+      const bool got = fread(&tf, sizeof(tf), 1, f) == 1;
+      fclose(f);
+      if (!got || tf.magic != TABLE_FILE_MAGIC || tf.key != key || tf.c != cb || tf.entries != table_entries(cb, N_POINTS)) continue;
+      if (tf.pid == (int32_t)getpid() || (kill(tf.pid, 0) != 0 && errno == ESRCH)) continue;   // ours but unregistered, or a dead owner
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, tf.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); continue; }
+      table_registry()[key] = SharedTable{p, 1, true, false};
+      c->d_table = p;
+      c->table_share = 2;
+      c->table_key = key;
+      c->c = cb;
+    }
+  }
+  if (c->d_table) {
+    c->nwin = table_num_windows(c->c);
+    unlock();
+    CU_TRY(cudaStreamSynchronize(st));
+    return true;
+  }
   int cbits = (int)want_c;
   for (;; cbits--) {
     const size_t need = (size_t)table_entries(cbits, N_POINTS) * AFFINE_BYTES;
@@ -319,16 +419,46 @@ bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long wind
   c->c = cbits;
   c->nwin = table_num_windows(cbits);
   const size_t entries = (size_t)table_entries(cbits, N_POINTS);
-  if (entries >= (size_t(1) << 31)) { set_err("table index does not fit 31 bits"); return false; }   // entry | sign << 31 (msm.cu)
-  CU_TRY(cudaMalloc(&c->d_table, entries * AFFINE_BYTES));
-  void* d_bases = nullptr;
-  CU_TRY(cudaMalloc(&d_bases, (size_t)c->nwin * N_POINTS * AFFINE_BYTES));
-  launch_table_bases(d_bases, c->d_srs, c->c, c->nwin, N_POINTS, st);
-  launch_table_fill(c->d_table, d_bases, c->c, c->nwin, N_POINTS, table_top_count(c->c), st);
-  CU_TRY(cudaStreamSynchronize(st));
-  CU_TRY(cudaGetLastError());
-  cudaFree(d_bases);
-  return true;
+  if (entries >= (size_t(1) << 31)) { unlock(); set_err("table index does not fit 31 bits"); return false; }   // entry | sign << 31 (msm.cu)
+  bool built = [&]() -> bool {
+    CU_TRY(cudaMalloc(&c->d_table, entries * AFFINE_BYTES));
+    void* d_bases = nullptr;
+    CU_TRY(cudaMalloc(&d_bases, (size_t)c->nwin * N_POINTS * AFFINE_BYTES));
+    launch_table_bases(d_bases, c->d_srs, c->c, c->nwin, N_POINTS, st);
+    launch_table_fill(c->d_table, d_bases, c->c, c->nwin, N_POINTS, table_top_count(c->c), st);
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    cudaFree(d_bases);
+    return true;
+  }();
+  if (built && share) {
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    const uint64_t key = base_key * 31 + (uint64_t)cbits;
+    TableFile tf;
+    memset(&tf, 0, sizeof(tf));
+    tf.magic = TABLE_FILE_MAGIC;
+    tf.key = key;
+    tf.entries = entries;
+    tf.pid = (int32_t)getpid();
+    tf.c = cbits;
+    bool published = false;
+    if (cudaIpcGetMemHandle(&tf.handle, c->d_table) == cudaSuccess) {
+      const std::string path = table_path(key), tmp = path + ".tmp";
+      FILE* f = fopen(tmp.c_str(), "wb");
+      if (f) {
+        published = fwrite(&tf, sizeof(tf), 1, f) == 1;
+        fclose(f);
+        published = published && rename(tmp.c_str(), path.c_str()) == 0;
+      }
+    } else {
+      cudaGetLastError();
+    }
+    table_registry()[key] = SharedTable{c->d_table, 1, false, published};
+    c->table_share = 1;
+    c->table_key = key;
+  }
+  unlock();
+  return built;
 }
 
 long current_mode() {
@@ -371,7 +501,7 @@ std::map<LazyKey, Ctx*>& lazy_map() {
   static std::map<LazyKey, Ctx*> m;
   return m;
 }
-uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
   const uint64_t* w = (const uint64_t*)p;  // all inputs are multiples of 8 bytes
   for (size_t i = 0; i < n / 8; i++) {
     h ^= w[i];
@@ -1174,6 +1304,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "msm_ba_min_blobs") { if (value < 1) return 1; opts().msm_ba_min_blobs = value; return 0; }
   if (n == "verify_super_blobs") { if (value < 1) return 1; opts().verify_super_blobs = value; return 0; }
   if (n == "lincomb_points_in_g1") { if (value != 0 && value != 1) return 1; opts().lincomb_points_in_g1 = value; return 0; }
+  if (n == "share_table") { if (value != 0 && value != 1) return 1; opts().share_table = value; return 0; }
   if (n == "cell_window_bits") { if (value < 4 || value > 14) return 1; opts().cell_window_bits = value; return 0; }
   if (n == "cell_chunk_blobs") { if (value < 1 || value > 65536) return 1; opts().cell_chunk_blobs = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
@@ -1190,6 +1321,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "msm_ba_min_blobs") return opts().msm_ba_min_blobs;
   if (n == "verify_super_blobs") return opts().verify_super_blobs;
   if (n == "lincomb_points_in_g1") return opts().lincomb_points_in_g1;
+  if (n == "share_table") return opts().share_table;
   if (n == "cell_window_bits") return opts().cell_window_bits;
   if (n == "cell_chunk_blobs") return opts().cell_chunk_blobs;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel
@@ -1690,6 +1822,10 @@ C_KZG_RET lwkzg_debug_batch_challenge(uint8_t* out32, const KZGSettings* s) {
 int lwkzg_window_bits(const KZGSettings* s) {
   Ctx* c = ctx_of(s);
   return c ? c->c : -1;
+}
+int lwkzg_table_share(const KZGSettings* s) {
+  Ctx* c = ctx_of(s);
+  return c ? c->table_share : -1;
 }
 
 // ---- measurement hook for BASELINE config 5 (variable-base MSM size sweep):
