@@ -247,9 +247,10 @@ C_KZG_RET lwkzg_compute_cells_and_kzg_proofs_batch(Cell *cells, KZGProof *proofs
 C_KZG_RET lwkzg_compute_cells_and_kzg_proofs_batch_device(void *d_cells, void *d_proofs, const void *d_blobs, size_t n,
                                                           const KZGSettings *s, void *stream, void *d_status);
 /* Test hook: intermediate values of the FK20 pipeline for one blob, so a parity test can name the stage that deviates:
- * scalars = the 8192 MSM scalars DFT_128(circulant column b)_j / 128 as 32-byte little-endian integers, index j * 64 + b;
+ * scalars = the 8192 MSM scalars DFT_128(circulant column b)_j / 128 as 32-byte little-endian integers, at index
+ * (j / 64) * 4096 + b * 64 + j % 64 (the order of the two half tables);
  * hhat48 = the 128 MSM results (compressed, natural j); h48 = after the inverse G1 FFT (compressed; position p holds
- * H_brp7(p), odd positions infinity); fk20_xy96 = the 8192 FK20 points X[j * 64 + b] as canonical little-endian x || y. */
+ * H_brp7(p), odd positions infinity); fk20_xy96 = the 8192 FK20 points X(j, b) in the same order, canonical little-endian x || y. */
 C_KZG_RET lwkzg_debug_cell_stages(uint8_t *scalars, uint8_t *hhat48, uint8_t *h48, uint8_t *fk20_xy96, const Blob *blob,
                                   const KZGSettings *s);
 /* window of the FK20 digit table in use (-1 before the first cell call) */

@@ -527,9 +527,11 @@ def debug_cell_stages(blob: bytes, s):
     h = ctypes.create_string_buffer(128 * 48)
     fk = ctypes.create_string_buffer(8192 * 96)
     _check(load_library().lwkzg_debug_cell_stages(sc, hh, h, fk, blob, _sp(s)), "lwkzg_debug_cell_stages")
-    scalars = [int.from_bytes(sc.raw[32 * i: 32 * i + 32], "little") for i in range(8192)]
+    # the library's MSM order is (j // 64) * 4096 + b * 64 + j % 64; returned here as [j * 64 + b]
+    order = [(j // 64) * 4096 + b * 64 + j % 64 for j in range(128) for b in range(64)]
+    scalars = [int.from_bytes(sc.raw[32 * i: 32 * i + 32], "little") for i in order]
     pts = []
-    for i in range(8192):
+    for i in order:
         x = int.from_bytes(fk.raw[96 * i: 96 * i + 48], "little")
         y = int.from_bytes(fk.raw[96 * i + 48: 96 * i + 96], "little")
         pts.append(None if x == 0 and y == 0 else (x, y))

@@ -87,7 +87,9 @@ __global__ void cell_fk20_points_kernel(G1Affine* __restrict__ out, const G1Xyzz
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= EXT_POINTS) return;
   const int j = t / 64, b = t % 64;
-  out[t] = xyzz_to_affine(pts[brp7(j) * 64 + b]);
+  // MSM order: half v = j / 64 has its own 4096-point table, point b * 64 + (j % 64) -- so the points of ONE frequency
+  // are those congruent to j mod 64, which is what a thread of the batched-affine kernel sums (msm_ba.cuh)
+  out[(j / 64) * N_POINTS + b * 64 + (j % 64)] = xyzz_to_affine(pts[brp7(j) * 64 + b]);
 }
 
 // ------------------------------------------------------------------ G1 FFT stage
@@ -374,29 +376,33 @@ __global__ void __launch_bounds__(64 * TOEP_COLS) cell_toeplitz_kernel(uint32_t*
   for (int pos = t; pos < 128; pos += 64) {
     const Fr v = fr_from_mont(fr_mul(sm_load<128>(sm, pos), inv128));
     const int j = brp7(pos);
-    uint4* dst = reinterpret_cast<uint4*>(scalars + (((size_t)blob * 128 + j) * 64 + b) * 8);
+    uint4* dst = reinterpret_cast<uint4*>(scalars + ((((size_t)(j / 64) * gridDim.y + blob) * N_POINTS) + b * 64 + (j % 64)) * 8);
     dst[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     dst[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
   }
 }
 
-// One warp per (blob, frequency): 64 points, lanes 0..15 sum the m-halves, lanes 16..31 the q-halves.
-__global__ void __launch_bounds__(32) cell_msm_kernel(G1Xyzz* __restrict__ out, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars, int c, int nwin,
-                                                     uint32_t cnt_top, int n_blobs) {
+// One warp per (blob, frequency): 64 points, lanes 0..15 sum the m-halves, lanes 16..31 the q-halves.  The path for
+// small batches; from CELL_BA_MIN_BLOBS blobs up the batched-affine kernel of the commitment MSM runs in its
+// segmented form (msm_ba.cuh: 5 M + 1 S per table entry instead of 8 M + 2 S).
+__global__ void __launch_bounds__(32) cell_msm_kernel(G1Xyzz* __restrict__ out, const uint4* __restrict__ table, size_t half_words, const uint8_t* __restrict__ scalars,
+                                                     int c, int nwin, uint32_t cnt_top, int n_blobs) {
   __shared__ uint32_t sk[4][32];
   __shared__ uint32_t red[48 * 16];
   const int tid = threadIdx.x;
   const int j = blockIdx.x % N_CELLS, blob = blockIdx.x / N_CELLS;
-  const uint8_t* sc = scalars + (size_t)blockIdx.x * 64 * 32;
+  const int v = j / 64, jl = j % 64;
+  const uint4* tab = table + (size_t)v * half_words;
+  const uint8_t* sc = scalars + ((size_t)v * n_blobs + blob) * BLOB_BYTES;
   const int half = tid / 16, pl = tid % 16;
   auto limb = [&](int w) { return sk[w][tid]; };
   G1Xyzz acc = xyzz_inf();
   for (int b = pl; b < 64; b += 16) {
+    const int pi = b * 64 + jl;
     uint32_t h4[4];
-    load_scalar_half<false>(h4, sc, b, half);
+    load_scalar_half<false>(h4, sc, pi, half);
 #pragma unroll
     for (int i = 0; i < 4; i++) sk[i][tid] = h4[i];
-    const uint32_t pi = (uint32_t)j * 64 + b;
     int carry = 0, d = 0;
     G1Affine cur = g1a_inf();
     for (int w = 0; w <= nwin; w++) {
@@ -404,10 +410,7 @@ __global__ void __launch_bounds__(32) cell_msm_kernel(G1Xyzz* __restrict__ out, 
       G1Affine nxt = g1a_inf();
       if (w < nwin) {
         dn = glv_digit(limb, c, nwin, w, carry);
-        if (dn != 0) {
-          const uint32_t cnt = (w == nwin - 1) ? cnt_top : (1u << (c - 1));
-          nxt = load_entry(table, (((size_t)w * EXT_POINTS) << (c - 1)) + (size_t)pi * cnt + (uint32_t)((dn < 0 ? -dn : dn) - 1));
-        }
+        if (dn != 0) nxt = load_entry(tab, entry_index(c, nwin, cnt_top, w, pi, dn < 0 ? -dn : dn));
       }
       if (d != 0) {
         cur.y = fp_cneg(cur.y, d < 0);
@@ -477,10 +480,21 @@ void launch_cell_toeplitz(void* d_scalars, const void* d_coef, int n, const void
   cell_toeplitz_kernel<<<dim3(64 / TOEP_COLS, n), 64 * TOEP_COLS, 0, st>>>((uint32_t*)d_scalars, (const Fr*)d_coef, (const Fr*)d_tw);
   count_launch();
 }
-void launch_cell_msm(void* d_pts, const void* d_table, int c, const void* d_scalars, int n, cudaStream_t st) {
+void launch_ba_segmented(void* d_out, const void* d_table, int c, const void* d_scalars, int n_blobs, void* d_scratch, int seg_stride, cudaStream_t st);   // msm_ba_v0.cu
+size_t cell_table_half_entries(int c) { return (size_t)glv_table_entries(c, N_POINTS); }
+size_t cell_msm_scratch_bytes(int n) { return n >= CELL_BA_MIN_BLOBS ? msm_ba_scratch_bytes(n) : 16; }
+void launch_cell_msm(void* d_pts, const void* d_table, int c, const void* d_scalars, int n, void* d_scratch, cudaStream_t st) {
   if (n <= 0) return;
-  cell_msm_kernel<<<(unsigned)n * N_CELLS, 32, 0, st>>>((G1Xyzz*)d_pts, (const uint4*)d_table, (const uint8_t*)d_scalars, c, glv_num_windows(c),
-                                                                glv_top_max(c) + 1u, n);
+  const size_t half_entries = cell_table_half_entries(c);
+  if (n >= CELL_BA_MIN_BLOBS && glv_num_windows(c) <= 64) {
+    for (int v = 0; v < 2; v++)
+      launch_ba_segmented((G1Xyzz*)d_pts + (size_t)v * 64 * n, (const uint8_t*)d_table + (size_t)v * half_entries * AFFINE_BYTES, c,
+                          (const uint8_t*)d_scalars + (size_t)v * n * BLOB_BYTES, n, d_scratch, n, st);
+    count_launch(2);
+    return;
+  }
+  cell_msm_kernel<<<(unsigned)n * N_CELLS, 32, 0, st>>>((G1Xyzz*)d_pts, (const uint4*)d_table, half_entries * 6, (const uint8_t*)d_scalars, c, glv_num_windows(c),
+                                                     glv_top_max(c) + 1u, n);
   count_launch();
 }
 void launch_cell_proofs_finalize(void* d_proofs48, const void* d_pts, int n, cudaStream_t st) {

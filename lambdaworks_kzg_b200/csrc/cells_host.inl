@@ -11,7 +11,7 @@ struct CellCtx {
   void* d_fk20 = nullptr;         // the 8192 FK20 points themselves (affine Montgomery, 768 KB): test hook
   cudaStream_t st = nullptr;
   cudaEvent_t ev = nullptr;
-  DevBuf blobs, coef, scalars, pts, cells, proofs, status;
+  DevBuf blobs, coef, scalars, pts, cells, proofs, status, msm_scratch;
   // verification / recovery workspace
   DevBuf v_commit, v_cidx, v_cellidx, v_cells, v_proofs, v_evals, v_status, v_pts, v_wcoef, v_rpow, v_scal, v_r, v_out, v_ok, v_msm_a, v_msm_b;
   void* h_stage = nullptr;
@@ -21,7 +21,7 @@ struct CellCtx {
 void destroy_cell_ctx(CellCtx* cc) {
   if (!cc) return;
   if (cc->st) cudaStreamSynchronize(cc->st);
-  for (DevBuf* b : {&cc->blobs, &cc->coef, &cc->scalars, &cc->pts, &cc->cells, &cc->proofs, &cc->status, &cc->v_commit, &cc->v_cidx, &cc->v_cellidx,
+  for (DevBuf* b : {&cc->blobs, &cc->coef, &cc->scalars, &cc->pts, &cc->cells, &cc->proofs, &cc->status, &cc->msm_scratch, &cc->v_commit, &cc->v_cidx, &cc->v_cellidx,
                     &cc->v_cells, &cc->v_proofs, &cc->v_evals, &cc->v_status, &cc->v_pts, &cc->v_wcoef, &cc->v_rpow, &cc->v_scal, &cc->v_r, &cc->v_out,
                     &cc->v_ok, &cc->v_msm_a, &cc->v_msm_b})
     b->release();
@@ -95,16 +95,19 @@ bool cell_ctx_build(Ctx* c) {
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
     int cbits = (int)std::min(std::max(want, 4L), 14L);
     for (;; cbits--) {
-      const size_t need = (size_t)table_entries(cbits, EXT_POINTS) * AFFINE_BYTES;
+      const size_t need = 2 * cell_table_half_entries(cbits) * AFFINE_BYTES;
       if (need + (size_t(6) << 30) <= free_b || cbits <= 4) break;
     }
     cc->c = cbits;
     cc->nwin = table_num_windows(cbits);
-    const size_t entries = (size_t)table_entries(cbits, EXT_POINTS);
-    CU_TRY(cudaMalloc(&cc->d_table, entries * AFFINE_BYTES));
-    CU_TRY(cudaMalloc(&d_bases, (size_t)cc->nwin * EXT_POINTS * AFFINE_BYTES));
-    launch_table_bases(d_bases, d_aff, cc->c, cc->nwin, EXT_POINTS, cc->st);
-    launch_table_fill(cc->d_table, d_bases, cc->c, cc->nwin, EXT_POINTS, table_top_count(cc->c), cc->st);
+    // one table per half of the frequencies (4096 points each, the commitment table's own layout), back to back
+    const size_t half = cell_table_half_entries(cbits);
+    CU_TRY(cudaMalloc(&cc->d_table, 2 * half * AFFINE_BYTES));
+    CU_TRY(cudaMalloc(&d_bases, (size_t)cc->nwin * N_POINTS * AFFINE_BYTES));
+    for (int v = 0; v < 2; v++) {
+      launch_table_bases(d_bases, (const uint8_t*)d_aff + (size_t)v * N_POINTS * AFFINE_BYTES, cc->c, cc->nwin, N_POINTS, cc->st);
+      launch_table_fill((uint8_t*)cc->d_table + (size_t)v * half * AFFINE_BYTES, d_bases, cc->c, cc->nwin, N_POINTS, table_top_count(cc->c), cc->st);
+    }
     CU_TRY(cudaStreamSynchronize(cc->st));
     CU_TRY(cudaGetLastError());
     cudaFree(d_pts);
@@ -130,13 +133,13 @@ long cell_chunk() {
 bool cell_reserve(CellCtx* cc, size_t m, bool own_io) {
   if (own_io && !(cc->blobs.ensure(m * BLOB_BYTES) && cc->cells.ensure(m * N_CELLS * CELL_BYTES) && cc->proofs.ensure(m * N_CELLS * 48))) return false;
   return cc->coef.ensure(m * BLOB_BYTES) && cc->scalars.ensure(m * EXT_POINTS * 32) && cc->pts.ensure(m * N_CELLS * XYZZ_BYTES) &&
-         cc->status.ensure(m * sizeof(int));
+         cc->status.ensure(m * sizeof(int)) && cc->msm_scratch.ensure(cell_msm_scratch_bytes((int)m));
 }
 
 // coefficient form (cc->coef, m blobs) -> 128 proofs per blob
 void cell_enqueue_proofs(CellCtx* cc, void* d_proofs, int m) {
   launch_cell_toeplitz(cc->scalars.p, cc->coef.p, m, cc->d_tw, cc->st);
-  launch_cell_msm(cc->pts.p, cc->d_table, cc->c, cc->scalars.p, m, cc->st);
+  launch_cell_msm(cc->pts.p, cc->d_table, cc->c, cc->scalars.p, m, cc->msm_scratch.p, cc->st);
   cell_g1_idft_dft(cc, cc->pts.p, m);
   launch_cell_proofs_finalize(d_proofs, cc->pts.p, m, cc->st);
 }
@@ -181,12 +184,21 @@ C_KZG_RET cells_host_batch(const KZGSettings* s, size_t n, const Blob* blobs, Ce
     uint8_t* h_cells = hs;
     uint8_t* h_proofs = h_cells + (cells_out ? m * N_CELLS * CELL_BYTES : 0);
     int* h_status = (int*)(h_proofs + (proofs_out ? m * N_CELLS * 48 : 0));
+    bool clean = false;   // every item of the pass succeeded: results went straight to the caller's buffers
     bool good = [&]() -> bool {
       CU_TRY(cudaMemcpyAsync(cc->blobs.p, blobs + off, m * BLOB_BYTES, cudaMemcpyHostToDevice, cc->st));
       if (!cell_enqueue_chunk(c, cc->blobs.p, (int)m, cells_out ? cc->cells.p : nullptr, proofs_out ? cc->proofs.p : nullptr, (int*)cc->status.p)) return false;
-      if (cells_out) CU_TRY(cudaMemcpyAsync(h_cells, cc->cells.p, m * N_CELLS * CELL_BYTES, cudaMemcpyDeviceToHost, cc->st));
-      if (proofs_out) CU_TRY(cudaMemcpyAsync(h_proofs, cc->proofs.p, m * N_CELLS * 48, cudaMemcpyDeviceToHost, cc->st));
+      // the status array is complete after the first kernels of the pass; it decides where the results are copied:
+      // straight into the caller's memory when every item is good (the usual case: no staging copy of 256 KiB per
+      // blob on the host), through the pinned staging area when a failed item's slot must stay untouched
       CU_TRY(cudaMemcpyAsync(h_status, cc->status.p, m * sizeof(int), cudaMemcpyDeviceToHost, cc->st));
+      CU_TRY(cudaStreamSynchronize(cc->st));
+      clean = true;
+      for (size_t i = 0; i < m; i++) clean = clean && h_status[i] == 0;
+      uint8_t* dst_cells = (clean && cells_out) ? (uint8_t*)(cells_out + off * N_CELLS) : h_cells;
+      uint8_t* dst_proofs = (clean && proofs_out) ? (uint8_t*)(proofs_out + off * N_CELLS) : h_proofs;
+      if (cells_out) CU_TRY(cudaMemcpyAsync(dst_cells, cc->cells.p, m * N_CELLS * CELL_BYTES, cudaMemcpyDeviceToHost, cc->st));
+      if (proofs_out) CU_TRY(cudaMemcpyAsync(dst_proofs, cc->proofs.p, m * N_CELLS * 48, cudaMemcpyDeviceToHost, cc->st));
       CU_TRY(cudaStreamSynchronize(cc->st));
       CU_TRY(cudaGetLastError());
       return true;
@@ -194,8 +206,10 @@ C_KZG_RET cells_host_batch(const KZGSettings* s, size_t n, const Blob* blobs, Ce
     if (!good) return C_KZG_ERROR;
     for (size_t i = 0; i < m; i++) {
       if (h_status[i] == 0) {
-        if (cells_out) memcpy(&cells_out[(off + i) * N_CELLS], h_cells + i * N_CELLS * CELL_BYTES, (size_t)N_CELLS * CELL_BYTES);
-        if (proofs_out) memcpy(&proofs_out[(off + i) * N_CELLS], h_proofs + i * N_CELLS * 48, (size_t)N_CELLS * 48);
+        if (!clean) {
+          if (cells_out) memcpy(&cells_out[(off + i) * N_CELLS], h_cells + i * N_CELLS * CELL_BYTES, (size_t)N_CELLS * CELL_BYTES);
+          if (proofs_out) memcpy(&proofs_out[(off + i) * N_CELLS], h_proofs + i * N_CELLS * 48, (size_t)N_CELLS * 48);
+        }
       } else if (first == C_KZG_OK) {
         first = (C_KZG_RET)h_status[i];
       }
@@ -217,7 +231,7 @@ C_KZG_RET cells_device_batch(const KZGSettings* s, size_t n, const void* d_blobs
   CellCtx* cc = c->cell;
   const size_t chunk = std::min<size_t>(n, (size_t)cell_chunk());
   // growing a buffer frees the old one: wait for whatever still uses it
-  if (cc->coef.cap < chunk * BLOB_BYTES || cc->status.cap < chunk * sizeof(int)) cudaStreamSynchronize(cc->st);
+  if (cc->coef.cap < chunk * BLOB_BYTES || cc->status.cap < chunk * sizeof(int) || cc->msm_scratch.cap < cell_msm_scratch_bytes((int)chunk)) cudaStreamSynchronize(cc->st);
   if (!cell_reserve(cc, chunk, false)) return C_KZG_ERROR;
   bool good = [&]() -> bool {
     CU_TRY(cudaEventRecord(cc->ev, user));
@@ -364,8 +378,8 @@ C_KZG_RET cells_recover(Cell* cells_out, KZGProof* proofs_out, const uint64_t* c
 }
 
 // Test hook: the intermediate values of the FK20 pipeline for ONE blob, so that a parity test can say WHICH stage
-// deviates: the 8192 MSM scalars (canonical little-endian limbs, [j][b]), Hhat_j (compressed, natural j), H after the
-// inverse FFT (compressed, position p holds H_brp7(p), odd positions infinity) and the FK20 points X[j * 64 + b]
+// deviates: the 8192 MSM scalars (canonical little-endian limbs, index (j / 64) * 4096 + b * 64 + j % 64), Hhat_j (compressed, natural j), H after the
+// inverse FFT (compressed, position p holds H_brp7(p), odd positions infinity) and the FK20 points in the same order
 // (canonical little-endian limbs x || y, 96 bytes each).
 C_KZG_RET cells_debug_stages(uint8_t* scalars, uint8_t* hhat48, uint8_t* h48, uint8_t* fk20_xy96, const Blob* blob, const KZGSettings* s) {
   Ctx* c = ctx_of(s);
@@ -382,7 +396,7 @@ C_KZG_RET cells_debug_stages(uint8_t* scalars, uint8_t* hhat48, uint8_t* h48, ui
     launch_cell_poly(cc->coef.p, nullptr, cc->blobs.p, 1, c->mode, cc->d_tw, st);
     launch_cell_toeplitz(cc->scalars.p, cc->coef.p, 1, cc->d_tw, st);
     CU_TRY(cudaMemcpyAsync(scalars, cc->scalars.p, (size_t)EXT_POINTS * 32, cudaMemcpyDeviceToHost, st));
-    launch_cell_msm(cc->pts.p, cc->d_table, cc->c, cc->scalars.p, 1, st);
+    launch_cell_msm(cc->pts.p, cc->d_table, cc->c, cc->scalars.p, 1, cc->msm_scratch.p, st);
     launch_msm_finalize(tmp.p, nullptr, cc->pts.p, 1, N_CELLS, st);
     CU_TRY(cudaMemcpyAsync(hhat48, tmp.p, (size_t)N_CELLS * 48, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));

@@ -19,7 +19,7 @@ void launch_cell_twiddles(void* d_tw8192, cudaStream_t st);                     
 void launch_cell_twiddle_naf(void* d_naf, cudaStream_t st);                       // 128 x CELL_NAF_WORDS u32
 // pts[v * 64 + b] = s_(64 (62 - v) + b) for v <= 62, infinity above: the 64 reversed, strided, zero-padded SRS columns
 void launch_cell_srs_columns(void* d_pts_xyzz, const void* d_srs_monomial_aff, cudaStream_t st);
-// out[j * 64 + b] = affine(pts[brp7(j) * 64 + b]): the FK20 points in MSM order
+// out[(j / 64) * 4096 + b * 64 + j % 64] = affine(pts[brp7(j) * 64 + b]): the FK20 points in MSM order
 void launch_cell_fk20_points(void* d_aff_out, const void* d_pts_xyzz, cudaStream_t st);
 
 // ---- G1 FFT of size 128 over `batch` independent vectors, one stage per launch; pts[idx * batch + item] (XYZZ).
@@ -34,11 +34,17 @@ void launch_cell_g1_fft_stage(void* d_pts, int batch, int half, bool dif, bool i
 // 1 = evaluations little-endian, 2 = evaluations big-endian (Deneb).  Non-canonical words are the caller's to flag
 // (launch_le_blob_check); here they are reduced.
 void launch_cell_poly(void* d_coef, void* d_cells, const void* d_blobs, int n, int mode, const void* d_tw8192, cudaStream_t st);
-// FK20 scalars: for every offset b the circulant vector of coefficient column b, DFT_128, scaled by 1/128, canonical:
-// d_scalars[((blob * 128 + j) * 64 + b) * 8 .. +8]
+// FK20 scalars: for every offset b the circulant vector of coefficient column b, DFT_128, scaled by 1/128, canonical.
+// Frequency j = 64 v + j', offset b  ->  d_scalars[((v * n + blob) * 4096 + b * 64 + j') * 8 .. +8]: each half v is a
+// "blob" of 4096 scalars for the fixed-base MSM kernels, over the half's own table of the points X[v][b * 64 + j']
 void launch_cell_toeplitz(void* d_scalars, const void* d_coef, int n, const void* d_tw8192, cudaStream_t st);
-// Hhat[j * n + blob] = sum_b scalars[blob][j][b] * X[j * 64 + b] over the GLV digit table of the 8192 FK20 points
-void launch_cell_msm(void* d_pts_xyzz, const void* d_table, int c, const void* d_scalars, int n, cudaStream_t st);
+// Hhat[j * n + blob] = sum_b scalar(blob, j, b) * X(j, b) over the two GLV digit tables (one per half of the frequencies,
+// cell_table_half_entries(c) entries each, back to back).  n >= CELL_BA_MIN_BLOBS: the batched-affine kernel in its
+// segmented form, two launches; below: one warp per (blob, frequency).  d_scratch: cell_msm_scratch_bytes(n)
+constexpr int CELL_BA_MIN_BLOBS = 224;
+size_t cell_table_half_entries(int c);
+size_t cell_msm_scratch_bytes(int n);
+void launch_cell_msm(void* d_pts_xyzz, const void* d_table, int c, const void* d_scalars, int n, void* d_scratch, cudaStream_t st);
 // proofs[(blob * 128 + i) * 48] = compress(pts[brp7(i) * n + blob])
 void launch_cell_proofs_finalize(void* d_proofs48, const void* d_pts_xyzz, int n, cudaStream_t st);
 

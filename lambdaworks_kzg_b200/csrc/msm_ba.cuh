@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t ba_entry_of(uint32_t code, int c, int nwin, 
 
 template <bool BE, int K, int TH, bool PF>
 __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
-                                                   uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top) {
+                                                   uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride) {
   static_assert(K <= 64, "slot masks are 64 bits wide");
   static_assert(48 * (TH / 2) * 4 <= BA_STAGE_WORDS * TH * 16, "the block-reduction scratch aliases the staging area");
   constexpr int HT = TH / 2;              // threads per GLV half
@@ -295,6 +295,20 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
     xyzz_madd_hot(acc, a);
   }
   __syncthreads();   // the reduction scratch aliases the staging columns
+  if (seg_stride > 0) {
+    // segmented form (FK20 cell proofs, cells.cu): thread hl of either half holds the sum over the points
+    // pi = hl (mod HT), which the caller arranged to be ONE small MSM; the two GLV halves of segment hl meet
+    // (psi on the q-half) and the block writes HT results instead of one: partials[hl * seg_stride + blob]
+    if (half == 1) xyzz_to_smem(red, HT, hl, acc);
+    __syncthreads();
+    if (half == 0) {
+      G1Xyzz o = xyzz_from_smem(red, HT, hl);
+      xyzz_psi_ni(o);
+      xyzz_add_ni(acc, o);
+      partials[(size_t)hl * seg_stride + blob] = acc;
+    }
+    return;
+  }
   block_reduce_xyzz_glv<TH>(acc, red);
   if (tid == 0) partials[blob] = acc;
 }
@@ -304,25 +318,25 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
 template <bool BE, int K, int MINB, int TH, bool PF>
 __global__ void __launch_bounds__(TH, MINB)
 msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
-                     uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top) {
-  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top);
+                     uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride) {
+  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top, seg_stride);
 }
 template <bool BE, int K, int REGS, int TH, bool PF>
 __global__ void __maxnreg__(REGS)
 msm_gather_ba_kernel_r(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
-                       uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top) {
-  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top);
+                       uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride) {
+  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top, seg_stride);
 }
 
 template <int K, int MINB, int TH>
 static void launch_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
-                      void* d_scratch, cudaStream_t st) {
+                      void* d_scratch, cudaStream_t st, int seg_stride = 0) {
   const int nwin = glv_num_windows(c);
   const uint32_t cnt_top = glv_top_max(c) + 1u;
   constexpr size_t smem = ba_smem_bytes<K, TH>();
   static bool attr_set = false;
-  void (*kbe)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t);
-  void (*kle)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t);
+  void (*kbe)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t, int);
+  void (*kle)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t, int);
   if constexpr (MINB > 0) {
     kbe = msm_gather_ba_kernel<true, K, MINB, TH, LWKZG_BA_PREFETCH>;
     kle = msm_gather_ba_kernel<false, K, MINB, TH, LWKZG_BA_PREFETCH>;
@@ -338,9 +352,9 @@ static void launch_ba(void* d_partials, const void* d_table, int c, const void* 
     attr_set = true;
   }
   if (be_input)
-    kbe<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top);
+    kbe<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top, seg_stride);
   else
-    kle<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top);
+    kle<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top, seg_stride);
 }
 
 }  // namespace lw

@@ -298,3 +298,23 @@ def test_fk20_stages_against_the_exponent_model(lw, s2, o2):
     for p in range(128):
         want = bls.g1_mul(bls.G1, H[_bitrev(p, 7)]) if p % 2 == 0 else None
         assert h[p] == bls.g1_compress(want), p
+
+
+def test_large_batch_kernel_equals_small_batch_kernel(lw, s2):
+    """From 224 blobs up the FK20 MSMs run on the batched-affine kernel in its segmented form; below, one warp per
+    (blob, frequency).  Same bytes either way, including degenerate blobs inside the large batch."""
+    n = 230
+    blobs = [lw.synth_blob_host(900 + k) for k in range(n)]
+    blobs[5] = bytes(B)                                   # zero polynomial: every proof infinity
+    blobs[77] = (9).to_bytes(32, "big") * 4096            # constant
+    blobs[229] = bytes(32 * 4095) + (1).to_bytes(32, "big")
+    _, big, st = lw.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n, s2, want_cells=False)
+    assert st == [0] * n
+    lw.set_option("cell_chunk_blobs", 100)               # passes of 100 + 100 + 30 blobs: the warp-per-frequency kernel
+    try:
+        _, small, st = lw.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n, s2, want_cells=False)
+    finally:
+        lw.set_option("cell_chunk_blobs", 864)
+    assert st == [0] * n and big == small
+    inf = bytes([0xC0]) + bytes(47)
+    assert big[5 * 6144: 6 * 6144] == inf * 128 and big[77 * 6144: 78 * 6144] == inf * 128
