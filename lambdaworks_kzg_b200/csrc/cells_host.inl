@@ -53,7 +53,7 @@ bool cell_ctx_build(Ctx* c) {
     CU_TRY(cudaStreamCreateWithFlags(&cc->st, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&cc->ev, cudaEventDisableTiming));
     CU_TRY(cudaMalloc(&cc->d_tw, (size_t)EXT_POINTS * 32));
-    CU_TRY(cudaMalloc(&cc->d_naf, (size_t)128 * CELL_NAF_WORDS * 4));
+    CU_TRY(cudaMalloc(&cc->d_naf, (size_t)128 * CELL_NAF_BYTES));
     launch_cell_twiddles(cc->d_tw, cc->st);
     launch_cell_twiddle_naf(cc->d_naf, cc->st);
     // g2[64]

@@ -12,11 +12,11 @@ constexpr int N_CELLS = 128;
 constexpr int CELL_ELEMS = 64;
 constexpr int CELL_BYTES = 2048;
 constexpr int EXT_POINTS = 8192;          // FIELD_ELEMENTS_PER_EXT_BLOB = FK20 points (64 offsets x 128 frequencies)
-constexpr int CELL_NAF_WORDS = 20;        // per 128th root of unity: {m, q} x {+, -} x 160-bit digit mask
+constexpr int CELL_NAF_BYTES = 320;       // per 128th root of unity: 160 width-4 NAF digits (int8) of each GLV half
 
 // ---- setup
 void launch_cell_twiddles(void* d_tw8192, cudaStream_t st);                       // w^k, k < 8192 (Montgomery), w = FR_ROOT_8192
-void launch_cell_twiddle_naf(void* d_naf, cudaStream_t st);                       // 128 x CELL_NAF_WORDS u32
+void launch_cell_twiddle_naf(void* d_naf, cudaStream_t st);                       // 128 x CELL_NAF_BYTES
 // pts[v * 64 + b] = s_(64 (62 - v) + b) for v <= 62, infinity above: the 64 reversed, strided, zero-padded SRS columns
 void launch_cell_srs_columns(void* d_pts_xyzz, const void* d_srs_monomial_aff, cudaStream_t st);
 // out[(j / 64) * 4096 + b * 64 + j % 64] = affine(pts[brp7(j) * 64 + b]): the FK20 points in MSM order
