@@ -22,7 +22,7 @@ The JSON line (rank 0):
   msm_sweep     BASELINE config 5: variable-base G1 MSM 2^12 .. 2^22, points/s and roofline fraction per size, next to
                 the CPU restatement's g1_lincomb
   latency       single-call latency of every c-kzg entry point, GPU vs the CPU restatement
-  cells         PeerDAS / EIP-7594 in the mainnet wire format: cells + FK20 cell proofs of 864 blobs (device-resident and
+  cells         PeerDAS / EIP-7594 in the mainnet wire format: cells + FK20 cell proofs of 888 blobs (device-resident and
                 through the host API), verify / recover latencies, checked against committed known answers
   cpu_baseline  the C restatement of the reference's CPU path (oracle/c) on a bounded sample of the same workload
 
@@ -51,7 +51,7 @@ IMAD_NOMINAL = 148 * 64 * 1.965e9  # SURVEY §8d sanity ceiling: one IMAD.WIDE p
 METRIC = "blobs/sec commit+proof"
 UNIT = "blobs/s"
 VERIFY_BLOBS = 4096
-CELL_BLOBS = 864          # PeerDAS block: blobs per compute_cells_and_kzg_proofs batch (one pass; 864 x 128 = 110592 cell proofs)
+CELL_BLOBS = 888          # PeerDAS block: blobs per compute_cells_and_kzg_proofs batch (one pass; 888 x 128 = 113664 cell proofs)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE 1024-blob launch of msm_gather_ba_kernel from the ncu --set full
 # capture committed as profiles/r02_ncu_ba_staged_1024blob_raw.csv
 NCU_DRAM_BYTES_PER_BLOB = (35.42e9 + 9.33e9) / 1024

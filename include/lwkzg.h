@@ -325,7 +325,7 @@ int lwkzg_table_share(const KZGSettings *s);
  * ones attached to it.  A disk cache is deliberately absent: the GPU rebuilds the table at 26 GiB/s, faster than any
  * disk delivers it.  Cells: "cell_window_bits" (window of the FK20 digit table over 8192
  * points, 4..14, default 13 = 29 GiB, shrunk to what free device memory allows), "cell_chunk_blobs" (blobs per
- * pass of a cell batch, default 864: one full wave of the G1 FFT stage kernel).
+ * pass of a cell batch, default 888: two full waves of the MSM kernel, one of the G1 FFT stage kernel).
  * Returns 0 on success. */
 int lwkzg_set_option(const char *name, long value);
 long lwkzg_get_option(const char *name);

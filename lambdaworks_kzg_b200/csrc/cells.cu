@@ -257,7 +257,7 @@ __device__ __noinline__ void g1_mul_root(G1Xyzz& t, const int8_t* __restrict__ n
 }
 
 #ifndef LWKZG_CELL_FFT_MIN_BLOCKS
-#define LWKZG_CELL_FFT_MIN_BLOCKS 6
+#define LWKZG_CELL_FFT_MIN_BLOCKS 8   // 128 registers, 16 warps per SM: +5 % over 6 blocks / 168 registers (B200, profiles/r02_cells_chunk_sweep.log)
 #endif
 __global__ void __launch_bounds__(64, LWKZG_CELL_FFT_MIN_BLOCKS)
 cell_g1_fft_stage_kernel(G1Xyzz* __restrict__ pts, int batch, int batch_pad, int half, int dif, int inverse, int upper_half_zero,

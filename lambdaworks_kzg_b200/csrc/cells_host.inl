@@ -154,16 +154,8 @@ bool cell_enqueue_chunk(Ctx* c, const void* d_blobs, int m, void* d_cells, void*
   return true;
 }
 
-C_KZG_RET cells_host_batch(const KZGSettings* s, size_t n, const Blob* blobs, Cell* cells_out, KZGProof* proofs_out, int* status) {
-  if (n == 0) return C_KZG_OK;
-  if (!blobs || (!cells_out && !proofs_out)) { set_err("null argument"); return C_KZG_BADARGS; }
-  Ctx* c = ctx_of(s);
-  if (!c) return C_KZG_ERROR;
-  if (!c->srs_valid) {
-    set_err("SRS re-hydration failed: g1_values holds a point that is not on the curve");
-    if (status) for (size_t i = 0; i < n; i++) status[i] = C_KZG_ERROR;
-    return C_KZG_ERROR;
-  }
+// host buffers, ONE device; status[n] receives one code per blob
+C_KZG_RET cells_host_batch_on(Ctx* c, size_t n, const Blob* blobs, Cell* cells_out, KZGProof* proofs_out, int* status) {
   CtxLock lock(c);
   if (!cell_ctx_build(c)) return C_KZG_ERROR;
   CellCtx* cc = c->cell;
@@ -213,10 +205,68 @@ C_KZG_RET cells_host_batch(const KZGSettings* s, size_t n, const Blob* blobs, Ce
       } else if (first == C_KZG_OK) {
         first = (C_KZG_RET)h_status[i];
       }
-      if (status) status[off + i] = h_status[i];
+      status[off + i] = h_status[i];
     }
   }
-  if (!status && first != C_KZG_OK) { set_err("invalid blob"); return first; }
+  (void)first;
+  return C_KZG_OK;
+}
+
+// Host-buffer cell batches: one device, or -- after lwkzg_set_devices -- contiguous shards of the blobs on every
+// listed GPU (cells and proofs of different blobs are independent: no exchange), one host thread per device.
+C_KZG_RET cells_host_batch(const KZGSettings* s, size_t n, const Blob* blobs, Cell* cells_out, KZGProof* proofs_out, int* status) {
+  if (n == 0) return C_KZG_OK;
+  if (!blobs || (!cells_out && !proofs_out)) { set_err("null argument"); return C_KZG_BADARGS; }
+  Ctx* c = ctx_of(s);
+  if (!c) return C_KZG_ERROR;
+  if (!c->srs_valid) {
+    set_err("SRS re-hydration failed: g1_values holds a point that is not on the curve");
+    if (status) for (size_t i = 0; i < n; i++) status[i] = C_KZG_ERROR;
+    return C_KZG_ERROR;
+  }
+  std::vector<int> st_own;
+  int* st = status;
+  if (!st) { st_own.assign(n, 0); st = st_own.data(); }
+  C_KZG_RET rc = C_KZG_OK;
+  std::vector<Ctx*> ctxs = n >= 2 ? ctxs_for(c) : std::vector<Ctx*>{c};
+  if (ctxs.size() > 1 && n >= 2 * ctxs.size()) {
+    // replicas are built from the host arrays, which hold the Lagrange points in the Lagrange modes: hand them the
+    // monomial points the primary context kept
+    for (Ctx* r : ctxs) {
+      if (r == c || r->d_mono || !c->d_mono) continue;
+      std::lock_guard<std::mutex> lk(r->mu);
+      DeviceGuard dg(r->device);
+      if (cudaMalloc(&r->d_mono, (size_t)N_POINTS * AFFINE_BYTES) != cudaSuccess ||
+          cudaMemcpyPeer(r->d_mono, r->device, c->d_mono, c->device, (size_t)N_POINTS * AFFINE_BYTES) != cudaSuccess) {
+        set_err("could not replicate the monomial SRS");
+        return C_KZG_ERROR;
+      }
+      r->mono_owned = true;
+    }
+    const size_t g = ctxs.size();
+    std::vector<C_KZG_RET> rcs(g, C_KZG_OK);
+    std::vector<std::string> errs(g);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < g; k++)
+      th.emplace_back([&, k]() {
+        size_t first, cnt;
+        shard_of(n, g, k, first, cnt);
+        if (!cnt) return;
+        rcs[k] = cells_host_batch_on(ctxs[k], cnt, blobs + first, cells_out ? cells_out + first * N_CELLS : nullptr,
+                                     proofs_out ? proofs_out + first * N_CELLS : nullptr, st + first);
+        if (rcs[k] != C_KZG_OK) errs[k] = tl_err;
+      });
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < g; k++)
+      if (rcs[k] != C_KZG_OK && rc == C_KZG_OK) { rc = rcs[k]; set_err(errs[k]); }
+  } else {
+    rc = cells_host_batch_on(c, n, blobs, cells_out, proofs_out, st);
+  }
+  if (rc != C_KZG_OK) return rc;
+  if (!status) {
+    for (size_t i = 0; i < n; i++)
+      if (st[i]) { set_err("invalid blob"); return (C_KZG_RET)st[i]; }
+  }
   return C_KZG_OK;
 }
 

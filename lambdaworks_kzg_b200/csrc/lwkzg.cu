@@ -58,8 +58,8 @@ struct Options {
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
   long share_table = 0;              // 1 = one digit table per (SRS, window, device) for every settings object and PROCESS that loads it
   long cell_window_bits = 13;        // window of the FK20 digit table (8192 points; 13 bits = 29 GiB), shrunk to what free HBM allows
-  long cell_chunk_blobs = 864;       // blobs per pass of a cell batch: 27 x 32 blobs x 64 butterflies = 1728 warps per G1 FFT stage, one wave of the
-                                     // 12 x 148 = 1776 warp slots the stage kernel gets
+  long cell_chunk_blobs = 888;       // blobs per pass of a cell batch: 2 x 444 = exactly two waves of the batched-affine MSM kernel, and 28 x 32 blobs
+                                     // x 64 butterflies = 1792 warps per G1 FFT stage, one wave of the 16 x 148 warp slots the stage kernel gets
   long mode = 0;  // 0 = MODE_REFERENCE (what lambdaworks_kzg computes), 1 = MODE_CKZG_LE (what the YAML vectors encode),
                   // 2 = MODE_DENEB (the mainnet wire format: big-endian canonical scalars over the Lagrange SRS)
   Options() {

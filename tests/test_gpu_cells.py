@@ -125,7 +125,7 @@ def test_batch_and_device_api_equal_single_calls(lw, s2, blob11):
     try:
         cells, proofs, st = lw.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n, s2)
     finally:
-        lw.set_option("cell_chunk_blobs", 864)
+        lw.set_option("cell_chunk_blobs", 888)
     assert st == [0, 0, 0, lw.C_KZG_BADARGS, 0]
     for i in range(n):
         if i == 3:
@@ -314,7 +314,22 @@ def test_large_batch_kernel_equals_small_batch_kernel(lw, s2):
     try:
         _, small, st = lw.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n, s2, want_cells=False)
     finally:
-        lw.set_option("cell_chunk_blobs", 864)
+        lw.set_option("cell_chunk_blobs", 888)
     assert st == [0] * n and big == small
     inf = bytes([0xC0]) + bytes(47)
     assert big[5 * 6144: 6 * 6144] == inf * 128 and big[77 * 6144: 78 * 6144] == inf * 128
+
+
+def test_cells_in_library_multi_device_byte_equality():
+    """lwkzg_set_devices: a cell batch sharded over every visible GPU from one process equals the single-device bytes."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "multi_device_cells_check.py")], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "MULTI_DEVICE_CELLS_OK" in p.stdout
