@@ -318,7 +318,8 @@ int lwkzg_table_share(const KZGSettings *s);
  * be128(4096) || blob || commitment, batch challenge domain || be64(4096) || be64(n) || tuples, digests read
  * big-endian).  The mode is captured when a KZGSettings is
  * loaded / first used.  Env: LWKZG_WINDOW_BITS, LWKZG_CHUNK_BLOBS, LWKZG_MODE,
- * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS, LWKZG_SHARE_TABLE.  "share_table" (default 0; SURVEY 8 f2's table cache): 1 = the
+ * LWKZG_MSM_ALGO, LWKZG_MSM_BA_MIN_BLOBS, LWKZG_SHARE_TABLE.  "verify_streams" (compute streams a batched verification
+ * spreads its chunks over, default 6).  "share_table" (default 0; SURVEY 8 f2's table cache): 1 = the
  * digit table is keyed by (SRS contents, window, device) and held ONCE per GPU -- settings objects of one process share
  * it by reference count, other processes attach to it through a CUDA IPC handle published under /dev/shm (attaching
  * takes milliseconds instead of the 3.8 s build and no further 100 GiB); the process that built it must outlive the

@@ -58,6 +58,9 @@ struct Options {
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
+  long verify_streams = 6;           // compute streams a batched verification spreads its chunks over (1..8).  Measured on B200, 4096 blobs:
+                                     // 8 streams 25.5-27.8 ms device-resident (a chunk's hash kernel takes 13 ms instead of 2.5 now and then), 4-6
+                                     // streams 21.0 ms, 3 streams 24.4 ms; from pinned memory 20.9-21.4 ms either way
   long share_table = 0;              // 1 = one digit table per (SRS, window, device) for every settings object and PROCESS that loads it
   long cell_window_bits = 13;        // window of the FK20 digit table (8192 points; 13 bits = 29 GiB), shrunk to what free HBM allows
   long cell_chunk_blobs = 888;       // blobs per pass of a cell batch: 2 x 444 = exactly two waves of the batched-affine MSM kernel, and 28 x 32 blobs
@@ -1288,6 +1291,14 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     return true;
   };
   cudaStream_t cs[2 * NSLOT];
+  // how many of them are used: with the copy stream, the hash stream and the caller's stream, more than eight streams
+  // share hardware queues (CUDA_DEVICE_MAX_CONNECTIONS defaults to 8) and chunks serialise behind the sequential
+  // batch-challenge launches of a stream they have nothing to do with
+  int ncs;
+  {
+    std::lock_guard<std::mutex> lk2(g_mu);
+    ncs = (int)std::min<long>(std::max<long>(opts().verify_streams, 1), 2 * NSLOT);
+  }
   for (int i = 0; i < NSLOT; i++) { cs[2 * i] = c->slot[i].st; cs[2 * i + 1] = c->slot[i].aux; }
   auto sync_all = [&]() -> bool {
     CU_TRY(cudaStreamSynchronize(c->copy_st));
@@ -1317,7 +1328,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
       const uint8_t* d_blobs = dev_inputs ? (const uint8_t*)blobs + off * BLOB_BYTES : (const uint8_t*)c->vb_blobs.p + (off - base) * BLOB_BYTES;
       void* d_states = (uint8_t*)c->vb_states.p + off * 32;
       cudaEvent_t ev_copied = c->ev_pool[2 * j], ev_tuples = c->ev_pool[2 * j + 1];
-      cudaStream_t st = cs[(k + 1) % (2 * NSLOT)];   // chunk 0 not on s0: its hash runs beside the commitment decompression
+      cudaStream_t st = cs[(k + 1) % ncs];   // chunk 0 not on s0: its hash runs beside the commitment decompression
       if (!dev_inputs) {
         if (pageable) {
           if (!c->ring.h2d((void*)d_blobs, blobs + off, (size_t)m * BLOB_BYTES, c->ring_seq++, c->copy_st)) return false;
@@ -1361,7 +1372,7 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
       }
     }
   }
-  if (trace) { cudaEventRecord(tr[1], c->copy_st); cudaEventRecord(tr[2], c->hash_st); cudaEventRecord(tr[4], cs[k % (2 * NSLOT)]); }
+  if (trace) { cudaEventRecord(tr[1], c->copy_st); cudaEventRecord(tr[2], c->hash_st); cudaEventRecord(tr[4], cs[k % ncs]); }
   if (!sync_all()) return false;
   if (trace) {
     cudaStreamSynchronize(c->hash_st);
@@ -1441,6 +1452,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "verify_super_blobs") { if (value < 1) return 1; opts().verify_super_blobs = value; return 0; }
   if (n == "lincomb_points_in_g1") { if (value != 0 && value != 1) return 1; opts().lincomb_points_in_g1 = value; return 0; }
   if (n == "share_table") { if (value != 0 && value != 1) return 1; opts().share_table = value; return 0; }
+  if (n == "verify_streams") { if (value < 1 || value > 8) return 1; opts().verify_streams = value; return 0; }
   if (n == "cell_window_bits") { if (value < 4 || value > 14) return 1; opts().cell_window_bits = value; return 0; }
   if (n == "cell_chunk_blobs") { if (value < 1 || value > 65536) return 1; opts().cell_chunk_blobs = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
@@ -1458,6 +1470,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "verify_super_blobs") return opts().verify_super_blobs;
   if (n == "lincomb_points_in_g1") return opts().lincomb_points_in_g1;
   if (n == "share_table") return opts().share_table;
+  if (n == "verify_streams") return opts().verify_streams;
   if (n == "cell_window_bits") return opts().cell_window_bits;
   if (n == "cell_chunk_blobs") return opts().cell_chunk_blobs;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel

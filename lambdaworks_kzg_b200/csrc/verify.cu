@@ -361,9 +361,11 @@ void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, c
   count_launch();
 }
 static int bch_wire_flags(int wire) { return wire == 1 ? BCH_LE : wire == 2 ? BCH_BE_HDR : 0; }
+// (measured and not kept: giving this one-warp kernel an SM of its own by asking for all of the SM's shared memory --
+// no change; what slowed the device-resident batch was eight chunk streams at once, see "verify_streams")
 void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, int wire) {
   batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, nullptr, (const uint8_t*)d_tuples160, (unsigned long long)n_total, 0, 0,
-                                           BCH_INIT | BCH_FINAL | bch_wire_flags(wire));
+                                                              BCH_INIT | BCH_FINAL | bch_wire_flags(wire));
   count_launch();
 }
 size_t batch_challenge_state_bytes() { return sizeof(Sha256State); }
@@ -371,8 +373,8 @@ int batch_challenge_blocks_ready(size_t tuples_ready) { return (int)((32 + 160 *
 void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples160, size_t n_total, int blk0, int blk1, bool first, bool last,
                                  cudaStream_t st, int wire) {
   if (!last && blk1 <= blk0 && !first) return;
-  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (Sha256State*)d_state, (const uint8_t*)d_tuples160, (unsigned long long)n_total, blk0, blk1,
-                                           (first ? BCH_INIT : 0) | (last ? BCH_FINAL : 0) | bch_wire_flags(wire));
+  batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (Sha256State*)d_state, (const uint8_t*)d_tuples160, (unsigned long long)n_total,
+                                                              blk0, blk1, (first ? BCH_INIT : 0) | (last ? BCH_FINAL : 0) | bch_wire_flags(wire));
   count_launch();
 }
 struct RlcLayout { size_t sc_a, sc_b, pts_b, ypart, ticket, msm_a, msm_b, total; };
