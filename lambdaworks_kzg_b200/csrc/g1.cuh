@@ -312,7 +312,9 @@ LW_COLD bool g1_in_subgroup(const G1Affine& p) {
 
 // /root/reference/src/compression.rs:62-103.  Returns false
 // on any rejection.  *out is affine; infinity -> (0,0).
-LW_COLD bool g1_decompress(G1Affine& out, const uint8_t* in48) {
+// check_subgroup = false leaves the r-torsion test to the caller (g1_in_subgroup): batched verification runs it
+// beside the blob hashes instead of in front of them
+LW_COLD bool g1_decompress(G1Affine& out, const uint8_t* in48, bool check_subgroup = true) {
   uint8_t b0 = in48[0];
   if (!(b0 & 0x80)) return false;
   if (b0 & 0x40) { out = g1a_inf(); return true; }  // remaining bits unchecked, like the reference
@@ -329,12 +331,12 @@ LW_COLD bool g1_decompress(G1Affine& out, const uint8_t* in48) {
   // y == 0 cannot happen (no 2-torsion); if it did both roots coincide.
   if (large != want_large) y = fp_neg(y);
   out.x = x; out.y = y;
-  return g1_in_subgroup(out);
+  return check_subgroup ? g1_in_subgroup(out) : true;
 }
 
 // Strict (ZCash / blst, as c-kzg-4844 requires) variant for MODE_CKZG_LE:
 // infinity must be encoded exactly as c0 00..00 and x must be canonical (< p).
-LW_COLD bool g1_decompress_strict(G1Affine& out, const uint8_t* in48) {
+LW_COLD bool g1_decompress_strict(G1Affine& out, const uint8_t* in48, bool check_subgroup = true) {
   uint8_t b0 = in48[0];
   if (!(b0 & 0x80)) return false;
   if (b0 & 0x40) {
@@ -351,7 +353,7 @@ LW_COLD bool g1_decompress_strict(G1Affine& out, const uint8_t* in48) {
   }
   xc.l[11] &= 0x1FFFFFFFu;
   if (!limbs_lt<12>(xc.l, k::FP_MOD)) return false;
-  return g1_decompress(out, in48);
+  return g1_decompress(out, in48, check_subgroup);
 }
 
 }  // namespace lw

@@ -65,7 +65,10 @@ void launch_poly_eval_quot(void* d_q, void* d_y, void* d_y_be32, const void* d_b
 // ---- point codecs (codec.cu)
 // status[i] = 0 ok / 2 (C_KZG_ERROR) rejected.  d_aff (Montgomery, may be NULL),
 // d_recompressed48 (canonical re-encoding, may be NULL)
-void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st, bool strict = false);
+void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st, bool strict = false,
+                          bool check_subgroup = true);
+// the r-torsion test of points decoded with check_subgroup = false (d_aff must not be NULL there): status 0 / 2 (1 if strict)
+void launch_g1_subgroup_check(int* d_status, const void* d_aff, int n, cudaStream_t st, bool strict = false);
 void launch_status_or(int* d_status, const int* d_other, int n, cudaStream_t st);
 void launch_zero_failed(void* d_out, int bytes_per_item, const int* d_status, int n, cudaStream_t st);
 

@@ -58,6 +58,9 @@ struct Options {
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
+  long verify_split_subgroup = 0;    // 1 = batched verification runs the r-torsion tests of the points beside the first blob hashes instead of in front
+                                     // of them.  Measured and not kept as the default: device-resident 20.8 -> 20.8 ms, from pinned memory 21.2 -> 25 ms
+                                     // (blob-hash kernels that run beside the thread-per-point kernels take several times longer)
   long verify_streams = 6;           // compute streams a batched verification spreads its chunks over (1..8).  Measured on B200, 4096 blobs:
                                      // 8 streams 25.5-27.8 ms device-resident (a chunk's hash kernel takes 13 ms instead of 2.5 now and then), 4-6
                                      // streams 21.0 ms, 3 streams 24.4 ms; from pinned memory 20.9-21.4 ms either way
@@ -264,7 +267,7 @@ struct Ctx {
   cudaStream_t hash_st = nullptr, copy_st = nullptr;
   cudaEvent_t ev_hash = nullptr;
   std::vector<cudaEvent_t> ev_pool;   // per chunk: blob copy landed / tuples written
-  DevBuf vb_hstate, vb_blobs, vb_states, vb_status2;
+  DevBuf vb_hstate, vb_blobs, vb_states, vb_status2, vb_sub;
   // pinned host staging for batch results: a D2H copy into pageable memory would block the host
   // until the chunk's kernels finish and serialise the two pipeline slots
   void* h_stage = nullptr;
@@ -363,7 +366,7 @@ void destroy_ctx(Ctx* c) {
   }
   if (c->hash_st) cudaStreamSynchronize(c->hash_st);
   for (DevBuf* b : {&c->vb_cin, &c->vb_pin, &c->vb_caff, &c->vb_piaff, &c->vb_c48r, &c->vb_p48r, &c->vb_z, &c->vb_y, &c->vb_tuples, &c->vb_status,
-                    &c->vb_r, &c->vb_partial, &c->vb_scratch, &c->vb_ok, &c->vb_zy_in, &c->vb_hstate, &c->vb_blobs, &c->vb_states, &c->vb_status2})
+                    &c->vb_r, &c->vb_partial, &c->vb_scratch, &c->vb_ok, &c->vb_zy_in, &c->vb_hstate, &c->vb_blobs, &c->vb_states, &c->vb_status2, &c->vb_sub})
     b->release();
   if (c->ev_hash) cudaEventDestroy(c->ev_hash);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1264,15 +1267,33 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   // latency-bound thread-per-point kernels and run side by side
   CU_TRY(cudaMemcpyAsync(c->vb_cin.p, commitments, n * 48, in_kind, s0));
   CU_TRY(cudaMemcpyAsync(c->vb_pin.p, proofs, n * 48, in_kind, c->hash_st));
-  launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0, le);
+  // Large batches: decoding (a square root) gates the blob hashes, the r-torsion tests (two thirds of a decompression)
+  // do not -- they run beside the first chunks on the two compute streams the chunks leave free and are merged into
+  // the status array at the end.
+  bool split;
+  {
+    std::lock_guard<std::mutex> lk2(g_mu);
+    split = opts().verify_split_subgroup != 0 && n > 64 && opts().verify_streams <= 2 * NSLOT - 2;
+  }
+  if (split && !c->vb_sub.ensure(2 * n * sizeof(int))) return false;
+  launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0, le, !split);
   // proofs: decode status into the (still unused) tuples buffer, then merge
-  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, c->hash_st, le);
+  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, c->hash_st, le, !split);
   CU_TRY(cudaEventRecord(c->ev_hash, c->hash_st));
   CU_TRY(cudaStreamWaitEvent(s0, c->ev_hash, 0));
   launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, (int)n, s0);
   // the blob copies and SHA midstates do not need the decoded points: only the challenge tail does, so the
   // slot streams wait for the decompression through an event instead of the host waiting here
   CU_TRY(cudaEventRecord(c->slot[0].ev_in, s0));
+  if (split) {
+    cudaStream_t sa = c->slot[NSLOT - 1].st, sb = c->slot[NSLOT - 1].aux;
+    CU_TRY(cudaStreamWaitEvent(sa, c->slot[0].ev_in, 0));
+    CU_TRY(cudaStreamWaitEvent(sb, c->slot[0].ev_in, 0));
+    launch_g1_subgroup_check((int*)c->vb_sub.p, c->vb_caff.p, (int)n, sa, le);
+    launch_g1_subgroup_check((int*)c->vb_sub.p + n, c->vb_piaff.p, (int)n, sb, le);
+    CU_TRY(cudaEventRecord(c->slot[NSLOT - 1].ev_done, sa));
+    CU_TRY(cudaEventRecord(c->slot[NSLOT - 1].ev_aux, sb));
+  }
   // Blobs land in a verify-owned staging area big enough for a whole super-batch, so no chunk ever waits for a
   // buffer: one copy stream issues the H2D copies back to back, and each chunk's kernels (SHA midstate ->
   // challenge -> evaluation -> tuple) start on one of 2 * NSLOT compute streams as soon as its copy has landed.
@@ -1373,6 +1394,12 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     }
   }
   if (trace) { cudaEventRecord(tr[1], c->copy_st); cudaEventRecord(tr[2], c->hash_st); cudaEventRecord(tr[4], cs[k % ncs]); }
+  if (split) {
+    CU_TRY(cudaStreamWaitEvent(s0, c->slot[NSLOT - 1].ev_done, 0));
+    CU_TRY(cudaStreamWaitEvent(s0, c->slot[NSLOT - 1].ev_aux, 0));
+    launch_status_or((int*)c->vb_status.p, (const int*)c->vb_sub.p, (int)n, s0);
+    launch_status_or((int*)c->vb_status.p, (const int*)c->vb_sub.p + n, (int)n, s0);
+  }
   if (!sync_all()) return false;
   if (trace) {
     cudaStreamSynchronize(c->hash_st);
@@ -1453,6 +1480,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "lincomb_points_in_g1") { if (value != 0 && value != 1) return 1; opts().lincomb_points_in_g1 = value; return 0; }
   if (n == "share_table") { if (value != 0 && value != 1) return 1; opts().share_table = value; return 0; }
   if (n == "verify_streams") { if (value < 1 || value > 8) return 1; opts().verify_streams = value; return 0; }
+  if (n == "verify_split_subgroup") { if (value != 0 && value != 1) return 1; opts().verify_split_subgroup = value; return 0; }
   if (n == "cell_window_bits") { if (value < 4 || value > 14) return 1; opts().cell_window_bits = value; return 0; }
   if (n == "cell_chunk_blobs") { if (value < 1 || value > 65536) return 1; opts().cell_chunk_blobs = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
@@ -1471,6 +1499,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "lincomb_points_in_g1") return opts().lincomb_points_in_g1;
   if (n == "share_table") return opts().share_table;
   if (n == "verify_streams") return opts().verify_streams;
+  if (n == "verify_split_subgroup") return opts().verify_split_subgroup;
   if (n == "cell_window_bits") return opts().cell_window_bits;
   if (n == "cell_chunk_blobs") return opts().cell_chunk_blobs;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel

@@ -19,8 +19,10 @@ d_st = torch.zeros(n, dtype=torch.int32, device=dev)
 lw.commit_and_prove_batch_device(d_c.data_ptr(), d_p.data_ptr(), d_blobs.data_ptr(), n, s, st, d_st.data_ptr())
 torch.cuda.synchronize()
 hb, hc, hp = d_blobs.cpu().pin_memory(), d_c.cpu().pin_memory(), d_p.cpu().pin_memory()
-for ns in [int(x) for x in os.environ.get("STREAMS", "8").split(",")]:
+for ns in [int(x) for x in os.environ.get("STREAMS", "6").split(",")]:
+  for split in [int(x) for x in os.environ.get("SPLIT", "1").split(",")]:
     lw.set_option("verify_streams", ns)
+    lw.set_option("verify_split_subgroup", split)
     for name, fn in (("device-resident", lambda: lw.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_c.data_ptr(), d_p.data_ptr(), n, s)),
                      ("pinned", lambda: lw.verify_blob_kzg_proof_batch_ptr(hb.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, s))):
         fn()
@@ -29,4 +31,4 @@ for ns in [int(x) for x in os.environ.get("STREAMS", "8").split(",")]:
             t = time.perf_counter()
             ok = fn()
             ts.append((time.perf_counter() - t) * 1e3)
-        print("streams=%d %s verify n=%d -> %s: min %.2f ms, median %.2f ms" % (ns, name, n, ok, min(ts), sorted(ts)[2]), flush=True)
+        print("split=%d streams=%d %s verify n=%d -> %s: min %.2f ms, median %.2f ms" % (split, ns, name, n, ok, min(ts), sorted(ts)[2]), flush=True)
