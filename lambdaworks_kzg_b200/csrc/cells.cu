@@ -140,8 +140,9 @@ __device__ __noinline__ void cell_add_c(G1Xyzz& a, const G1Xyzz& b, bool neg_b) 
   if (!xyzz_is_inf(b)) {
     const Fp by = fp_cneg(b.y, neg_b);
     if (xyzz_is_inf(a)) {
-      a = b;
-      a.y = by;
+      // unrolled limb copies, not a struct assignment: see the ptxas note in DESIGN 3.5
+#pragma unroll
+      for (int i = 0; i < 12; i++) { a.x.l[i] = b.x.l[i]; a.y.l[i] = by.l[i]; a.zz.l[i] = b.zz.l[i]; a.zzz.l[i] = b.zzz.l[i]; }
     } else {
       const Fp U1 = fp_mul_nv(a.x, b.zz), S1 = fp_mul_nv(a.y, b.zzz);
       const Fp Pd = fp_sub(fp_mul_nv(b.x, a.zz), U1), Rd = fp_sub(fp_mul_nv(by, a.zzz), S1);

@@ -184,9 +184,70 @@ LW_INL void xyzz_madd_hot(G1Xyzz& acc, const G1Affine& p) {
 
 // Out-of-line copies of the group law for cold callers (scalar-mul ladders,
 // verification, setup): the hot MSM loop keeps the force-inlined versions.
-LW_COLD void xyzz_madd_ni(G1Xyzz& acc, const G1Affine& p) { xyzz_madd(acc, p); }
-LW_COLD void xyzz_add_ni(G1Xyzz& a, const G1Xyzz& b) { xyzz_add(a, b); }
-LW_COLD void xyzz_dbl_ni(G1Xyzz& a) { a = xyzz_dbl(a); }
+// They are COMPACT as well: every field multiplication is a call to the one out-of-line multiplier, so each of
+// these is a few hundred bytes of SASS instead of 40-60 KB of inlined Montgomery products (the same formulas, the
+// same results).  The cold kernels run one warp per block all over the GPU, next to the hash kernels of the
+// pipelines; their instruction footprint is what they compete with.
+LW_COLD void xyzz_dbl_ni(G1Xyzz& p) {
+  if (!xyzz_is_inf(p)) {
+    const Fp U = fp_dbl(p.y), V = fp_sqr_nv(U), W = fp_mul_nv(U, V), S = fp_mul_nv(p.x, V), X2 = fp_sqr_nv(p.x);
+    const Fp M = fp_add(fp_dbl(X2), X2);
+    const Fp X3 = fp_sub(fp_sqr_nv(M), fp_dbl(S));
+    p.y = fp_sub(fp_mul_nv(M, fp_sub(S, X3)), fp_mul_nv(W, p.y));
+    p.x = X3;
+    p.zz = fp_mul_nv(V, p.zz);      // y == 0 (2-torsion) gives zz = 0 = infinity, as it should
+    p.zzz = fp_mul_nv(W, p.zzz);
+  }
+}
+LW_COLD void xyzz_madd_ni(G1Xyzz& acc, const G1Affine& p) {
+  if (!g1a_is_inf(p)) {
+    if (xyzz_is_inf(acc)) {
+      acc.x = p.x; acc.y = p.y; acc.zz = fp_one(); acc.zzz = fp_one();
+    } else {
+      const Fp Pd = fp_sub(fp_mul_nv(p.x, acc.zz), acc.x);
+      const Fp Rd = fp_sub(fp_mul_nv(p.y, acc.zzz), acc.y);
+      if (fp_is_zero(Pd)) {
+        if (fp_is_zero(Rd)) {
+          acc.x = p.x; acc.y = p.y; acc.zz = fp_one(); acc.zzz = fp_one();
+          xyzz_dbl_ni(acc);
+        } else {
+          acc = xyzz_inf();
+        }
+      } else {
+        const Fp PP = fp_sqr_nv(Pd), PPP = fp_mul_nv(Pd, PP), Q = fp_mul_nv(acc.x, PP);
+        const Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
+        acc.y = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(acc.y, PPP));
+        acc.x = X3;
+        acc.zz = fp_mul_nv(acc.zz, PP);
+        acc.zzz = fp_mul_nv(acc.zzz, PPP);
+      }
+    }
+  }
+}
+LW_COLD void xyzz_add_ni(G1Xyzz& a, const G1Xyzz& b) {
+  if (!xyzz_is_inf(b)) {
+    if (xyzz_is_inf(a)) {
+      // limb by limb, unrolled: ptxas 12.9 rolls a struct copy into a loop whose counter lives in a uniform register
+      // that the other side of this divergent branch uses for an operand address
+#pragma unroll
+      for (int i = 0; i < 12; i++) { a.x.l[i] = b.x.l[i]; a.y.l[i] = b.y.l[i]; a.zz.l[i] = b.zz.l[i]; a.zzz.l[i] = b.zzz.l[i]; }
+    } else {
+      const Fp U1 = fp_mul_nv(a.x, b.zz), S1 = fp_mul_nv(a.y, b.zzz);
+      const Fp Pd = fp_sub(fp_mul_nv(b.x, a.zz), U1), Rd = fp_sub(fp_mul_nv(b.y, a.zzz), S1);
+      if (fp_is_zero(Pd)) {
+        if (fp_is_zero(Rd)) xyzz_dbl_ni(a);
+        else a = xyzz_inf();
+      } else {
+        const Fp PP = fp_sqr_nv(Pd), PPP = fp_mul_nv(Pd, PP), Q = fp_mul_nv(U1, PP);
+        const Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
+        a.y = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(S1, PPP));
+        a.x = X3;
+        a.zz = fp_mul_nv(fp_mul_nv(a.zz, b.zz), PP);
+        a.zzz = fp_mul_nv(fp_mul_nv(a.zzz, b.zzz), PPP);
+      }
+    }
+  }
+}
 
 // XYZZ -> affine (one inversion); infinity -> (0,0)
 LW_COLD G1Affine xyzz_to_affine(const G1Xyzz& p) {
