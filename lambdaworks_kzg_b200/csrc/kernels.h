@@ -86,7 +86,8 @@ void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st)
 // single verification: C - y*g1_0 + z*pi  vs  pi  (bilinear rearrangement)
 // inputs: affine Montgomery C, pi; canonical z, y.  ok written as int.
 void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y,
-                          const void* d_g1_0_aff, const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st);
+                          const void* d_g1_0_aff, const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st,
+                          int* d_status = nullptr, int sub_code = 0);   // sub_code != 0: also run the r-torsion tests of C and pi, failure -> *d_status
 // tuples: compress(C)||z||y||compress(pi) (160 B each)
 void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le = false);
 // r = H(domain || le64(4096) || le64(n_total) || tuples) -> canonical r (8 u32).  wire: 0 = reference (little-endian

@@ -1247,8 +1247,10 @@ bool vb_reserve(Ctx* c, size_t n, bool stage_blobs = true) {
 // through vb_status.
 // hash_r: also derive the batch challenge r (utils.rs:166-206) into vb_r, absorbing each chunk's tuples as soon as
 // they exist.
+// defer_subgroup: the points are decoded without their r-torsion tests -- the single-proof kernel runs them itself,
+// beside its scalar multiplications (verify_single_from_workspace(..., true))
 bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const Bytes48* proofs, size_t n, bool hash_r = false,
-                    bool dev_inputs = false) {
+                    bool dev_inputs = false, bool defer_subgroup = false) {
   c->vb_n = 0;   // whatever a previous phase 1 left in the workspace is about to be overwritten
   // the reference re-hydrates the SRS before anything else in every entry point (lib.rs:256-262, 420-426, 468-474,
   // 548-554): an unusable SRS is an error whatever the other arguments are -- and the kernels below need it
@@ -1276,9 +1278,9 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
     split = opts().verify_split_subgroup != 0 && n > 64 && opts().verify_streams <= 2 * NSLOT - 2;
   }
   if (split && !c->vb_sub.ensure(2 * n * sizeof(int))) return false;
-  launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0, le, !split);
+  launch_g1_decompress(c->vb_caff.p, c->vb_c48r.p, (int*)c->vb_status.p, c->vb_cin.p, (int)n, s0, le, !split && !defer_subgroup);
   // proofs: decode status into the (still unused) tuples buffer, then merge
-  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, c->hash_st, le, !split);
+  launch_g1_decompress(c->vb_piaff.p, c->vb_p48r.p, (int*)c->vb_tuples.p, c->vb_pin.p, (int)n, c->hash_st, le, !split && !defer_subgroup);
   CU_TRY(cudaEventRecord(c->ev_hash, c->hash_st));
   CU_TRY(cudaStreamWaitEvent(s0, c->ev_hash, 0));
   launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, (int)n, s0);
@@ -1436,16 +1438,21 @@ bool first_bad_status(Ctx* c, size_t n, int& code) {
 }
 C_KZG_RET bad_code(int code) { return code == 1 ? C_KZG_BADARGS : C_KZG_ERROR; }
 
-// single-proof verification with everything already decoded in the workspace (item 0)
-bool verify_single_from_workspace(Ctx* c, bool& ok) {
+// single-proof verification with everything already decoded in the workspace (item 0).  deferred_subgroup: C and pi
+// were decoded without their r-torsion tests; the kernel runs them on its second warp, beside the scalar
+// multiplications, and reports a failure through vb_status[0] -> `bad` (0 = fine)
+bool verify_single_from_workspace(Ctx* c, bool& ok, bool deferred_subgroup = false, int* bad = nullptr) {
   cudaStream_t s0 = c->slot[0].st;
   // reference: KZG::verify subtracts y * srs[0] (= G for a monomial setup); c-kzg uses the generator itself
-  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->lagrange() ? c->d_gen : c->d_srs, c->d_prep0, c->d_prep1, c->lagrange() || c->srs_in_g1, s0);
-  int okv = 0;
-  CU_TRY(cudaMemcpyAsync(&okv, c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
+  launch_verify_single((int*)c->vb_ok.p, c->vb_caff.p, c->vb_piaff.p, c->vb_z.p, c->vb_y.p, c->lagrange() ? c->d_gen : c->d_srs, c->d_prep0, c->d_prep1,
+                       c->lagrange() || c->srs_in_g1, s0, deferred_subgroup ? (int*)c->vb_status.p : nullptr, c->lagrange() ? 1 : 2);
+  int out[2] = {0, 0};
+  CU_TRY(cudaMemcpyAsync(&out[0], c->vb_ok.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
+  if (deferred_subgroup) CU_TRY(cudaMemcpyAsync(&out[1], c->vb_status.p, sizeof(int), cudaMemcpyDeviceToHost, s0));
   CU_TRY(cudaStreamSynchronize(s0));
   CU_TRY(cudaGetLastError());
-  ok = okv != 0;
+  ok = out[0] != 0;
+  if (bad) *bad = out[1];
   return true;
 }
 
@@ -1632,8 +1639,10 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
     CU_TRY(cudaMemcpyAsync(c->vb_zy_in.p, zy, 64, cudaMemcpyHostToDevice, s0));
     const bool le = c->lagrange(), be = c->be_wire();
     // the two point decompressions (sqrt + subgroup check, ~2 ms each on one thread) run side by side
-    launch_g1_decompress(c->vb_caff.p, nullptr, (int*)c->vb_status.p, c->vb_cin.p, 1, s0, le);
-    launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, c->hash_st, le);
+    // (decoding only: the r-torsion tests, two thirds of a decompression, run inside the verification kernel beside
+    // its scalar multiplications)
+    launch_g1_decompress(c->vb_caff.p, nullptr, (int*)c->vb_status.p, c->vb_cin.p, 1, s0, le, false);
+    launch_g1_decompress(c->vb_piaff.p, nullptr, (int*)c->vb_tuples.p, c->vb_pin.p, 1, c->hash_st, le, false);
     CU_TRY(cudaEventRecord(c->ev_hash, c->hash_st));
     CU_TRY(cudaStreamWaitEvent(s0, c->ev_hash, 0));
     launch_status_or((int*)c->vb_status.p, (const int*)c->vb_tuples.p, 1, s0);
@@ -1647,16 +1656,16 @@ C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Byte
       launch_fr_from_be(c->vb_z.p, c->vb_zy_in.p, 1, s0);
       launch_fr_from_be(c->vb_y.p, (const uint8_t*)c->vb_zy_in.p + 32, 1, s0);
     }
-    CU_TRY(cudaStreamSynchronize(s0));
     return true;
   }();
   if (!good) return C_KZG_ERROR;
+  // no host round trip in between: the verification kernel is queued right behind the decoding (a rejected point is
+  // decoded as infinity, so it runs on well-defined values either way) and the status word -- decode errors,
+  // non-canonical field elements, points outside G1 -- is read together with the result
   int bad = 0;
-  if (!first_bad_status(c, 1, bad)) return C_KZG_ERROR;
-  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
-  if (!c->srs_valid || !c->g2_valid) { set_err("SRS re-hydration failed"); return C_KZG_ERROR; }
   bool res = false;
-  if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
+  if (!verify_single_from_workspace(c, res, true, &bad)) return C_KZG_ERROR;
+  if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   *ok = res;
   return C_KZG_OK;
 }
@@ -1668,13 +1677,14 @@ static C_KZG_RET verify_blob_single(bool* ok, const Blob* blob, const Bytes48* c
   Ctx* c = ctx_of(s);
   if (!c) return C_KZG_ERROR;
   CtxLock L(c);
-  if (!verify_prepare(c, blob, commitment_bytes, proof_bytes, 1, false, dev_inputs)) return C_KZG_ERROR;
+  if (!verify_prepare(c, blob, commitment_bytes, proof_bytes, 1, false, dev_inputs, true)) return C_KZG_ERROR;
   int bad = 0;
   if (!first_bad_status(c, 1, bad)) return C_KZG_ERROR;
   if (bad) { set_err("invalid commitment, proof or field element bytes"); return bad_code(bad); }
   bool res = false;
   c->vb_n = 0;
-  if (!verify_single_from_workspace(c, res)) return C_KZG_ERROR;
+  if (!verify_single_from_workspace(c, res, true, &bad)) return C_KZG_ERROR;
+  if (bad) { set_err("commitment or proof is not in G1"); return bad_code(bad); }
   *ok = res;
   return C_KZG_OK;
 }

@@ -71,7 +71,8 @@ __device__ __forceinline__ bool two_pairing_check(const G1Affine* pts, const G2P
 __global__ void __launch_bounds__(LW_PAIR_LANES) verify_single_kernel(int* __restrict__ ok_out, const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
                                                             const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
                                                             const G1Affine* __restrict__ g1_0, const G2Prepared* __restrict__ prep0,
-                                                            const G2Prepared* __restrict__ prep1, int g1_0_in_subgroup) {
+                                                            const G2Prepared* __restrict__ prep1, int g1_0_in_subgroup, int* __restrict__ status,
+                                                            int sub_code) {
   __shared__ G1Xyzz sh_pt[4];
   __shared__ WarpPairingMem sh_m;
   __shared__ G1Affine sh_pair[2];
@@ -99,6 +100,12 @@ __global__ void __launch_bounds__(LW_PAIR_LANES) verify_single_kernel(int* __res
     }
     sh_pt[lane] = g1_mul_scalar(base, half == 0 ? m : q, 4);
     }
+  }
+  // sub_code != 0: C and pi were decoded WITHOUT the r-torsion test (the larger part of a decompression); two lanes
+  // of the second warp run it here, beside the scalar multiplications of the first warp instead of in front of them.
+  // A failure is reported through status[0] and overrides whatever the pairing says.
+  if (sub_code != 0 && (lane == 32 || lane == 33)) {
+    if (!g1_in_subgroup(lane == 32 ? C : PI)) atomicCAS(status, 0, sub_code);
   }
   __syncthreads();
   if (lane == 0) {
@@ -349,9 +356,10 @@ void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st)
   count_launch();
 }
 void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y, const void* d_g1_0_aff,
-                          const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st) {
+                          const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st, int* d_status, int sub_code) {
   verify_single_kernel<<<1, LW_PAIR_LANES, 0, st>>>(d_ok, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
-                                         (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1, g1_0_in_subgroup ? 1 : 0);
+                                         (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1, g1_0_in_subgroup ? 1 : 0,
+                                         d_status, d_status ? sub_code : 0);
   count_launch();
 }
 void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le) {
