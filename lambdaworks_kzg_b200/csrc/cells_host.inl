@@ -10,7 +10,7 @@ struct CellCtx {
   void* d_prep64 = nullptr;       // prepared Miller-loop lines of g2[64] = [tau^64]G2
   void* d_fk20 = nullptr;         // the 8192 FK20 points themselves (affine Montgomery, 768 KB): test hook
   cudaStream_t st = nullptr;
-  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev = nullptr, ev_v[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // ev_v: fork / join points of a batched cell verification
   DevBuf blobs, coef, scalars, pts, cells, proofs, status, msm_scratch;
   // verification / recovery workspace
   DevBuf v_commit, v_cidx, v_cellidx, v_cells, v_proofs, v_evals, v_status, v_pts, v_wcoef, v_rpow, v_scal, v_r, v_out, v_ok, v_msm_a, v_msm_b;
@@ -29,6 +29,8 @@ void destroy_cell_ctx(CellCtx* cc) {
     if (p) cudaFree(p);
   if (cc->h_stage) cudaFreeHost(cc->h_stage);
   if (cc->ev) cudaEventDestroy(cc->ev);
+  for (cudaEvent_t e : cc->ev_v)
+    if (e) cudaEventDestroy(e);
   if (cc->st) cudaStreamDestroy(cc->st);
   delete cc;
 }
@@ -52,6 +54,7 @@ bool cell_ctx_build(Ctx* c) {
   bool good = [&]() -> bool {
     CU_TRY(cudaStreamCreateWithFlags(&cc->st, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&cc->ev, cudaEventDisableTiming));
+    for (cudaEvent_t& e : cc->ev_v) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU_TRY(cudaMalloc(&cc->d_tw, (size_t)EXT_POINTS * 32));
     CU_TRY(cudaMalloc(&cc->d_naf, (size_t)128 * CELL_NAF_BYTES));
     launch_cell_twiddles(cc->d_tw, cc->st);
@@ -356,18 +359,34 @@ C_KZG_RET cells_verify_batch(bool* ok, const Bytes48* commitments, const uint64_
     CU_TRY(cudaMemcpyAsync(cc->v_cells.p, cells, n * CELL_BYTES, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(cc->v_proofs.p, proofs, n * 48, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemsetAsync(d_st, 0, (2 * n + nc) * sizeof(int), st));
+    // Three things need nothing but the inputs and run side by side: the challenge r (ONE sequential SHA-256 over
+    // 2112 bytes per cell, the longest of them) on the context's high-priority hash stream, the decompression of the
+    // proofs on a second stream, cell parsing + commitment decompression here.
+    cudaStream_t sh = c->hash_st, sp = c->slot[1].st;
+    CU_TRY(cudaEventRecord(cc->ev_v[0], st));
+    CU_TRY(cudaStreamWaitEvent(sh, cc->ev_v[0], 0));
+    CU_TRY(cudaStreamWaitEvent(sp, cc->ev_v[0], 0));
+    launch_cell_batch_challenge(cc->v_r.p, cc->v_commit.p, (int)nc, (const uint32_t*)cc->v_cidx.p, (const uint64_t*)cc->v_cellidx.p, cc->v_cells.p,
+                                cc->v_proofs.p, (int)n, c->mode, sh);
+    CU_TRY(cudaEventRecord(cc->ev_v[1], sh));
+    launch_g1_decompress(pts, nullptr, d_st + n, cc->v_proofs.p, (int)n, sp, c->lagrange());
+    CU_TRY(cudaEventRecord(cc->ev_v[2], sp));
     launch_cell_parse(cc->v_evals.p, d_st, cc->v_cells.p, (int)n, c->mode, st);
-    launch_g1_decompress(pts, nullptr, d_st + n, cc->v_proofs.p, (int)n, st, c->lagrange());
     launch_g1_decompress(pts + n * AFFINE_BYTES, nullptr, d_st + 2 * n, cc->v_commit.p, (int)nc, st, c->lagrange());
     CU_TRY(cudaMemcpyAsync(pts + (n + nc) * AFFINE_BYTES, c->d_mono, (size_t)CELL_ELEMS * AFFINE_BYTES, cudaMemcpyDeviceToDevice, st));
-    launch_cell_batch_challenge(cc->v_r.p, cc->v_commit.p, (int)nc, (const uint32_t*)cc->v_cidx.p, (const uint64_t*)cc->v_cellidx.p, cc->v_cells.p,
-                                cc->v_proofs.p, (int)n, c->mode, st);
+    CU_TRY(cudaStreamWaitEvent(st, cc->ev_v[1], 0));
     launch_cell_verify_scalars(cc->v_wcoef.p, cc->v_rpow.p, cc->v_scal.p, cc->v_evals.p, (const uint64_t*)cc->v_cellidx.p, (const uint32_t*)cc->v_cidx.p,
                                (int)n, (int)nc, cc->v_r.p, cc->d_tw, st);
+    CU_TRY(cudaEventRecord(cc->ev_v[3], st));
+    // the two MSMs side by side: sum r^k pi_k on the proofs' stream, the right-hand side here
     uint8_t* out = (uint8_t*)cc->v_out.p;
+    CU_TRY(cudaStreamWaitEvent(sp, cc->ev_v[3], 0));
+    launch_var_msm_mont(out, pts, cc->v_rpow.p, n, cc->v_msm_a.p, sp);
+    CU_TRY(cudaEventRecord(cc->ev_v[4], sp));
     CU_TRY(cudaMemsetAsync(out + 96, 0, 96, st));
-    launch_var_msm_mont(out, pts, cc->v_rpow.p, n, cc->v_msm_a.p, st);              // sum r^k pi_k
+    CU_TRY(cudaStreamWaitEvent(st, cc->ev_v[2], 0));   // the proofs are decoded
     launch_var_msm_mont(out + 192, pts, cc->v_scal.p, np, cc->v_msm_b.p, st);       // RLP + RLC - RLI
+    CU_TRY(cudaStreamWaitEvent(st, cc->ev_v[4], 0));
     launch_batch_final((int*)cc->v_ok.p, out, 1, c->d_prep0, cc->d_prep64, st);
     CU_TRY(cudaMemcpyAsync(h_status.data(), d_st, h_status.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(&okv, cc->v_ok.p, sizeof(int), cudaMemcpyDeviceToHost, st));
