@@ -419,7 +419,7 @@ def main():
                    "cpu_note": "oracle/c restates commit / proof only (no pairing), one thread: the reference is single-threaded inside a call"}
     cells = None
     if rank == 0 and not args.no_extras:
-        cells = cells_block(lw, torch, dev)
+        cells = cells_block(lw, torch, dev, peak=roofline["peak"] * 1e12 if roofline else None)
     if rank == 0 and world == 1:
         cpu_base, _ = cpu_reference_run(1, 1)
 
@@ -441,7 +441,7 @@ def main():
         dist.destroy_process_group()
 
 
-def cells_block(lw, torch, dev, n=CELL_BLOBS):
+def cells_block(lw, torch, dev, n=CELL_BLOBS, peak=None):
     """PeerDAS / EIP-7594 (include/lwkzg.h part 3) in the mainnet wire format (MODE_DENEB): cells + FK20 cell
     proofs of n device-resident blobs, the same through the host API, and the single-call latencies.  Checked against
     the committed known answers (tests/golden/cell_kats.json, made by the oracle without FK20) and by verifying a
@@ -529,7 +529,21 @@ def cells_block(lw, torch, dev, n=CELL_BLOBS):
             "verify_cell_kzg_proof_batch_128_cells_1_blob": lat(lambda: lw.verify_cell_kzg_proof_batch([com] * 128, list(range(128)), cs, ps, s)),
             "verify_cell_kzg_proof_batch_%d_cells_%d_blobs" % (len(pick), n): lat(lambda: lw.verify_cell_kzg_proof_batch(*v_args, s), reps=2),
         }
-        return {"mode": "MODE_DENEB (mainnet wire format)", "blobs": n, "fk20_window_bits": lw.cell_window_bits(s),
+        # executed integer work of a blob's 128 proofs: 8192 points x 2 GLV halves x W windows of batched-affine
+        # additions (5 M + 1 S) + the fold of the accumulators, and 642 twiddle ladders of 129 Jacobian doublings (2 M + 5 S)
+        # + ~52 mixed additions (7 M + 4 S) + the table of odd multiples
+        cwb = lw.cell_window_bits(s)
+        nwin = -(-128 // cwb)
+        M, S = MAC32_M, MAC32_S
+        mac_msm = 8192 * 2 * nwin * (1 - 2.0 ** -cwb) * (5 * M + S) + 2 * 128 * 63 * (8 * M + 2 * S)
+        mac_fft = 642 * (129 * (2 * M + 5 * S) + 52 * (7 * M + 4 * S) + 3 * (2 * M + 5 * S) + 3 * (7 * M + 4 * S) + 40 * M)
+        pk = peak or max(lw.imad_peak(1), lw.imad_peak(0))
+        roof = {"bound": "int32-imad", "unit": "TMAC32/s", "peak": pk / 1e12,
+                "achieved": n * (mac_msm + mac_fft) / (ms_both * 1e-3) / 1e12, "frac": n * (mac_msm + mac_fft) / (ms_both * 1e-3) / pk,
+                "executed_mac32_per_blob": {"fk20_msm (msm_gather_ba_kernel, segmented)": mac_msm, "g1_fft (cell_g1_fft_stage_kernel)": mac_fft},
+                "note": "whole pass (poly + toeplitz + 2 MSM launches + 14 FFT stage launches + finalize) against the measured integer-multiply "
+                        "peak; per-kernel shares and ncu pipe utilisation: profiles/r02_cells_summary.md (fmaheavy 72 % MSM, 61-68 % FFT stages)"}
+        return {"mode": "MODE_DENEB (mainnet wire format)", "blobs": n, "fk20_window_bits": lw.cell_window_bits(s), "roofline": roof,
                 "setup_s": {"load_trusted_setup (Lagrange SRS + 8-bit commitment table)": t1 - t0, "first cell call (FK20 points + digit table)": t_first},
                 "device_resident": {"cells_and_proofs_ms": ms_both, "cells_only_ms": ms_cells, "blobs_per_s": n / (ms_both * 1e-3),
                                     "cell_proofs_per_s": n * 128 / (ms_both * 1e-3)},
