@@ -58,6 +58,8 @@ struct Options {
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
+  long cache_config = 0;             // device-wide cudaDeviceSetCacheConfig hint applied when a context is built: 0 = leave alone, 1 = prefer shared,
+                                     // 3 = prefer equal (kernels with different shared-memory carve-outs do not share an SM)
   long verify_split_subgroup = 0;    // 1 = batched verification runs the r-torsion tests of the points beside the first blob hashes instead of in front
                                      // of them.  Measured and not kept as the default: device-resident 20.8 -> 20.8 ms, from pinned memory 21.2 -> 25 ms
                                      // (blob-hash kernels that run beside the thread-per-point kernels take several times longer)
@@ -78,6 +80,7 @@ struct Options {
     if (const char* e = getenv("LWKZG_MSM_ALGO")) msm_algo = atol(e);
     if (const char* e = getenv("LWKZG_MSM_BA_MIN_BLOBS")) msm_ba_min_blobs = atol(e);
     if (const char* e = getenv("LWKZG_SHARE_TABLE")) share_table = atol(e) != 0;
+    if (const char* e = getenv("LWKZG_CACHE_CONFIG")) cache_config = atol(e);
   }
 };
 Options& opts() {
@@ -389,6 +392,16 @@ void destroy_ctx(Ctx* c) {
 
 bool build_ctx_inner(Ctx* c, const g1_t* g1, const g2_t* g2, int mode, long window_override) {
   CU_TRY(cudaGetDevice(&c->device));
+  {
+    long cfg;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      cfg = opts().cache_config;
+    }
+    if (cfg == 1) cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
+    else if (cfg == 2) cudaDeviceSetCacheConfig(cudaFuncCachePreferL1);
+    else if (cfg == 3) cudaDeviceSetCacheConfig(cudaFuncCachePreferEqual);
+  }
   int lo = 0, hi = 0;
   CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   for (auto& s : c->slot) {
@@ -1488,6 +1501,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "share_table") { if (value != 0 && value != 1) return 1; opts().share_table = value; return 0; }
   if (n == "verify_streams") { if (value < 1 || value > 8) return 1; opts().verify_streams = value; return 0; }
   if (n == "verify_split_subgroup") { if (value != 0 && value != 1) return 1; opts().verify_split_subgroup = value; return 0; }
+  if (n == "cache_config") { if (value < 0 || value > 3) return 1; opts().cache_config = value; return 0; }
   if (n == "cell_window_bits") { if (value < 4 || value > 14) return 1; opts().cell_window_bits = value; return 0; }
   if (n == "cell_chunk_blobs") { if (value < 1 || value > 65536) return 1; opts().cell_chunk_blobs = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
@@ -1507,6 +1521,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "share_table") return opts().share_table;
   if (n == "verify_streams") return opts().verify_streams;
   if (n == "verify_split_subgroup") return opts().verify_split_subgroup;
+  if (n == "cache_config") return opts().cache_config;
   if (n == "cell_window_bits") return opts().cell_window_bits;
   if (n == "cell_chunk_blobs") return opts().cell_chunk_blobs;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel

@@ -6,6 +6,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import lambdaworks_kzg_b200 as lw
 
+if os.environ.get("CACHECFG"):
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    torch.cuda.init()
+    print("cudaDeviceSetCacheConfig ->", rt.cudaDeviceSetCacheConfig(int(os.environ["CACHECFG"])), flush=True)
 n = int(os.environ.get("NB", "4096"))
 lw.set_option("window_bits", int(os.environ.get("WB", "13")))
 s = lw.load_trusted_setup_file(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "trusted_setup.txt"))
