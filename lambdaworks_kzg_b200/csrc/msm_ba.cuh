@@ -94,6 +94,13 @@ __device__ __forceinline__ Fp fp_from_stage(const uint4* p /* 3 words, stride TH
   return e;
 }
 
+template <int TH>
+__device__ __forceinline__ void fp_to_stage(uint4* p /* 3 words, stride TH */, const Fp& e) {
+  p[0] = make_uint4(e.l[0], e.l[1], e.l[2], e.l[3]);
+  p[TH] = make_uint4(e.l[4], e.l[5], e.l[6], e.l[7]);
+  p[2 * TH] = make_uint4(e.l[8], e.l[9], e.l[10], e.l[11]);
+}
+
 constexpr int BA_STAGE_WORDS = 15;   // T.x T.y (6) + A.x A.y (6) + prefix product (3) 128-bit words per thread
 template <int K, int TH>
 constexpr size_t ba_smem_bytes() { return (size_t)BA_STAGE_WORDS * TH * 16 + (size_t)K * TH * 2 + 4 * TH * 4; }
@@ -275,8 +282,8 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
       // every staged word of this slot now sits in a register: request the next slot while the remaining
       // four products run
       if (k > 0) request2(k - 1, e_next);
+      const Fp lam = fp_mul_nv(dy, dinv);   // (before inv * d: dy and dinv die here, five field elements live across either call)
       inv = fp_mul_nv(inv, d);
-      const Fp lam = fp_mul_nv(dy, dinv);
       const Fp x3 = fp_sub(fp_sub(fp_sqr_nv(lam), ax), t.x);
       const Fp y3 = fp_sub(fp_mul_nv(lam, fp_sub(ax, x3)), ay);
       store_fp_scratch<TH>(slot, x3);
@@ -284,15 +291,50 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
     }
   }
 
-  // fold the K accumulators, then the block
-  G1Xyzz acc = xyzz_inf();
+  // fold the K accumulators, then the block.  The running XYZZ sum lives in the (now idle) staging column of the
+  // thread, not in registers: with it there the fold needs five live field elements instead of nine (1024-blob launch
+  // 19.05 -> 18.9 ms).  Measured with it: the kernel at 128 registers / four blocks per SM, 180 bytes of spills left --
+  // 19.1 ms, no gain from the fourth block (profiles/r02_ba_128reg_variant.log).
+  // words 0-2 x, 3-5 y, 6-8 zz, 9-11 zzz
+  cp_async_wait_all();
+  bool acc_inf = true;
 #pragma unroll 1
   for (int k = 0; k < K; k++) {
     if ((infmask >> k) & 1ull) continue;
-    G1Affine a;
-    a.x = load_fp_scratch<TH>(my + (k * 9) * TH);
-    a.y = load_fp_scratch<TH>(my + (k * 9 + 3) * TH);
-    xyzz_madd_hot(acc, a);
+    const Fp px = load_fp_scratch<TH>(my + (k * 9) * TH), py = load_fp_scratch<TH>(my + (k * 9 + 3) * TH);
+    if (acc_inf) {
+      const Fp one = fp_one();
+      fp_to_stage<TH>(stage, px); fp_to_stage<TH>(stage + 3 * TH, py); fp_to_stage<TH>(stage + 6 * TH, one); fp_to_stage<TH>(stage + 9 * TH, one);
+      acc_inf = false;
+      continue;
+    }
+    const Fp Pd = fp_sub(fp_mul_nv(px, fp_from_stage<TH>(stage + 6 * TH)), fp_from_stage<TH>(stage));
+    const Fp Rd = fp_sub(fp_mul_nv(py, fp_from_stage<TH>(stage + 9 * TH)), fp_from_stage<TH>(stage + 3 * TH));
+    if (fp_is_zero(Pd)) {   // same x: doubling or cancellation (cold)
+      G1Xyzz a4;
+      a4.x = fp_from_stage<TH>(stage); a4.y = fp_from_stage<TH>(stage + 3 * TH); a4.zz = fp_from_stage<TH>(stage + 6 * TH); a4.zzz = fp_from_stage<TH>(stage + 9 * TH);
+      G1Affine p;
+      p.x = px; p.y = py;
+      xyzz_madd_rare(a4, p);
+      if (xyzz_is_inf(a4)) {
+        acc_inf = true;
+      } else {
+        fp_to_stage<TH>(stage, a4.x); fp_to_stage<TH>(stage + 3 * TH, a4.y); fp_to_stage<TH>(stage + 6 * TH, a4.zz); fp_to_stage<TH>(stage + 9 * TH, a4.zzz);
+      }
+      continue;
+    }
+    const Fp PP = fp_sqr_nv(Pd), PPP = fp_mul_nv(Pd, PP);
+    const Fp Q = fp_mul_nv(fp_from_stage<TH>(stage), PP);
+    const Fp X3 = fp_sub(fp_sub(fp_sqr_nv(Rd), PPP), fp_dbl(Q));
+    fp_to_stage<TH>(stage, X3);
+    const Fp Y3 = fp_sub(fp_mul_nv(Rd, fp_sub(Q, X3)), fp_mul_nv(fp_from_stage<TH>(stage + 3 * TH), PPP));
+    fp_to_stage<TH>(stage + 3 * TH, Y3);
+    fp_to_stage<TH>(stage + 6 * TH, fp_mul_nv(fp_from_stage<TH>(stage + 6 * TH), PP));
+    fp_to_stage<TH>(stage + 9 * TH, fp_mul_nv(fp_from_stage<TH>(stage + 9 * TH), PPP));
+  }
+  G1Xyzz acc = xyzz_inf();
+  if (!acc_inf) {
+    acc.x = fp_from_stage<TH>(stage); acc.y = fp_from_stage<TH>(stage + 3 * TH); acc.zz = fp_from_stage<TH>(stage + 6 * TH); acc.zzz = fp_from_stage<TH>(stage + 9 * TH);
   }
   __syncthreads();   // the reduction scratch aliases the staging columns
   if (seg_stride > 0) {
