@@ -53,8 +53,8 @@ UNIT = "blobs/s"
 VERIFY_BLOBS = 4096
 CELL_BLOBS = 888          # PeerDAS block: blobs per compute_cells_and_kzg_proofs batch (one pass; 888 x 128 = 113664 cell proofs)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE 1024-blob launch of msm_gather_ba_kernel from the ncu --set full
-# capture committed as profiles/r02_ncu_ba_staged_1024blob_raw.csv
-NCU_DRAM_BYTES_PER_BLOB = (35.42e9 + 9.33e9) / 1024
+# capture committed as profiles/r02_ncu_ba_1024blob_end_of_round_raw.csv
+NCU_DRAM_BYTES_PER_BLOB = (35.41e9 + 9.30e9) / 1024
 
 
 def workload_name(n, wb):
@@ -351,15 +351,15 @@ def main():
                     "frac_executed": executed / (k_ms * 1e-3) / peak,
                     "floor_mac32_per_launch": floor_mac,
                     "frac_floor": floor_mac / (k_ms * 1e-3) / peak,
-                    "ncu_fmaheavy_pct": 72.4,
-                    "ncu_source": "sm__pipe_fmaheavy_cycles_active of the 1024-blob launch: profiles/r02_ncu_ba_staged_noprefetch_metrics.csv",
+                    "ncu_fmaheavy_pct": 74.6,
+                    "ncu_source": "sm__pipe_fmaheavy_cycles_active of the 1024-blob launch (18.87 ms under ncu): profiles/r02_ncu_ba_1024blob_end_of_round_raw.csv",
                     "table_entries_per_point": epp,
                     "kernel_share_of_step": 2 * k_ms / ms_per_step,
                     # second half of BASELINE's metric: G1 MSM points/s (fixed-base MSM over the 4096-point SRS, this kernel)
                     "g1_msm_points_per_s": n * 4096 / (k_ms * 1e-3),
                     "traffic": traffic,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 1024-blob launch, scaled to this launch's blob count "
-                                      "(profiles/r02_ncu_ba_staged_noprefetch_metrics.csv)",
+                                      "(profiles/r02_ncu_ba_1024blob_end_of_round_raw.csv)",
                     "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "alg_bytes_per_launch": alg_bytes,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
