@@ -291,6 +291,9 @@ double lwkzg_bench_pairing(int iters, const KZGSettings *s);
  * the "window_bits" option if HBM was short), -1 on error */
 int lwkzg_window_bits(const KZGSettings *s);
 
+/* Test hook (host only, no GPU needed): the parallel byte copy that stages pageable caller buffers into the pinned
+ * ring (a pool of host threads, LWKZG_STAGE_THREADS; copies below 1 MiB are a plain memcpy). */
+void lwkzg_debug_stage_copy(void *dst, const void *src, size_t bytes);
 /* how these settings hold their digit table: 0 = private copy, 1 = built here and published ("share_table"),
  * 2 = attached to the table another PROCESS built (CUDA IPC), 3 = shared with another settings object of this
  * process; -1 on error */

@@ -2026,6 +2026,7 @@ int lwkzg_window_bits(const KZGSettings* s) {
   Ctx* c = ctx_of(s);
   return c ? c->c : -1;
 }
+void lwkzg_debug_stage_copy(void* dst, const void* src, size_t bytes) { HostStager::get().copy(dst, src, bytes); }
 int lwkzg_table_share(const KZGSettings* s) {
   Ctx* c = ctx_of(s);
   return c ? c->table_share : -1;

@@ -101,3 +101,23 @@ def test_synth_blob_generator_spec():
                 w += v.to_bytes(8, "big")
             w = bytes([w[0] & 0x3F]) + w[1:]
             assert blob[32 * i: 32 * i + 32] == w
+
+
+def test_parallel_stage_copy_is_a_faithful_memcpy(lib):
+    """The host-thread pool that stages pageable caller buffers (csrc/lwkzg.cu HostStager) moves bytes and nothing else:
+    odd sizes, sizes around the slice boundaries, back-to-back calls."""
+    import random
+
+    lib.lwkzg_debug_stage_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    lib.lwkzg_debug_stage_copy.restype = None
+    rng = random.Random(7)
+    for size in (0, 1, 4095, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 3 * (1 << 20) + 12345, 33554432 + 7, 8 * 4096 * 9 + 3):
+        src = (ctypes.c_ubyte * max(size, 1))()
+        block = bytes(rng.getrandbits(8) for _ in range(4099))
+        data = (block * (size // len(block) + 1))[:size]
+        ctypes.memmove(src, data, size)
+        dst = (ctypes.c_ubyte * (max(size, 1) + 16))()
+        ctypes.memset(dst, 0xAB, size + 16)
+        lib.lwkzg_debug_stage_copy(dst, src, size)
+        assert bytes(dst[:size]) == data
+        assert bytes(dst[size: size + 16]) == b"\xab" * 16   # nothing written past the end
