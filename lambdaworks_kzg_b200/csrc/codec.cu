@@ -51,17 +51,20 @@ void launch_zero_failed(void* d_out, int bytes_per_item, const int* d_status, in
 
 void launch_g1_decompress(void* d_aff, void* d_recompressed48, int* d_status, const void* d_in48, int n, cudaStream_t st, bool strict, bool check_subgroup) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(g1_decompress_kernel);
   g1_decompress_kernel<<<(n + 31) / 32, 32, 0, st>>>((G1Affine*)d_aff, (uint8_t*)d_recompressed48, d_status, (const uint8_t*)d_in48, n, strict ? 1 : 0,
                                                     check_subgroup ? 1 : 0);
   count_launch();
 }
 void launch_g1_subgroup_check(int* d_status, const void* d_aff, int n, cudaStream_t st, bool strict) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(g1_subgroup_kernel);
   g1_subgroup_kernel<<<(n + 31) / 32, 32, 0, st>>>(d_status, (const G1Affine*)d_aff, n, strict ? 1 : 0);
   count_launch();
 }
 void launch_status_or(int* d_status, const int* d_other, int n, cudaStream_t st) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(status_or_kernel);
   status_or_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_status, d_other, n);
   count_launch();
 }

@@ -6,6 +6,20 @@
 #include <stddef.h>
 #include <stdint.h>
 
+// Kernels that run side by side in the verification pipeline all ask for the SAME shared-memory carve-out (the
+// largest, like the batched-affine MSM kernel): blocks of kernels with different carve-outs do not share an SM -- it
+// drains and is reconfigured between them -- which made a blob-hash kernel next to the thread-per-point decompression
+// take 13 ms instead of 2.5 (profiles/r02_verify_notes.md).  Function attributes are per device.
+#define LW_SAME_CARVEOUT(kernel)                                                                              \
+  do {                                                                                                        \
+    static bool lw_done_[64] = {};                                                                            \
+    int lw_dev_ = 0;                                                                                          \
+    if (cudaGetDevice(&lw_dev_) == cudaSuccess && lw_dev_ >= 0 && lw_dev_ < 64 && !lw_done_[lw_dev_]) {       \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+      lw_done_[lw_dev_] = true;                                                                               \
+    }                                                                                                         \
+  } while (0)
+
 namespace lw {
 
 constexpr int N_POINTS = 4096;          // FIELD_ELEMENTS_PER_BLOB

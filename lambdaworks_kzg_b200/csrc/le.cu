@@ -183,6 +183,7 @@ void launch_affine_to_canon(void* d_out24, const void* d_aff, int n, cudaStream_
 }
 void launch_le_blob_check(int* d_status, const void* d_blobs, int n, cudaStream_t st, bool be) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(le_blob_check_kernel);
   le_blob_check_kernel<<<n, 128, 0, st>>>(d_status, (const uint8_t*)d_blobs, n, be ? 1 : 0);
   count_launch();
 }
@@ -193,6 +194,7 @@ void launch_le_fr_parse(void* d_out, int* d_status, const void* d_in32, int n, c
 }
 void launch_le_eval_quot(void* d_q, void* d_y, void* d_y_le32, const void* d_blobs, const void* d_z, const void* d_roots, int n, cudaStream_t st, bool be) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(le_eval_quot_kernel);
   le_eval_quot_kernel<<<(n + LE_WARPS - 1) / LE_WARPS, LE_WARPS * 32, 0, st>>>((uint32_t*)d_q, (uint32_t*)d_y, (uint8_t*)d_y_le32, (const uint8_t*)d_blobs,
                                                                               (const uint32_t*)d_z, (const Fr*)d_roots, n, be ? 1 : 0);
   count_launch();

@@ -58,6 +58,8 @@ struct Options {
   long msm_ba_min_blobs = 256;
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
+  long verify_overlap_decode = 1;    // batched verification: blob hashes start beside the point decompression (possible since the decompression
+                                     // kernels carry the hash kernels' shared-memory carve-out) instead of behind it
   long cache_config = 0;             // device-wide cudaDeviceSetCacheConfig hint applied when a context is built: 0 = leave alone, 1 = prefer shared,
                                      // 3 = prefer equal (kernels with different shared-memory carve-outs do not share an SM)
   long verify_split_subgroup = 0;    // 1 = batched verification runs the r-torsion tests of the points beside the first blob hashes instead of in front
@@ -1285,9 +1287,10 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
   // Large batches: decoding (a square root) gates the blob hashes, the r-torsion tests (two thirds of a decompression)
   // do not -- they run beside the first chunks on the two compute streams the chunks leave free and are merged into
   // the status array at the end.
-  bool split;
+  bool split, overlap_decode;
   {
     std::lock_guard<std::mutex> lk2(g_mu);
+    overlap_decode = opts().verify_overlap_decode != 0;
     split = opts().verify_split_subgroup != 0 && n > 64 && opts().verify_streams <= 2 * NSLOT - 2;
   }
   if (split && !c->vb_sub.ensure(2 * n * sizeof(int))) return false;
@@ -1378,11 +1381,11 @@ bool verify_prepare(Ctx* c, const Blob* blobs, const Bytes48* commitments, const
       // (measured: a hash kernel that starts while the two decompression kernels are still running takes 9-15 ms
       // instead of 2.7 -- so every chunk waits for them, ~2 ms after the call began, before anything else)
       // (small batches use the warp-per-blob hash, which does not show this, and want the overlap)
-      if (n > 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
+      if (!overlap_decode && n > 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
       if (trace) { for (auto& e : tc) cudaEventCreate(&e); cudaEventRecord(tc[0], st); }
       launch_challenge_midstate(d_states, d_blobs, m, st, true, be);
       if (trace) cudaEventRecord(tc[1], st);
-      if (n <= 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
+      if (overlap_decode || n <= 64) CU_TRY(cudaStreamWaitEvent(st, c->slot[0].ev_in, 0));
       if (le) {
         int* st2 = (int*)c->vb_status2.p + off;
         CU_TRY(cudaMemsetAsync(st2, 0, (size_t)m * sizeof(int), st));
@@ -1502,6 +1505,7 @@ int lwkzg_set_option(const char* name, long value) {
   if (n == "verify_streams") { if (value < 1 || value > 8) return 1; opts().verify_streams = value; return 0; }
   if (n == "verify_split_subgroup") { if (value != 0 && value != 1) return 1; opts().verify_split_subgroup = value; return 0; }
   if (n == "cache_config") { if (value < 0 || value > 3) return 1; opts().cache_config = value; return 0; }
+  if (n == "verify_overlap_decode") { if (value != 0 && value != 1) return 1; opts().verify_overlap_decode = value; return 0; }
   if (n == "cell_window_bits") { if (value < 4 || value > 14) return 1; opts().cell_window_bits = value; return 0; }
   if (n == "cell_chunk_blobs") { if (value < 1 || value > 65536) return 1; opts().cell_chunk_blobs = value; return 0; }
   if (n == "msm_ba_variant") { if (value < 0 || value >= msm_ba_num_variants()) return 1; msm_ba_set_variant((int)value); return 0; }
@@ -1522,6 +1526,7 @@ long lwkzg_get_option(const char* name) {
   if (n == "verify_streams") return opts().verify_streams;
   if (n == "verify_split_subgroup") return opts().verify_split_subgroup;
   if (n == "cache_config") return opts().cache_config;
+  if (n == "verify_overlap_decode") return opts().verify_overlap_decode;
   if (n == "cell_window_bits") return opts().cell_window_bits;
   if (n == "cell_chunk_blobs") return opts().cell_chunk_blobs;
   if (n == "msm_ba_threads") return msm_ba_threads();   // read-only: threads per blob of the batched-affine kernel

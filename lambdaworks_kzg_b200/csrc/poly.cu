@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(POLY_WARPS * 32) poly_eval_quot_kernel(uint32_
 // warp-per-blob kernel's ~2x shorter critical path is what counts; false: the hash hides under a commitment MSM and
 // the thread-per-blob kernel leaves the issue slots to it.
 void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaStream_t st, bool latency, bool be_header) {
+  LW_SAME_CARVEOUT(challenge_midstate_warp_kernel);
+  LW_SAME_CARVEOUT(challenge_midstate_group_kernel<8>);
+  LW_SAME_CARVEOUT(challenge_midstate_kernel);
   if (n <= 0) return;
   const int bh = be_header ? 1 : 0;
   if (n <= 64)
@@ -238,6 +241,7 @@ void launch_challenge_midstate(void* d_states, const void* d_blobs, int n, cudaS
 }
 void launch_challenge_finish(void* d_z, const void* d_states, const void* d_blobs, const void* d_commit48, int n, cudaStream_t st, bool le_digest) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(challenge_finish_kernel);
   challenge_finish_kernel<<<(n + 31) / 32, 32, 0, st>>>((uint32_t*)d_z, (const Sha256State*)d_states, (const uint8_t*)d_blobs, (const uint8_t*)d_commit48, n,
                                                        le_digest ? 1 : 0);
   count_launch();
@@ -249,6 +253,7 @@ void launch_fr_from_be(void* d_z, const void* d_z_be32, int n, cudaStream_t st) 
 }
 void launch_poly_eval_quot(void* d_q, void* d_y, void* d_y_be32, const void* d_blobs, const void* d_z, int n, cudaStream_t st) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(poly_eval_quot_kernel);
   poly_eval_quot_kernel<<<(n + POLY_WARPS - 1) / POLY_WARPS, POLY_WARPS * 32, 0, st>>>((uint32_t*)d_q, (uint32_t*)d_y, (uint8_t*)d_y_be32,
                                                                                       (const uint8_t*)d_blobs, (const uint32_t*)d_z, n);
   count_launch();

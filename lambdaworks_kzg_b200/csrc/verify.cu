@@ -364,6 +364,7 @@ void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, 
 }
 void launch_make_tuples(void* d_tuples160, const void* d_c48, const void* d_z, const void* d_y, const void* d_pi48, int n, cudaStream_t st, bool le) {
   if (n <= 0) return;
+  LW_SAME_CARVEOUT(make_tuples_kernel);
   make_tuples_kernel<<<(n + 63) / 64, 64, 0, st>>>((uint8_t*)d_tuples160, (const uint8_t*)d_c48, (const uint32_t*)d_z, (const uint32_t*)d_y, (const uint8_t*)d_pi48, n,
                                                   le ? 1 : 0);
   count_launch();
@@ -372,6 +373,7 @@ static int bch_wire_flags(int wire) { return wire == 1 ? BCH_LE : wire == 2 ? BC
 // (measured and not kept: giving this one-warp kernel an SM of its own by asking for all of the SM's shared memory --
 // no change; what slowed the device-resident batch was eight chunk streams at once, see "verify_streams")
 void launch_batch_challenge(void* d_r, const void* d_tuples160, size_t n_total, cudaStream_t st, int wire) {
+  LW_SAME_CARVEOUT(batch_challenge_kernel);
   batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, nullptr, (const uint8_t*)d_tuples160, (unsigned long long)n_total, 0, 0,
                                                               BCH_INIT | BCH_FINAL | bch_wire_flags(wire));
   count_launch();
@@ -381,6 +383,7 @@ int batch_challenge_blocks_ready(size_t tuples_ready) { return (int)((32 + 160 *
 void launch_batch_challenge_part(void* d_r, void* d_state, const void* d_tuples160, size_t n_total, int blk0, int blk1, bool first, bool last,
                                  cudaStream_t st, int wire) {
   if (!last && blk1 <= blk0 && !first) return;
+  LW_SAME_CARVEOUT(batch_challenge_kernel);
   batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, (Sha256State*)d_state, (const uint8_t*)d_tuples160, (unsigned long long)n_total,
                                                               blk0, blk1, (first ? BCH_INIT : 0) | (last ? BCH_FINAL : 0) | bch_wire_flags(wire));
   count_launch();

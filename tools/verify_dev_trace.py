@@ -28,6 +28,7 @@ for ns in [int(x) for x in os.environ.get("STREAMS", "6").split(",")]:
   for split in [int(x) for x in os.environ.get("SPLIT", "1").split(",")]:
     lw.set_option("verify_streams", ns)
     lw.set_option("verify_split_subgroup", split)
+    lw.set_option("verify_overlap_decode", int(os.environ.get("OVERLAP", "1")))
     for name, fn in (("device-resident", lambda: lw.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_c.data_ptr(), d_p.data_ptr(), n, s)),
                      ("pinned", lambda: lw.verify_blob_kzg_proof_batch_ptr(hb.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, s))):
         fn()
