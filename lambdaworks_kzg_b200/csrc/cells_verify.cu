@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(REC_THREADS) cell_recover_kernel(Fr* __restric
 void launch_cell_parse(void* d_evals, int* d_status, const void* d_cells, int n_cells, int mode, cudaStream_t st) {
   if (n_cells <= 0) return;
   const long total = (long)n_cells * CELL_ELEMS;
+  LW_SAME_CARVEOUT(cell_parse_kernel);
   cell_parse_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((uint32_t*)d_evals, d_status, (const uint8_t*)d_cells, n_cells, mode);
   count_launch();
 }
@@ -376,6 +377,7 @@ void launch_cell_batch_challenge(void* d_r, const void* d_commitments48, int n_c
   put(6, CELL_ELEMS);
   put(8, m.n_commitments);
   put(10, m.n_cells);
+  LW_SAME_CARVEOUT(cell_batch_challenge_kernel);
   cell_batch_challenge_kernel<<<1, 32, 0, st>>>((uint32_t*)d_r, m);
   count_launch();
 }
@@ -383,6 +385,8 @@ void launch_cell_batch_challenge(void* d_r, const void* d_commitments48, int n_c
 void launch_cell_verify_scalars(void* d_wcoef, void* d_rpow, void* d_scalars_b, const void* d_evals, const uint64_t* d_cell_indices,
                                 const uint32_t* d_commitment_indices, int n_cells, int n_commitments, const void* d_r, const void* d_tw8192, cudaStream_t st) {
   if (n_cells <= 0) return;
+  LW_SAME_CARVEOUT(cell_interp_kernel);
+  LW_SAME_CARVEOUT(cell_verify_finish_kernel);
   cell_interp_kernel<<<n_cells, 32, 0, st>>>((Fr*)d_wcoef, (uint32_t*)d_rpow, (uint32_t*)d_scalars_b, (const uint32_t*)d_evals, d_cell_indices,
                                             (const uint32_t*)d_r, (const Fr*)d_tw8192);
   cell_verify_finish_kernel<<<1, 128, 0, st>>>((uint32_t*)d_scalars_b, (const Fr*)d_wcoef, (const uint32_t*)d_rpow, d_commitment_indices, n_cells, n_commitments);
