@@ -18,6 +18,24 @@ struct CellCtx {
   size_t h_stage_cap = 0;
 };
 
+// temporaries of the set-up / test-hook paths: freed on every exit, also the error ones
+struct ScratchMem {
+  std::vector<void*> ptrs;
+  void* get(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { set_err("cudaMalloc failed"); return nullptr; }
+    ptrs.push_back(p);
+    return p;
+  }
+  void* keep(void* p) {   // hand one allocation over to the caller
+    ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end());
+    return p;
+  }
+  ~ScratchMem() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+};
+
 void destroy_cell_ctx(CellCtx* cc) {
   if (!cc) return;
   if (cc->st) cudaStreamSynchronize(cc->st);
@@ -61,30 +79,29 @@ bool cell_ctx_build(Ctx* c) {
     launch_cell_twiddle_naf(cc->d_naf, cc->st);
     // g2[64]
     {
+      ScratchMem tmp;
       uint32_t g2canon[48];
       const g2_t& q = c->g2_host[CELL_ELEMS];
       blst_fp_to_canon(&g2canon[0], &q.x.fp[0]);
       blst_fp_to_canon(&g2canon[12], &q.x.fp[1]);
       blst_fp_to_canon(&g2canon[24], &q.y.fp[0]);
       blst_fp_to_canon(&g2canon[36], &q.y.fp[1]);
-      void* d_g2 = nullptr;
-      int* d_bad = nullptr;
-      CU_TRY(cudaMalloc(&d_g2, sizeof(g2canon)));
-      CU_TRY(cudaMalloc(&d_bad, sizeof(int)));
+      void* d_g2 = tmp.get(sizeof(g2canon));
+      int* d_bad = (int*)tmp.get(sizeof(int));
+      if (!d_g2 || !d_bad) return false;
       CU_TRY(cudaMalloc(&cc->d_prep64, g2_prepared_bytes()));
       CU_TRY(cudaMemcpyAsync(d_g2, g2canon, sizeof(g2canon), cudaMemcpyHostToDevice, cc->st));
       launch_g2_prepare(cc->d_prep64, d_bad, d_g2, cc->st);
       int bad = 1;
       CU_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, cc->st));
       CU_TRY(cudaStreamSynchronize(cc->st));
-      cudaFree(d_g2);
-      cudaFree(d_bad);
       if (bad) { set_err("g2_values[64] is not on the twist"); return false; }
     }
     // FK20 points
-    void *d_pts = nullptr, *d_aff = nullptr, *d_bases = nullptr;
-    CU_TRY(cudaMalloc(&d_pts, (size_t)EXT_POINTS * XYZZ_BYTES));
-    CU_TRY(cudaMalloc(&d_aff, (size_t)EXT_POINTS * AFFINE_BYTES));
+    ScratchMem tmp;
+    void* d_pts = tmp.get((size_t)EXT_POINTS * XYZZ_BYTES);
+    void* d_aff = tmp.get((size_t)EXT_POINTS * AFFINE_BYTES);
+    if (!d_pts || !d_aff) return false;
     launch_cell_srs_columns(d_pts, c->d_mono, cc->st);
     for (int half = 64; half >= 1; half >>= 1) launch_cell_g1_fft_stage(d_pts, 64, half, true, false, false, cc->d_naf, cc->st);
     launch_cell_fk20_points(d_aff, d_pts, cc->st);
@@ -106,16 +123,15 @@ bool cell_ctx_build(Ctx* c) {
     // one table per half of the frequencies (4096 points each, the commitment table's own layout), back to back
     const size_t half = cell_table_half_entries(cbits);
     CU_TRY(cudaMalloc(&cc->d_table, 2 * half * AFFINE_BYTES));
-    CU_TRY(cudaMalloc(&d_bases, (size_t)cc->nwin * N_POINTS * AFFINE_BYTES));
+    void* d_bases = tmp.get((size_t)cc->nwin * N_POINTS * AFFINE_BYTES);
+    if (!d_bases) return false;
     for (int v = 0; v < 2; v++) {
       launch_table_bases(d_bases, (const uint8_t*)d_aff + (size_t)v * N_POINTS * AFFINE_BYTES, cc->c, cc->nwin, N_POINTS, cc->st);
       launch_table_fill((uint8_t*)cc->d_table + (size_t)v * half * AFFINE_BYTES, d_bases, cc->c, cc->nwin, N_POINTS, table_top_count(cc->c), cc->st);
     }
     CU_TRY(cudaStreamSynchronize(cc->st));
     CU_TRY(cudaGetLastError());
-    cudaFree(d_pts);
-    cc->d_fk20 = d_aff;
-    cudaFree(d_bases);
+    cc->d_fk20 = tmp.keep(d_aff);
     return true;
   }();
   if (!good) {
@@ -459,7 +475,7 @@ C_KZG_RET cells_debug_stages(uint8_t* scalars, uint8_t* hhat48, uint8_t* h48, ui
   cudaStream_t st = cc->st;
   bool good = [&]() -> bool {
     if (!cell_reserve(cc, 1, true)) return false;
-    DevBuf tmp;
+    struct Tmp : DevBuf { ~Tmp() { release(); } } tmp;
     if (!tmp.ensure((size_t)EXT_POINTS * 48)) return false;
     CU_TRY(cudaMemcpyAsync(cc->blobs.p, blob, BLOB_BYTES, cudaMemcpyHostToDevice, st));
     launch_cell_poly(cc->coef.p, nullptr, cc->blobs.p, 1, c->mode, cc->d_tw, st);
@@ -479,7 +495,6 @@ C_KZG_RET cells_debug_stages(uint8_t* scalars, uint8_t* hhat48, uint8_t* h48, ui
     CU_TRY(cudaMemcpyAsync(fk20_xy96, tmp.p, (size_t)EXT_POINTS * 96, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
-    tmp.release();
     return true;
   }();
   return good ? C_KZG_OK : C_KZG_ERROR;
