@@ -333,3 +333,30 @@ def test_cells_in_library_multi_device_byte_equality():
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "multi_device_cells_check.py")], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "MULTI_DEVICE_CELLS_OK" in p.stdout
+
+
+def test_cells_are_linear_and_mode_independent(lw, s2, o2):
+    """Two properties that need neither the toxic waste nor the oracle's proof code: (1) proofs are linear in the blob
+    -- pi_i(a + b) = pi_i(a) + pi_i(b) as group elements, cells add field-wise; (2) the same polynomial given in
+    evaluation form (MODE_DENEB) and in coefficient form (MODE_REFERENCE) has the same cells and the same proofs."""
+    from oracle.py import bls
+
+    a = make_blob(51, 2)
+    b = make_blob(52, 2)
+    wa = [int.from_bytes(a[i: i + 32], "big") for i in range(0, B, 32)]
+    wb = [int.from_bytes(b[i: i + 32], "big") for i in range(0, B, 32)]
+    c = b"".join(((x + y) % R).to_bytes(32, "big") for x, y in zip(wa, wb))
+    (ca, pa), (cb, pb), (cc, pc) = (lw.compute_cells_and_kzg_proofs(x, s2) for x in (a, b, c))
+    for i in range(128):
+        ea = [int.from_bytes(ca[i][j: j + 32], "big") for j in range(0, 2048, 32)]
+        eb = [int.from_bytes(cb[i][j: j + 32], "big") for j in range(0, 2048, 32)]
+        assert cc[i] == b"".join(((x + y) % R).to_bytes(32, "big") for x, y in zip(ea, eb))
+        assert pc[i] == bls.g1_compress(bls.g1_add(bls.g1_decompress(pa[i]), bls.g1_decompress(pb[i]))), i
+    # coefficient form of a, through the reference-mode settings
+    coeffs = o2.blob_to_coeffs(a)
+    s0 = _load(lw, 0)
+    try:
+        c0, p0 = lw.compute_cells_and_kzg_proofs(b"".join(v.to_bytes(32, "big") for v in coeffs), s0)
+    finally:
+        s0.free()
+    assert c0 == ca and p0 == pa
