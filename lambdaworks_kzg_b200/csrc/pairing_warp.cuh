@@ -36,29 +36,39 @@ struct WarpScratch {
 // ---- phase 1 of dst = a * b: lane L < 18 prepares the operands of one Karatsuba product (1a), 54 lanes do one of
 // the 54 Fp multiplications behind the 18 Fp2 products each -- one multiplication deep instead of three (1b) -- and
 // lane L < 18 assembles its Fp2 product (1c)
+// v if keep, else 0 -- limb selects, no branch: the phases below must not diverge (a warp executes BOTH sides of every
+// branch its lanes disagree on, and each side is dozens of multi-limb additions on the critical path of every Fp12 product)
+LW_INL Fp2 fp2_keep_if(const Fp2& v, bool keep) {
+  Fp2 r;
+  for (int i = 0; i < 12; i++) { r.c0.l[i] = keep ? v.c0.l[i] : 0u; r.c1.l[i] = keep ? v.c1.l[i] : 0u; }
+  return r;
+}
+// Phase 1a, data-driven: Karatsuba product L = 6 k + m multiplies the sum of the coefficients x_i, i in sel(m), of
+// the c0 half (k = 0), of the c1 half (k = 1) or of both (k = 2): at most four terms.  Every lane runs the same code --
+// four loads (unused terms read slot 0 and are zeroed), a two-level sum, c0 + c1 -- and the A-side (lanes 0..17, from
+// a) and the B-side (lanes 32..49, from b) run on different warps instead of one after the other.
 LW_COLD void wfp12_mul_phase1a(WarpScratch& sc, const WarpFp12& a, const WarpFp12& b, int lane) {
-  if (lane >= 18) return;
-  const int k = lane / 6, m = lane % 6;
+  const int L = lane & 31, side = lane >> 5;
+  if (L >= 18 || side > 1) return;
+  const WarpFp12& src = side ? b : a;
+  const int k = L / 6, m = L % 6;
   const int sel = (m == 0) ? 1 : (m == 1) ? 2 : (m == 2) ? 4 : (m == 3) ? 6 : (m == 4) ? 3 : 5;  // subset of {x0,x1,x2}
-  // A, B = sums of the selected coefficients; the first term is copied, not added to zero (the additions are on
-  // the critical path of every Fp12 product)
-  Fp2 A = fp2_zero(), B = fp2_zero();
-  bool first = true;
-  for (int i = 0; i < 3; i++) {
-    if (!((sel >> i) & 1)) continue;
-    if (k == 0 || k == 2) {
-      if (first) { A = a.c[i]; B = b.c[i]; first = false; }
-      else { A = fp2_add(A, a.c[i]); B = fp2_add(B, b.c[i]); }
-    }
-    if (k == 1 || k == 2) {
-      if (first) { A = a.c[3 + i]; B = b.c[3 + i]; first = false; }
-      else { A = fp2_add(A, a.c[3 + i]); B = fp2_add(B, b.c[3 + i]); }
-    }
-  }
-  sc.opa[3 * lane] = A.c0;     sc.opb[3 * lane] = B.c0;
-  sc.opa[3 * lane + 1] = A.c1; sc.opb[3 * lane + 1] = B.c1;
-  sc.opa[3 * lane + 2] = fp_add(A.c0, A.c1);
-  sc.opb[3 * lane + 2] = fp_add(B.c0, B.c1);
+  const int i0 = (sel & 1) ? 0 : (sel & 2) ? 1 : 2;                    // lowest coefficient of the subset
+  const int i1 = (sel == 6) ? 2 : (sel == 3) ? 1 : (sel == 5) ? 2 : -1;  // the other one, if any
+  // term t: coefficient index or -1
+  const int t0 = (k == 1) ? 3 + i0 : i0;
+  const int t1 = (k == 2) ? 3 + i0 : -1;
+  const int t2 = (i1 < 0) ? -1 : (k == 1) ? 3 + i1 : i1;
+  const int t3 = (i1 < 0 || k != 2) ? -1 : 3 + i1;
+  const Fp2 x0 = src.c[t0];
+  const Fp2 x1 = fp2_keep_if(src.c[t1 < 0 ? 0 : t1], t1 >= 0);
+  const Fp2 x2 = fp2_keep_if(src.c[t2 < 0 ? 0 : t2], t2 >= 0);
+  const Fp2 x3 = fp2_keep_if(src.c[t3 < 0 ? 0 : t3], t3 >= 0);
+  const Fp2 X = fp2_add(fp2_add(x0, x1), fp2_add(x2, x3));
+  Fp* dst = side ? sc.opb : sc.opa;
+  dst[3 * L] = X.c0;
+  dst[3 * L + 1] = X.c1;
+  dst[3 * L + 2] = fp_add(X.c0, X.c1);
 }
 LW_COLD void wfp12_mul_phase1b(WarpScratch& sc, int lane) {
   for (int idx = lane; idx < 54; idx += LW_PAIR_LANES) {
@@ -75,18 +85,24 @@ LW_COLD void wfp12_mul_phase1c(WarpScratch& sc, int lane) {
   r.c1 = fp_sub(fp_sub(t2, t0), t1);
   sc.prod[lane] = r;
 }
-// coefficient i of the k-th Fp6 product from its six Karatsuba pieces
-LW_COLD Fp2 wfp6_coeff(const WarpScratch& sc, int k, int i) {
-  const Fp2* v = sc.prod + 6 * k;
-  if (i == 0) return fp2_add(v[0], fp2_mul_xi(fp2_sub(fp2_sub(v[3], v[1]), v[2])));
-  if (i == 1) return fp2_add(fp2_sub(fp2_sub(v[4], v[0]), v[1]), fp2_mul_xi(v[2]));
-  return fp2_add(fp2_sub(fp2_sub(v[5], v[0]), v[2]), v[1]);
-}
-// ---- phase 2a: lane L < 9 recombines coefficient L % 3 of Fp6 product L / 3 (nine lanes instead of each of the six
-// output lanes recomputing up to three of them)
+// ---- phase 2a: lane L < 9 recombines coefficient i = L % 3 of Fp6 product L / 3 from its six Karatsuba pieces v0..v5:
+//   i = 0: v0 + xi (v3 - v1 - v2)      i = 1: v4 - v0 - v1 + xi v2      i = 2: v5 + v1 - v0 - v2
+// written as ONE formula (P0 + P1) - (N0 + N1) + xi (Q - (M0 + M1)) with unused terms zeroed, so the nine lanes do not
+// diverge (three different return paths used to be executed one after the other)
 LW_COLD void wfp12_mul_phase2a(WarpScratch& sc, int lane) {
   if (lane >= 9) return;
-  sc.coef[lane] = wfp6_coeff(sc, lane / 3, lane % 3);
+  const int i = lane % 3;
+  const Fp2* v = sc.prod + 6 * (lane / 3);
+  const Fp2 P0 = v[i == 0 ? 0 : i == 1 ? 4 : 5];
+  const Fp2 P1 = fp2_keep_if(v[1], i == 2);
+  const Fp2 N0 = fp2_keep_if(v[0], i != 0);
+  const Fp2 N1 = fp2_keep_if(v[i == 1 ? 1 : 2], i != 0);
+  const Fp2 Q = fp2_keep_if(v[i == 0 ? 3 : 2], i != 2);
+  const Fp2 M0 = fp2_keep_if(v[1], i == 0);
+  const Fp2 M1 = fp2_keep_if(v[2], i == 0);
+  const Fp2 s1 = fp2_sub(fp2_add(P0, P1), fp2_add(N0, N1));
+  const Fp2 s2 = fp2_sub(Q, fp2_add(M0, M1));
+  sc.coef[lane] = fp2_add(s1, fp2_mul_xi(s2));
 }
 // ---- phase 2b: lane o < 6 writes output coefficient o
 LW_COLD void wfp12_mul_phase2b(WarpFp12& dst, const WarpScratch& sc, int lane) {
