@@ -403,10 +403,13 @@ def main():
         # ---- single-call latencies of the c-kzg entry points
         blob0 = bytes(blobs[:BLOB_BYTES].cpu().numpy().tobytes())
         c0, p0 = dev_coms[:48], dev_proofs[:48]
+        z5 = bytes(31) + b"\x05"
+        p5, y5 = lw.compute_kzg_proof(blob0, z5, settings)   # a true opening at z = 5: full-length scalars in the verification
+        assert lw.verify_kzg_proof(c0, z5, y5, p5, settings) is True
         calls = [("blob_to_kzg_commitment", lambda: lw.blob_to_kzg_commitment(blob0, settings)),
                  ("compute_kzg_proof", lambda: lw.compute_kzg_proof(blob0, bytes(31) + b"\x05", settings)),
                  ("compute_blob_kzg_proof", lambda: lw.compute_blob_kzg_proof(blob0, c0, settings)),
-                 ("verify_kzg_proof", lambda: lw.verify_kzg_proof(c0, bytes(32), blob0[:32], bytes([0xC0]) + bytes(47), settings)),
+                 ("verify_kzg_proof", lambda: lw.verify_kzg_proof(c0, z5, y5, p5, settings)),
                  ("verify_blob_kzg_proof", lambda: lw.verify_blob_kzg_proof(blob0, c0, p0, settings))]
         gpu_lat = {}
         for name, fn in calls:

@@ -68,7 +68,12 @@ __device__ __forceinline__ bool two_pairing_check(const G1Affine* pts, const G2P
 }
 
 // ok = [ e(C - y g1_0 + z pi, g2_0) * e(-pi, g2_1) == 1 ]
-__global__ void __launch_bounds__(LW_PAIR_LANES) verify_single_kernel(int* __restrict__ ok_out, const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
+// Block of VS_THREADS = 160: warps 0-1 are the pairing group (LW_PAIR_LANES); before that, lane 0 of each of the
+// warps 0..3 runs one of the four GLV half-ladders and lanes 0-1 of warp 4 the two r-torsion tests.  One ladder per
+// WARP, not four in one warp: the lanes of a warp execute every conditional addition any of them needs (94 % of the
+// bits for four random scalars instead of 50 %), so sharing a warp made each ladder cost 128 doublings + 120 additions.
+constexpr int VS_THREADS = 160;
+__global__ void __launch_bounds__(VS_THREADS) verify_single_kernel(int* __restrict__ ok_out, const G1Affine* __restrict__ c_aff, const G1Affine* __restrict__ pi_aff,
                                                             const uint32_t* __restrict__ z, const uint32_t* __restrict__ y,
                                                             const G1Affine* __restrict__ g1_0, const G2Prepared* __restrict__ prep0,
                                                             const G2Prepared* __restrict__ prep1, int g1_0_in_subgroup, int* __restrict__ status,
@@ -78,34 +83,35 @@ __global__ void __launch_bounds__(LW_PAIR_LANES) verify_single_kernel(int* __res
   __shared__ G1Affine sh_pair[2];
   const int lane = threadIdx.x;
   G1Affine C = *c_aff, PI = *pi_aff;
-  if (lane < 4) {
-    // four lanes share the two scalar multiplications: GLV halves k = q x^2 + m, [k]P = [m]P + [q](beta x, -y)
+  if (lane < 128 && (lane & 31) == 0) {
+    // four warps share the two scalar multiplications: GLV halves k = q x^2 + m, [k]P = [m]P + [q](beta x, -y)
     // (z and y are canonical, < r), 128 doublings each instead of 255
-    const int which = lane >> 1, half = lane & 1;
+    const int job = lane >> 5;
+    const int which = job >> 1, half = job & 1;
     uint32_t k[8], q[4], m[4];
     for (int i = 0; i < 8; i++) k[i] = which == 0 ? y[i] : z[i];
     glv_split(q, m, k);
     G1Affine base = which == 0 ? *g1_0 : PI;
-    // phi(P) = [-x^2]P holds on the r-torsion only: pi was subgroup-checked when decoded, a hand-built setup's
-    // g1[0] need not be (srs.rs:155-172 checks the curve equation only) -> plain 255-bit ladder on lane 0
+    // phi(P) = [-x^2]P holds on the r-torsion only: pi is subgroup-checked (when decoded, or beside this ladder), a
+    // hand-built setup's g1[0] need not be (srs.rs:155-172 checks the curve equation only) -> plain 255-bit ladder
     const bool glv = which == 1 || g1_0_in_subgroup != 0;
     if (!glv) {
-      sh_pt[lane] = half == 0 ? g1_mul_scalar(base, k, 8) : xyzz_inf();
+      sh_pt[job] = half == 0 ? g1_mul_scalar(base, k, 8) : xyzz_inf();
     } else {
-    if (half == 1 && !g1a_is_inf(base)) {
-      Fp beta;
-      for (int i = 0; i < 12; i++) beta.l[i] = k::FP_BETA[i];
-      base.x = fp_mul(base.x, beta);
-      base.y = fp_neg(base.y);
-    }
-    sh_pt[lane] = g1_mul_scalar(base, half == 0 ? m : q, 4);
+      if (half == 1 && !g1a_is_inf(base)) {
+        Fp beta;
+        for (int i = 0; i < 12; i++) beta.l[i] = k::FP_BETA[i];
+        base.x = fp_mul(base.x, beta);
+        base.y = fp_neg(base.y);
+      }
+      sh_pt[job] = g1_mul_scalar(base, half == 0 ? m : q, 4);
     }
   }
   // sub_code != 0: C and pi were decoded WITHOUT the r-torsion test (the larger part of a decompression); two lanes
-  // of the second warp run it here, beside the scalar multiplications of the first warp instead of in front of them.
+  // of the fifth warp run it here, beside the scalar multiplications instead of in front of them.
   // A failure is reported through status[0] and overrides whatever the pairing says.
-  if (sub_code != 0 && (lane == 32 || lane == 33)) {
-    if (!g1_in_subgroup(lane == 32 ? C : PI)) atomicCAS(status, 0, sub_code);
+  if (sub_code != 0 && (lane == 128 || lane == 129)) {
+    if (!g1_in_subgroup(lane == 128 ? C : PI)) atomicCAS(status, 0, sub_code);
   }
   __syncthreads();
   if (lane == 0) {
@@ -357,7 +363,7 @@ void launch_g2_check(int* d_bad, const void* d_canon_in, int n, cudaStream_t st)
 }
 void launch_verify_single(int* d_ok, const void* d_c_aff, const void* d_pi_aff, const void* d_z, const void* d_y, const void* d_g1_0_aff,
                           const void* d_prep0, const void* d_prep1, bool g1_0_in_subgroup, cudaStream_t st, int* d_status, int sub_code) {
-  verify_single_kernel<<<1, LW_PAIR_LANES, 0, st>>>(d_ok, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
+  verify_single_kernel<<<1, VS_THREADS, 0, st>>>(d_ok, (const G1Affine*)d_c_aff, (const G1Affine*)d_pi_aff, (const uint32_t*)d_z, (const uint32_t*)d_y,
                                          (const G1Affine*)d_g1_0_aff, (const G2Prepared*)d_prep0, (const G2Prepared*)d_prep1, g1_0_in_subgroup ? 1 : 0,
                                          d_status, d_status ? sub_code : 0);
   count_launch();

@@ -30,11 +30,14 @@ for rep in range(3):
 bad = list(proofs); bad[n // 2 - 1] = coms[0]
 t = time.perf_counter(); ok = lw.verify_blob_kzg_proof_batch(bl, coms, bad, s); dt = time.perf_counter() - t
 print("verify batch with proof #%d replaced -> %s: %.1f ms" % (n // 2 - 1, ok, dt * 1e3), flush=True)
+z5 = bytes(31) + b"\x05"
+p5, y5 = lw.compute_kzg_proof(bl[0], z5, s)
+assert lw.verify_kzg_proof(coms[0], z5, y5, p5, s) is True
 for name, fn in [("blob_to_kzg_commitment", lambda: lw.blob_to_kzg_commitment(bl[0], s)),
                  ("compute_blob_kzg_proof", lambda: lw.compute_blob_kzg_proof(bl[0], coms[0], s)),
                  ("compute_kzg_proof", lambda: lw.compute_kzg_proof(bl[0], bytes(31) + b"\x05", s)),
                  ("verify_blob_kzg_proof", lambda: lw.verify_blob_kzg_proof(bl[0], coms[0], proofs[0], s)),
-                 ("verify_kzg_proof", lambda: lw.verify_kzg_proof(coms[0], bytes(32), bl[0][:32], bytes([0xC0]) + bytes(47), s))]:
+                 ("verify_kzg_proof", lambda: lw.verify_kzg_proof(coms[0], z5, y5, p5, s))]:
     fn()
     t = time.perf_counter()
     for _ in range(5):
