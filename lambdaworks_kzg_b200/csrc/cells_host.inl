@@ -169,6 +169,7 @@ bool cell_enqueue_chunk(Ctx* c, const void* d_blobs, int m, void* d_cells, void*
   CU_TRY(cudaMemsetAsync(d_status, 0, (size_t)m * sizeof(int), cc->st));
   if (c->lagrange()) launch_le_blob_check(d_status, d_blobs, m, cc->st, c->be_wire());
   launch_cell_poly(cc->coef.p, d_cells, d_blobs, m, c->mode, cc->d_tw, cc->st);
+  CU_TRY(cudaEventRecord(cc->ev_v[0], cc->st));   // status and cells are final here; the proofs take 50x longer
   if (d_proofs) cell_enqueue_proofs(cc, d_proofs, m);
   return true;
 }
@@ -199,18 +200,23 @@ C_KZG_RET cells_host_batch_on(Ctx* c, size_t n, const Blob* blobs, Cell* cells_o
     bool good = [&]() -> bool {
       CU_TRY(cudaMemcpyAsync(cc->blobs.p, blobs + off, m * BLOB_BYTES, cudaMemcpyHostToDevice, cc->st));
       if (!cell_enqueue_chunk(c, cc->blobs.p, (int)m, cells_out ? cc->cells.p : nullptr, proofs_out ? cc->proofs.p : nullptr, (int*)cc->status.p)) return false;
-      // the status array is complete after the first kernels of the pass; it decides where the results are copied:
+      // The status array and the cells are complete after the first two kernels of the pass (~2 ms); the proofs
+      // follow ~80 ms later.  A side stream fetches the status as soon as it exists -- it decides where the results go:
       // straight into the caller's memory when every item is good (the usual case: no staging copy of 256 KiB per
-      // blob on the host), through the pinned staging area when a failed item's slot must stay untouched
-      CU_TRY(cudaMemcpyAsync(h_status, cc->status.p, m * sizeof(int), cudaMemcpyDeviceToHost, cc->st));
-      CU_TRY(cudaStreamSynchronize(cc->st));
+      // blob on the host), through the pinned staging area when a failed item's slot must stay untouched -- and
+      // then copies the cells while the proof kernels run.
+      cudaStream_t side = c->slot[2].st;
+      CU_TRY(cudaStreamWaitEvent(side, cc->ev_v[0], 0));
+      CU_TRY(cudaMemcpyAsync(h_status, cc->status.p, m * sizeof(int), cudaMemcpyDeviceToHost, side));
+      CU_TRY(cudaStreamSynchronize(side));
       clean = true;
       for (size_t i = 0; i < m; i++) clean = clean && h_status[i] == 0;
       uint8_t* dst_cells = (clean && cells_out) ? (uint8_t*)(cells_out + off * N_CELLS) : h_cells;
       uint8_t* dst_proofs = (clean && proofs_out) ? (uint8_t*)(proofs_out + off * N_CELLS) : h_proofs;
-      if (cells_out) CU_TRY(cudaMemcpyAsync(dst_cells, cc->cells.p, m * N_CELLS * CELL_BYTES, cudaMemcpyDeviceToHost, cc->st));
+      if (cells_out) CU_TRY(cudaMemcpyAsync(dst_cells, cc->cells.p, m * N_CELLS * CELL_BYTES, cudaMemcpyDeviceToHost, side));
       if (proofs_out) CU_TRY(cudaMemcpyAsync(dst_proofs, cc->proofs.p, m * N_CELLS * 48, cudaMemcpyDeviceToHost, cc->st));
       CU_TRY(cudaStreamSynchronize(cc->st));
+      CU_TRY(cudaStreamSynchronize(side));
       CU_TRY(cudaGetLastError());
       return true;
     }();
