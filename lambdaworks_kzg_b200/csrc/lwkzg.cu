@@ -1487,7 +1487,7 @@ struct CtxLock {
 extern "C" {
 
 const char* lwkzg_last_error(void) { return tl_err.c_str(); }
-const char* lwkzg_version(void) { return "lwkzg-b200 0.1 (sm_100a)"; }
+const char* lwkzg_version(void) { return "lwkzg-b200 0.2 (sm_100a)"; }
 uint64_t lwkzg_kernel_launches(void) { return lw::launches(); }
 
 int lwkzg_set_option(const char* name, long value) {
