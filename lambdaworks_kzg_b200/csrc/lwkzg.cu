@@ -55,7 +55,7 @@ struct Options {
   long msm_blocks_per_blob = 0;
   long chunk_blobs = 256;
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
-  long msm_ba_min_blobs = 256;
+  long msm_ba_min_blobs = 32;        // measured (tools/batch_size_sweep.py): the batched-affine kernel wins from 32 blobs up (64 blobs: 9.0 vs 12.1 ms)
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
   long verify_overlap_decode = 1;    // batched verification: blob hashes start beside the point decompression (possible since the decompression
