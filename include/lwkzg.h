@@ -303,7 +303,7 @@ int lwkzg_table_share(const KZGSettings *s);
  * automatically to what free device memory allows -- lwkzg_window_bits() tells; must
  * be set before the settings are first used), "msm_blocks_per_blob" (0 = auto),
  * "chunk_blobs" (host-batch pipeline chunk, default 256; 4 chunks in flight),
- * "msm_algo" (1 = default: batches of at least "msm_ba_min_blobs" (32) blobs use
+ * "msm_algo" (1 = default: batches of at least "msm_ba_min_blobs" (5) blobs use
  * the batched-affine MSM kernel, smaller ones the XYZZ kernel; 0 = XYZZ only;
  * both give identical bytes), "msm_ba_variant" (tuning: accumulators per thread
  * x threads per blob, see csrc/msm.cu), "verify_super_blobs" (blobs of a batched

@@ -51,10 +51,11 @@ unsigned long long table_entries(int c, int npoints);
 // partials: n * blocks_per_blob XYZZ accumulators.
 void launch_msm_gather(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input,
                        int n_blobs, int blocks_per_blob, cudaStream_t st);
-// batched-affine variant for large batches: one block per blob, one XYZZ partial per blob, plus a scratch area
-// for the per-thread affine accumulators
+// batched-affine variant: `split` blocks per blob (1 for large batches; 2, 4, 8 when the batch alone would not fill the
+// GPU: each block takes 1 / split of every thread's points), n_blobs * split XYZZ partials, plus a scratch area for the
+// per-thread affine accumulators (msm_ba_scratch_bytes(n_blobs * split))
 void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input,
-                          int n_blobs, void* d_scratch, cudaStream_t st);
+                          int n_blobs, void* d_scratch, cudaStream_t st, int split = 1);
 size_t msm_ba_scratch_bytes(int n_blobs);
 int msm_ba_threads();
 int msm_ba_slots();

@@ -55,7 +55,8 @@ struct Options {
   long msm_blocks_per_blob = 0;
   long chunk_blobs = 256;
   long msm_algo = 1;         // 0 = XYZZ accumulation only, 1 = batched-affine accumulation for large batches
-  long msm_ba_min_blobs = 32;        // measured (tools/batch_size_sweep.py): the batched-affine kernel wins from 32 blobs up (64 blobs: 9.0 vs 12.1 ms)
+  long msm_ba_min_blobs = 5;         // measured (tools/batch_size_sweep.py): with blobs split over up to 8 blocks the batched-affine kernel wins from
+                                     // five blobs up (4 blobs: 3.10 vs 2.78 ms, 6: 3.12 vs 3.83, 32: 3.9 vs 10.9, 64: 5.0 vs 12.1)
   long verify_super_blobs = 16384;   // blobs of a batched verification staged on the device at a time (2 GiB)
   long lincomb_points_in_g1 = 0;     // lwkzg_g1_lincomb: the caller vouches that every point is in the r-torsion (GLV split allowed)
   long verify_overlap_decode = 1;    // batched verification: blob hashes start beside the point decompression (possible since the decompression
@@ -711,8 +712,27 @@ bool use_batch_affine(int n) {
 // the total block work of its MSMs, not by the order they are issued in.
 size_t chunk_at(size_t off, size_t n, size_t chunk) { return std::min(chunk, n - off); }
 
+// blocks resident at once for the batched-affine kernel (3 per SM)
+int ba_block_slots() {
+  static int slots[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 444;
+  if (!slots[dev]) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    slots[dev] = 3 * sms;
+  }
+  return slots[dev];
+}
+
 int auto_bpb(int n) {
-  if (use_batch_affine(n)) return 1;
+  if (use_batch_affine(n)) {
+    // a batch that would leave block slots empty is split further: 2, 4 or 8 blocks per blob, each taking a share
+    // of every thread's points (a block's fold of its 64 accumulators per thread is the price: not beyond 8)
+    int split = 1;
+    while (split < 8 && n * split * 2 <= ba_block_slots()) split *= 2;
+    return split;
+  }
   long o;
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -728,7 +748,7 @@ int auto_bpb(int n) {
 void run_msm(Slot& s, const Ctx* c, const void* d_scalars, bool be_input, int n, int bpb, cudaStream_t st);
 
 bool slot_reserve(Slot& s, int n, int bpb, bool need_blobs) {
-  if (use_batch_affine(n) && !s.ba_scratch.ensure(msm_ba_scratch_bytes(n))) return false;
+  if (use_batch_affine(n) && !s.ba_scratch.ensure(msm_ba_scratch_bytes(n * bpb))) return false;
   if (need_blobs && !s.blobs.ensure((size_t)n * BLOB_BYTES)) return false;
   return s.q.ensure((size_t)n * BLOB_BYTES) && s.partials.ensure((size_t)n * bpb * XYZZ_BYTES) && s.states.ensure((size_t)n * 32) &&
          s.z.ensure((size_t)n * 32) && s.y.ensure((size_t)n * 32) && s.ybe.ensure((size_t)n * 32) && s.c48.ensure((size_t)n * 48) &&
@@ -739,7 +759,7 @@ bool slot_reserve(Slot& s, int n, int bpb, bool need_blobs) {
 // true when slot_reserve(s, n, bpb, need_blobs) would not have to reallocate anything
 bool slot_fits(const Slot& s, int n, int bpb, bool need_blobs) {
   const size_t m = (size_t)n;
-  if (use_batch_affine(n) && s.ba_scratch.cap < msm_ba_scratch_bytes(n)) return false;
+  if (use_batch_affine(n) && s.ba_scratch.cap < msm_ba_scratch_bytes(n * bpb)) return false;
   if (need_blobs && s.blobs.cap < m * BLOB_BYTES) return false;
   return s.q.cap >= m * BLOB_BYTES && s.partials.cap >= m * bpb * XYZZ_BYTES && s.states.cap >= m * 32 && s.z.cap >= m * 32 &&
          s.y.cap >= m * 32 && s.ybe.cap >= m * 32 && s.c48.cap >= m * 48 && s.cin48.cap >= m * 48 && s.p48.cap >= m * 48 &&
@@ -747,8 +767,8 @@ bool slot_fits(const Slot& s, int n, int bpb, bool need_blobs) {
 }
 
 void run_msm(Slot& s, const Ctx* c, const void* d_scalars, bool be_input, int n, int bpb, cudaStream_t st) {
-  if (bpb == 1 && use_batch_affine(n) && s.ba_scratch.cap >= msm_ba_scratch_bytes(n))
-    launch_msm_gather_ba(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, s.ba_scratch.p, st);
+  if (bpb <= 8 && use_batch_affine(n) && s.ba_scratch.cap >= msm_ba_scratch_bytes(n * bpb))
+    launch_msm_gather_ba(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, s.ba_scratch.p, st, bpb);
   else
     launch_msm_gather(s.partials.p, c->d_table, c->c, d_scalars, be_input, n, bpb, st);
 }
@@ -1984,9 +2004,13 @@ double lwkzg_bench_msm_kernel(const void* d_blobs, size_t n, int blocks_per_blob
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  run_msm(sl, c, d_blobs, true, (int)n, bpb, sl.st);  // warm-up
+  auto run = [&]() {
+    if (blocks_per_blob > 0) launch_msm_gather(sl.partials.p, c->d_table, c->c, d_blobs, true, (int)n, bpb, sl.st);   // explicit: the XYZZ kernel
+    else run_msm(sl, c, d_blobs, true, (int)n, bpb, sl.st);
+  };
+  run();  // warm-up
   cudaEventRecord(e0, sl.st);
-  for (int i = 0; i < iters; i++) run_msm(sl, c, d_blobs, true, (int)n, bpb, sl.st);
+  for (int i = 0; i < iters; i++) run();
   cudaEventRecord(e1, sl.st);
   cudaEventSynchronize(e1);
   float ms = 0;

@@ -75,7 +75,7 @@ msm_gather_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table
 void launch_msm_gather(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
                        int blocks_per_blob, cudaStream_t st);
 // defined in msm_ba_v*.cu (one translation unit per variant)
-#define LW_BA_DECL(N) void launch_ba_v##N(void*, const void*, int, const void*, bool, int, void*, cudaStream_t)
+#define LW_BA_DECL(N) void launch_ba_v##N(void*, const void*, int, const void*, bool, int, void*, cudaStream_t, int)
 LW_BA_DECL(0); LW_BA_DECL(1);
 struct BaVariant { int k, threads; };
 static const BaVariant BA_VARIANTS[] = {{64, 128}, {64, 64}};   // keep in step with msm_ba_v*.cu
@@ -91,15 +91,15 @@ size_t msm_ba_scratch_bytes(int n_blobs) {   // sized for the largest variant: 6
 
 // one block per blob (blobs on grid.x: no 65535 limit); partials: one XYZZ per blob
 void launch_msm_gather_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
-                          void* d_scratch, cudaStream_t st) {
+                          void* d_scratch, cudaStream_t st, int split) {
   if (n_blobs <= 0) return;
   if (glv_num_windows(c) > BA_VARIANTS[g_ba_variant].k) {   // tiny windows: a round could not hold one point's digits
-    launch_msm_gather(d_partials, d_table, c, d_scalars, be_input, n_blobs, 1, st);
+    launch_msm_gather(d_partials, d_table, c, d_scalars, be_input, n_blobs, split, st);
     return;
   }
   switch (g_ba_variant) {
-    case 1: launch_ba_v1(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
-    default: launch_ba_v0(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st); break;
+    case 1: launch_ba_v1(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st, split); break;
+    default: launch_ba_v0(d_partials, d_table, c, d_scalars, be_input, n_blobs, d_scratch, st, split); break;
   }
   count_launch();
 }

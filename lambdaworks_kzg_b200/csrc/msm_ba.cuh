@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t ba_entry_of(uint32_t code, int c, int nwin, 
 
 template <bool BE, int K, int TH, bool PF>
 __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
-                                                   uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride) {
+                                                   uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride, int split) {
   static_assert(K <= 64, "slot masks are 64 bits wide");
   static_assert(48 * (TH / 2) * 4 <= BA_STAGE_WORDS * TH * 16, "the block-reduction scratch aliases the staging area");
   constexpr int HT = TH / 2;              // threads per GLV half
@@ -129,16 +129,19 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
 
   const int tid = threadIdx.x;
   const int half = tid / HT, hl = tid % HT;
-  const int blob = blockIdx.x;
+  // split > 1 (small batches): `split` blocks share a blob, block `part` takes the points p in [part, part + 1) * NPT / split
+  // of every thread's residue class and writes its own partial sum; the finalize kernel adds them
+  const int blob = blockIdx.x / split, part = blockIdx.x % split;
+  const int npt = NPT / split, p_begin = part * npt;
   const uint8_t* sc = scalars + (size_t)blob * BLOB_BYTES;
   auto limb = [&](int w) { return sk[w][tid]; };
   // slot k: words 0-2 = A.x, 3-5 = A.y, 6-8 = exclusive prefix product
-  uint4* my = scratch + (size_t)blob * (K * 9 * TH) + tid;
+  uint4* my = scratch + (size_t)blockIdx.x * (K * 9 * TH) + tid;
 
   // A round consumes the 2^c-ary digits of PPR points: slot p * nwin + j <-> (point p of the round, window j).
   // Zero digits (probability 2^-c for uniform scalars) leave their slot idle for the round.
   const int PPR = K / nwin;
-  const int rounds = (NPT + PPR - 1) / PPR;
+  const int rounds = (npt + PPR - 1) / PPR;
   uint64_t infmask = K >= 64 ? ~0ull : ((1ull << K) - 1ull);   // accumulators at infinity
   for (int k = PPR * nwin; k < K; k++) sdig[k][tid] = 0;
 
@@ -170,11 +173,11 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
 
 #pragma unroll 1
   for (int rnd = 0; rnd < rounds; rnd++) {
-    const int pi0 = hl + HT * rnd * PPR;   // point of slot group p: pi0 + HT * p
+    const int pi0 = hl + HT * (p_begin + rnd * PPR);   // point of slot group p: pi0 + HT * p
     // ------------------------------------------------------------ pass 1a: digits of the round's points
 #pragma unroll 1
     for (int p = 0; p < PPR; p++) {
-      const bool have = rnd * PPR + p < NPT;
+      const bool have = rnd * PPR + p < npt;
       const int pi = pi0 + HT * p;
       if (have) {
         uint32_t h4[4];
@@ -352,7 +355,7 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
     return;
   }
   block_reduce_xyzz_glv<TH>(acc, red);
-  if (tid == 0) partials[blob] = acc;
+  if (tid == 0) partials[blockIdx.x] = acc;
 }
 
 // Two ways to fix the register budget: MINB > 0 -> __launch_bounds__(TH, MINB) (ptxas picks the count),
@@ -360,25 +363,25 @@ __device__ __forceinline__ void msm_gather_ba_body(G1Xyzz* __restrict__ partials
 template <bool BE, int K, int MINB, int TH, bool PF>
 __global__ void __launch_bounds__(TH, MINB)
 msm_gather_ba_kernel(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
-                     uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride) {
-  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top, seg_stride);
+                     uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride, int split) {
+  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top, seg_stride, split);
 }
 template <bool BE, int K, int REGS, int TH, bool PF>
 __global__ void __maxnreg__(REGS)
 msm_gather_ba_kernel_r(G1Xyzz* __restrict__ partials, const uint4* __restrict__ table, const uint8_t* __restrict__ scalars,
-                       uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride) {
-  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top, seg_stride);
+                       uint4* __restrict__ scratch, int c, int nwin, uint32_t cnt_top, int seg_stride, int split) {
+  msm_gather_ba_body<BE, K, TH, PF>(partials, table, scalars, scratch, c, nwin, cnt_top, seg_stride, split);
 }
 
 template <int K, int MINB, int TH>
 static void launch_ba(void* d_partials, const void* d_table, int c, const void* d_scalars, bool be_input, int n_blobs,
-                      void* d_scratch, cudaStream_t st, int seg_stride = 0) {
+                      void* d_scratch, cudaStream_t st, int seg_stride = 0, int split = 1) {
   const int nwin = glv_num_windows(c);
   const uint32_t cnt_top = glv_top_max(c) + 1u;
   constexpr size_t smem = ba_smem_bytes<K, TH>();
   static bool attr_set = false;
-  void (*kbe)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t, int);
-  void (*kle)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t, int);
+  void (*kbe)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t, int, int);
+  void (*kle)(G1Xyzz*, const uint4*, const uint8_t*, uint4*, int, int, uint32_t, int, int);
   if constexpr (MINB > 0) {
     kbe = msm_gather_ba_kernel<true, K, MINB, TH, LWKZG_BA_PREFETCH>;
     kle = msm_gather_ba_kernel<false, K, MINB, TH, LWKZG_BA_PREFETCH>;
@@ -394,9 +397,9 @@ static void launch_ba(void* d_partials, const void* d_table, int c, const void* 
     attr_set = true;
   }
   if (be_input)
-    kbe<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top, seg_stride);
+    kbe<<<n_blobs * split, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top, seg_stride, split);
   else
-    kle<<<n_blobs, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top, seg_stride);
+    kle<<<n_blobs * split, TH, smem, st>>>((G1Xyzz*)d_partials, (const uint4*)d_table, (const uint8_t*)d_scalars, (uint4*)d_scratch, c, nwin, cnt_top, seg_stride, split);
 }
 
 }  // namespace lw

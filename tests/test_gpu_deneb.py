@@ -134,7 +134,7 @@ def test_batch_api_large_batch_both_msm_kernels(lw, dn_settings, dn):
     try:
         c1, p1, st1 = lw.commit_and_prove_batch(blobs, n, dn_settings)
     finally:
-        lw.set_option("msm_ba_min_blobs", 32)
+        lw.set_option("msm_ba_min_blobs", 5)
     lw.set_option("msm_algo", 0)
     try:
         c0, p0, st0 = lw.commit_and_prove_batch(blobs, n, dn_settings)

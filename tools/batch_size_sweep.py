@@ -14,7 +14,7 @@ lw.synth_blobs_device(d_blobs.data_ptr(), 0, N, st)
 d_c = torch.zeros(N * 48, dtype=torch.uint8, device=dev)
 d_p = torch.zeros(N * 48, dtype=torch.uint8, device=dev)
 d_st = torch.zeros(N, dtype=torch.int32, device=dev)
-for n in (1, 8, 32, 64, 128, 192, 256, 384, 512, 1024, 2048):
+for n in (1, 2, 3, 4, 6, 8, 16, 32, 64, 128, 192, 256, 384, 512, 1024, 2048):
     row = []
     for ba_min in (1, 1 << 20):
         lw.set_option("msm_ba_min_blobs", ba_min)
@@ -31,4 +31,4 @@ for n in (1, 8, 32, 64, 128, 192, 256, 384, 512, 1024, 2048):
         ms = e0.elapsed_time(e1) / reps
         row.append((ms, n / ms * 1e3))
     print("n=%4d  batched-affine: %7.2f ms %7.0f blobs/s   XYZZ: %7.2f ms %7.0f blobs/s" % (n, row[0][0], row[0][1], row[1][0], row[1][1]), flush=True)
-lw.set_option("msm_ba_min_blobs", 32)
+lw.set_option("msm_ba_min_blobs", 5)

@@ -22,7 +22,7 @@ for mode in (0, 1):
         coms2, proofs2, st2 = lw.commit_and_prove_batch(b"".join(blobs) + bytes(131072) + (bytes(31) + b"\x01") * 4096, n + 2, s)
         assert st2 == [0] * (n + 2) and coms2[:n] == coms and proofs2[:n] == proofs
     lw.set_option("msm_ba_variant", 0)
-    lw.set_option("msm_ba_min_blobs", 32)
+    lw.set_option("msm_ba_min_blobs", 5)
     assert lw.verify_blob_kzg_proof_batch(blobs, coms, proofs, s) is True
     assert lw.verify_blob_kzg_proof(blobs[0], coms[0], proofs[0], s) is True
     z = bytes(31) + b"\x07" if mode == 0 else b"\x07" + bytes(31)
